@@ -1,0 +1,323 @@
+// Per-timestep attention kernels (HBM-bound): one CTA per sample streams that sample's
+// annotation tile a[b] (R x 512 bf16, 200 KB) through a ring of shared-memory stages with
+// TMA bulk copies, and serves every stream (fake / real / interpolate / tangent) that
+// shares the tile from the one read.
+//
+//   attn_fwd : alpha = softmax(e) over R (gen:16) ; z = sum_r alpha_r a_r (gen:17)
+//   attn_tan : JVP of the same (interp stream of the WGAN-GP tangent pass)
+//   attn_rev : alpha_bar_r = <z_bar, a_r>, softmax reverse (first order, or reverse over
+//              primal+tangent for the interp stream), P_bar accumulation.
+// e = P + c W_h itself (gen:14-15 in split form) is produced by the tcgen05 GEMM.
+#include "common.cuh"
+#include "../../include/sgg_b200.h"
+
+namespace sgg {
+
+constexpr int AT_C = 512;           // channels (gen:68)
+constexpr int AT_THREADS = 256;
+constexpr int AT_CHUNK_ROWS = 28;   // 196 = 7 * 28
+constexpr int AT_STAGES = 3;
+constexpr int AT_RMAX = 256;
+constexpr int AT_MAXV = 4;
+constexpr int AT_STAGE_BYTES = AT_CHUNK_ROWS * AT_C * 2;  // 28 KB
+
+struct AttnSmem {
+  __align__(128) uint8_t stage[AT_STAGES][AT_STAGE_BYTES];
+  __align__(16) float w[AT_RMAX][AT_MAXV];   // fwd: weights per region and stream; rev: alpha_bar
+  __align__(16) float eb[AT_MAXV][AT_RMAX];  // rev: e_bar per stream
+  __align__(8) uint64_t full[AT_STAGES];
+};
+
+__device__ __forceinline__ void attn_issue_chunk(AttnSmem& sm, const __nv_bfloat16* a_b, int chunk, int R) {
+  const int r0 = chunk * AT_CHUNK_ROWS;
+  const int rows = min(AT_CHUNK_ROWS, R - r0);
+  const int st = chunk % AT_STAGES;
+  const uint32_t bytes = rows * AT_C * 2;
+  mbar_expect_tx(&sm.full[st], bytes);
+  bulk_load_1d(sm.stage[st], a_b + (size_t)r0 * AT_C, bytes, &sm.full[st]);
+}
+
+// ------------------------------------------------------------------------------------ fwd
+struct AttnFwdParams {
+  const __nv_bfloat16* a;  // [B,R,C]
+  int B, R, nv;
+  int row_blk[AT_MAXV];    // stream v uses rows row_blk[v]*B + b of E/alpha/X
+  // mode 0 (softmax): E -> alpha ; mode 1 (tangent): alpha (saved) + edot -> adot
+  const float* E; long long ldE;      // scores (mode 0) or edot (mode 1)
+  const float* alpha_in;              // mode 1: saved alpha (same row indexing / ld as alpha_out)
+  float* alpha_out; long long ldA;    // alpha (mode 0) or adot (mode 1)
+  __nv_bfloat16* X; long long ldX; long long lo_off;  // z written at X[row, 0:C] (hi) and +lo_off (lo)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = p.R;
+  const int nchunks = (R + AT_CHUNK_ROWS - 1) / AT_CHUNK_ROWS;
+  const __nv_bfloat16* a_b = p.a + (size_t)b * R * AT_C;
+  if (tid == 0) {
+    for (int s = 0; s < AT_STAGES; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+    for (int c = 0; c < min(AT_STAGES, nchunks); ++c) attn_issue_chunk(sm, a_b, c, R);
+  }
+  // ---- per-stream weights (softmax or its tangent), one warp per stream
+  if (warp < p.nv) {
+    const long long row = (long long)p.row_blk[warp] * p.B + b;
+    const float* e = p.E + row * p.ldE;
+    float v[AT_RMAX / 32];
+    if (MODE == 0) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        const int r = lane + 32 * i;
+        v[i] = (r < R) ? e[r] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+      mx = warp_max(mx);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        v[i] = (lane + 32 * i < R) ? __expf(v[i] - mx) : 0.f;
+        s += v[i];
+      }
+      s = warp_sum(s);
+      const float inv = 1.0f / s;
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) v[i] *= inv;
+    } else {
+      const float* al = p.alpha_in + row * p.ldA;
+      float m = 0.f;
+      float ed[AT_RMAX / 32];
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        const int r = lane + 32 * i;
+        v[i] = (r < R) ? al[r] : 0.f;
+        ed[i] = (r < R) ? e[r] : 0.f;
+        m += v[i] * ed[i];
+      }
+      m = warp_sum(m);
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) v[i] = v[i] * (ed[i] - m);
+    }
+    float* ao = p.alpha_out + row * p.ldA;
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) {
+      const int r = lane + 32 * i;
+      if (r < R) {
+        ao[r] = v[i];
+        sm.w[r][warp] = v[i];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- z_v = sum_r w_v[r] a[r,:] ; thread owns channels 2*tid, 2*tid+1
+  float acc[AT_MAXV][2];
+#pragma unroll
+  for (int v = 0; v < AT_MAXV; ++v) acc[v][0] = acc[v][1] = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % AT_STAGES;
+    mbar_wait(&sm.full[st], (c / AT_STAGES) & 1);
+    const int r0 = c * AT_CHUNK_ROWS;
+    const int rows = min(AT_CHUNK_ROWS, R - r0);
+    const uint32_t* tile = reinterpret_cast<const uint32_t*>(sm.stage[st]);
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+      const uint32_t pk = tile[r * (AT_C / 2) + tid];
+      const float a0 = bf16lo_to_f32(pk), a1 = bf16hi_to_f32(pk);
+      const float4 w = *reinterpret_cast<const float4*>(sm.w[r0 + r]);
+      acc[0][0] = fmaf(w.x, a0, acc[0][0]); acc[0][1] = fmaf(w.x, a1, acc[0][1]);
+      acc[1][0] = fmaf(w.y, a0, acc[1][0]); acc[1][1] = fmaf(w.y, a1, acc[1][1]);
+      acc[2][0] = fmaf(w.z, a0, acc[2][0]); acc[2][1] = fmaf(w.z, a1, acc[2][1]);
+      acc[3][0] = fmaf(w.w, a0, acc[3][0]); acc[3][1] = fmaf(w.w, a1, acc[3][1]);
+    }
+    __syncthreads();
+    if (tid == 0 && c + AT_STAGES < nchunks) attn_issue_chunk(sm, a_b, c + AT_STAGES, R);
+  }
+#pragma unroll
+  for (int v = 0; v < AT_MAXV; ++v) {
+    if (v < p.nv) {
+      const long long row = (long long)p.row_blk[v] * p.B + b;
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(acc[v][0], h0, l0);
+      split_bf16(acc[v][1], h1, l1);
+      uint32_t* xh = reinterpret_cast<uint32_t*>(p.X + row * p.ldX);
+      uint32_t* xl = reinterpret_cast<uint32_t*>(p.X + row * p.ldX + p.lo_off);
+      xh[tid] = pack_bf16x2(h0, h1);
+      xl[tid] = pack_bf16x2(l0, l1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ rev
+struct AttnRevParams {
+  const __nv_bfloat16* a;
+  int B, R;
+  int nv;                   // number of z_bar vectors (primal streams [+ 1 tangent adjoint, last])
+  int tan_stream;           // index v of the stream that carries the tangent, or -1
+  int row_blk[AT_MAXV];     // row block of each vector in XB / alpha / EB
+  const float* XB; long long ldXB;        // z_bar = XB[row, 0:C]
+  const float* alpha; long long ldA;      // saved alpha
+  const float* edot;                      // [B, ldA] tangent of e for tan_stream (row b)
+  __nv_bfloat16* EB; long long ldEB; long long lo_off;  // e_bar hi/lo out (pad columns untouched)
+  float* Pbar; long long ldP;             // [B,R] += sum over primal streams of e_bar (may be null)
+};
+
+__global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = p.R;
+  const int nchunks = (R + AT_CHUNK_ROWS - 1) / AT_CHUNK_ROWS;
+  const __nv_bfloat16* a_b = p.a + (size_t)b * R * AT_C;
+  if (tid == 0) {
+    for (int s = 0; s < AT_STAGES; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+    for (int c = 0; c < min(AT_STAGES, nchunks); ++c) attn_issue_chunk(sm, a_b, c, R);
+  }
+  // z_bar slices: lane owns channels [lane*8, +8) and [256 + lane*8, +8)
+  float zb[AT_MAXV][16];
+#pragma unroll
+  for (int v = 0; v < AT_MAXV; ++v) {
+    if (v < p.nv) {
+      const float* z = p.XB + ((long long)p.row_blk[v] * p.B + b) * p.ldXB;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 q0 = *reinterpret_cast<const float4*>(z + h * 256 + lane * 8);
+        const float4 q1 = *reinterpret_cast<const float4*>(z + h * 256 + lane * 8 + 4);
+        zb[v][h * 8 + 0] = q0.x; zb[v][h * 8 + 1] = q0.y; zb[v][h * 8 + 2] = q0.z; zb[v][h * 8 + 3] = q0.w;
+        zb[v][h * 8 + 4] = q1.x; zb[v][h * 8 + 5] = q1.y; zb[v][h * 8 + 6] = q1.z; zb[v][h * 8 + 7] = q1.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) zb[v][j] = 0.f;
+    }
+  }
+  __syncthreads();  // barrier init visible before anyone waits
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % AT_STAGES;
+    mbar_wait(&sm.full[st], (c / AT_STAGES) & 1);
+    const int r0 = c * AT_CHUNK_ROWS;
+    const int rows = min(AT_CHUNK_ROWS, R - r0);
+    for (int r = warp; r < rows; r += AT_THREADS / 32) {
+      const uint4* rowp = reinterpret_cast<const uint4*>(sm.stage[st] + (size_t)r * AT_C * 2);
+      float d[AT_MAXV] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 pk = rowp[h * 32 + lane];
+        const uint32_t w4[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a0 = bf16lo_to_f32(w4[e]), a1 = bf16hi_to_f32(w4[e]);
+#pragma unroll
+          for (int v = 0; v < AT_MAXV; ++v) {
+            d[v] = fmaf(a0, zb[v][h * 8 + 2 * e], d[v]);
+            d[v] = fmaf(a1, zb[v][h * 8 + 2 * e + 1], d[v]);
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < AT_MAXV; ++v) d[v] = warp_sum(d[v]);
+      if (lane == 0) *reinterpret_cast<float4*>(sm.w[r0 + r]) = make_float4(d[0], d[1], d[2], d[3]);
+    }
+    __syncthreads();
+    if (tid == 0 && c + AT_STAGES < nchunks) attn_issue_chunk(sm, a_b, c + AT_STAGES, R);
+  }
+  // ---- softmax reverse: one warp per primal stream
+  const int ns = (p.tan_stream >= 0) ? p.nv - 1 : p.nv;
+  if (warp < ns) {
+    const int v = warp;
+    const long long row = (long long)p.row_blk[v] * p.B + b;
+    const float* al = p.alpha + row * p.ldA;
+    const bool tan = (v == p.tan_stream);
+    float alv[AT_RMAX / 32], ab[AT_RMAX / 32], adb[AT_RMAX / 32], ed[AT_RMAX / 32];
+    float m_t = 0.f, m_e = 0.f;
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) {
+      const int r = lane + 32 * i;
+      const bool ok = r < R;
+      alv[i] = ok ? al[r] : 0.f;
+      ab[i] = ok ? sm.w[r][v] : 0.f;
+      adb[i] = (ok && tan) ? sm.w[r][p.nv - 1] : 0.f;
+      ed[i] = (ok && tan) ? p.edot[(long long)b * p.ldA + r] : 0.f;
+      m_t += alv[i] * adb[i];
+      m_e += alv[i] * ed[i];
+    }
+    float s = 0.f;
+    if (tan) {
+      m_t = warp_sum(m_t);
+      m_e = warp_sum(m_e);
+    }
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) {
+      if (tan) ab[i] = ab[i] + adb[i] * (ed[i] - m_e) - ed[i] * m_t;  // w = abar + second-order terms
+      s += alv[i] * ab[i];
+    }
+    s = warp_sum(s);
+    __nv_bfloat16* ebh = p.EB + row * p.ldEB;
+    __nv_bfloat16* tbh = tan ? p.EB + ((long long)p.row_blk[p.nv - 1] * p.B + b) * p.ldEB : nullptr;
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) {
+      const int r = lane + 32 * i;
+      if (r < R) {
+        const float ebar = alv[i] * (ab[i] - s);
+        sm.eb[v][r] = ebar;
+        __nv_bfloat16 h, l;
+        split_bf16(ebar, h, l);
+        ebh[r] = h;
+        ebh[p.lo_off + r] = l;
+        if (tan) {
+          const float edb = alv[i] * (adb[i] - m_t);
+          split_bf16(edb, h, l);
+          tbh[r] = h;
+          tbh[p.lo_off + r] = l;
+        }
+      }
+    }
+  }
+  if (p.Pbar) {
+    __syncthreads();
+    for (int r = tid; r < R; r += AT_THREADS) {
+      float s = 0.f;
+      for (int v = 0; v < ns; ++v) s += sm.eb[v][r];
+      p.Pbar[(long long)b * p.ldP + r] += s;
+    }
+  }
+}
+
+static size_t attn_smem_bytes() { return sizeof(AttnSmem) + 128; }
+
+int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
+  SGG_CHECK(p.R > 0 && p.R <= AT_RMAX, "attn_fwd: R=%d out of range (1..%d)", p.R, AT_RMAX);
+  SGG_CHECK(p.nv >= 1 && p.nv <= AT_MAXV, "attn_fwd: nv=%d out of range", p.nv);
+  static bool configured = false;
+  if (!configured) {
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    configured = true;
+  }
+  if (mode == 0)
+    attn_fwd_kernel<0><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+  else
+    attn_fwd_kernel<1><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_rev(const AttnRevParams& p, cudaStream_t stream) {
+  SGG_CHECK(p.R > 0 && p.R <= AT_RMAX, "attn_rev: R=%d out of range (1..%d)", p.R, AT_RMAX);
+  SGG_CHECK(p.nv >= 1 && p.nv <= AT_MAXV, "attn_rev: nv=%d out of range", p.nv);
+  static bool configured = false;
+  if (!configured) {
+    SGG_CUDA(cudaFuncSetAttribute(attn_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    configured = true;
+  }
+  attn_rev_kernel<<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sgg

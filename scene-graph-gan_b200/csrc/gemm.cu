@@ -1,0 +1,317 @@
+// tcgen05 GEMM for sm_100a: TMA-staged bf16 operands (128B swizzle), fp32 accumulators in
+// TMEM, warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue warps), split-K over grid.z.
+//
+// Replaces every tf MatMul of the reference hot path (gen:15,79/87,88; disc:87,90) and the
+// MatMul gradients TF registers for them.  See include/sgg_b200.h (sgg_gemm_desc_t).
+#include "common.cuh"
+#include "../../include/sgg_b200.h"
+
+namespace sgg {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+struct GemmKParams {
+  int M, N;
+  int nseg;
+  int seg_a_k[SGG_GEMM_MAX_SEG], seg_a_mn[SGG_GEMM_MAX_SEG];
+  int seg_b_k[SGG_GEMM_MAX_SEG], seg_b_mn[SGG_GEMM_MAX_SEG];
+  int seg_kb[SGG_GEMM_MAX_SEG];  // k-blocks per segment
+  int total_kb;
+  float* C; long long ldc; int atomic;
+  __nv_bfloat16* Chl; long long ld_hl; long long lo_off;
+  const float* bias;
+  const float* addm; long long ld_addm; int add_mod;
+  float alpha;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmKParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + S::STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  // split-K range for this CTA
+  const int splits = gridDim.z;
+  const int kb_per = (p.total_kb + splits - 1) / splits;
+  const int kb_begin = blockIdx.z * kb_per;
+  const int kb_end = min(p.total_kb, kb_begin + kb_per);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < S::STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      // locate (segment, local k-block) of kb_begin
+      int seg = 0, kbl = kb_begin;
+      while (seg < p.nseg - 1 && kbl >= p.seg_kb[seg]) {
+        kbl -= p.seg_kb[seg];
+        ++seg;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * S::STAGE_BYTES;
+        uint8_t* sB = sA + A_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+        const int ka = p.seg_a_k[seg] + kbl * BK;
+        const int kb = p.seg_b_k[seg] + kbl * BK;
+        if (!A_MN) {
+          tma_load_2d(sA, &tmA, &full_bar[stage], ka, m0 + p.seg_a_mn[seg]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + p.seg_a_mn[seg] + 64 * j, ka);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB, &tmB, &full_bar[stage], kb, n0 + p.seg_b_mn[seg]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + p.seg_b_mn[seg] + 64 * j, kb);
+        }
+        if (++kbl == p.seg_kb[seg] && seg < p.nseg - 1) {
+          kbl = 0;
+          ++seg;
+        }
+        if (++stage == S::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
+        const uint32_t sB = sA + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = A_MN ? make_smem_desc(sA + k * 2048, BK * 128, 1024)
+                                   : make_smem_desc(sA + k * 32, 0, 1024);
+          const uint64_t db = B_MN ? make_smem_desc(sB + k * 2048, BK * 128, 1024)
+                                   : make_smem_desc(sB + k * 32, 0, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        if (i == nkb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == S::STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (nkb > 0) {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = m0 + q * 32 + (int)lane_id();
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+    const float* addrow = p.addm ? p.addm + (long long)(row % p.add_mod) * p.ld_addm : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+      const bool full = (col0 + 32 <= p.N);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+      }
+      if (addrow) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || col0 + j < p.N) v[j] += __ldg(addrow + col0 + j);
+      }
+      if (p.C) {
+        float* crow = p.C + (long long)row * p.ldc + col0;
+        if (p.atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) atomicAdd(crow + j, v[j]);
+        } else if (full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) crow[j] = v[j];
+        }
+      }
+      if (p.Chl) {
+        __nv_bfloat16* hrow = p.Chl + (long long)row * p.ld_hl + col0;
+        __nv_bfloat16* lrow = hrow + p.lo_off;
+        if (full && ((p.ld_hl & 7) == 0) && ((p.lo_off & 7) == 0) &&
+            ((reinterpret_cast<uintptr_t>(p.Chl) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(v[j + 2 * e], h0, l0);
+              split_bf16(v[j + 2 * e + 1], h1, l1);
+              h[e] = pack_bf16x2(h0, h1);
+              l[e] = pack_bf16x2(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(hrow + j) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(lrow + j) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) {
+              __nv_bfloat16 h0, l0;
+              split_bf16(v[j], h0, l0);
+              hrow[j] = h0;
+              lrow[j] = l0;
+            }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, int splits,
+                       cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    SGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    configured = true;
+  }
+  dim3 grid((kp.M + BM - 1) / BM, (kp.N + BN - 1) / BN, splits);
+  kern<<<grid, GEMM_THREADS, S::BYTES, stream>>>(tmA, tmB, kp);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const GemmKParams& kp, int splits, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, kp, splits, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, kp, splits, stream);
+  if (a_mn && b_mn) return launch_gemm<BN, true, true>(tmA, tmB, kp, splits, stream);
+  return launch_gemm<BN, true, false>(tmA, tmB, kp, splits, stream);
+}
+
+int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
+  SGG_CHECK(d.A && d.B, "sgg_gemm: null operand");
+  SGG_CHECK(d.M > 0 && d.N > 0, "sgg_gemm: bad M/N (%d, %d)", d.M, d.N);
+  SGG_CHECK(d.nseg >= 1 && d.nseg <= SGG_GEMM_MAX_SEG, "sgg_gemm: nseg=%d out of range", d.nseg);
+  SGG_CHECK(d.C || d.Chl, "sgg_gemm: no output");
+  GemmKParams kp{};
+  kp.M = d.M;
+  kp.N = d.N;
+  kp.nseg = d.nseg;
+  kp.total_kb = 0;
+  for (int s = 0; s < d.nseg; ++s) {
+    SGG_CHECK(d.seg_klen[s] > 0 && d.seg_klen[s] % BK == 0, "sgg_gemm: segment %d length %d not a multiple of %d",
+              s, d.seg_klen[s], BK);
+    kp.seg_a_k[s] = d.seg_a_k[s];
+    kp.seg_a_mn[s] = d.seg_a_mn[s];
+    kp.seg_b_k[s] = d.seg_b_k[s];
+    kp.seg_b_mn[s] = d.seg_b_mn[s];
+    kp.seg_kb[s] = d.seg_klen[s] / BK;
+    kp.total_kb += kp.seg_kb[s];
+  }
+  kp.C = d.C; kp.ldc = d.ldc; kp.atomic = d.atomic;
+  kp.Chl = reinterpret_cast<__nv_bfloat16*>(d.Chl); kp.ld_hl = d.ld_hl; kp.lo_off = d.lo_off;
+  kp.bias = d.bias;
+  kp.addm = d.addm; kp.ld_addm = d.ld_addm; kp.add_mod = d.add_mod > 0 ? d.add_mod : 1;
+  kp.alpha = d.alpha;
+  int splits = d.splits > 1 ? d.splits : 1;
+  if (splits > kp.total_kb) splits = kp.total_kb;
+  SGG_CHECK(splits == 1 || (d.atomic && d.C && !d.Chl && !d.bias && !d.addm),
+            "sgg_gemm: split-K needs the atomic fp32 epilogue only");
+  int bn = d.block_n;
+  if (bn == 0) {
+    const int tm = (d.M + BM - 1) / BM;
+    if (d.N <= 64) bn = 64;
+    else if (d.N <= 128) bn = 128;
+    else bn = (tm * ((d.N + 255) / 256) * splits >= 120) ? 256 : 128;
+  }
+  SGG_CHECK(bn == 64 || bn == 128 || bn == 256, "sgg_gemm: block_n=%d unsupported", bn);
+  CUtensorMap tmA, tmB;
+  // K-major: tensor [MN rows, K cols], box {64 k, tile rows}.  MN-major: tensor [K rows, MN cols], box {64 mn, 64 k}.
+  SGG_TRY(make_tmap_bf16_2d(&tmA, d.A, d.a_rows, d.a_cols, d.a_ld, 64, d.a_mn_major ? BK : BM));
+  SGG_TRY(make_tmap_bf16_2d(&tmB, d.B, d.b_rows, d.b_cols, d.b_ld, 64, d.b_mn_major ? BK : bn));
+  const bool amn = d.a_mn_major != 0, bmn = d.b_mn_major != 0;
+  switch (bn) {
+    case 64: return dispatch_major<64>(amn, bmn, tmA, tmB, kp, splits, stream);
+    case 128: return dispatch_major<128>(amn, bmn, tmA, tmB, kp, splits, stream);
+    default: return dispatch_major<256>(amn, bmn, tmA, tmB, kp, splits, stream);
+  }
+}
+
+}  // namespace sgg
+
+extern "C" int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream) {
+  if (!d) {
+    sgg::set_error("sgg_gemm: null descriptor");
+    return -1;
+  }
+  return sgg::gemm(*d, reinterpret_cast<cudaStream_t>(stream));
+}
