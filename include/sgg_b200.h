@@ -64,7 +64,7 @@ typedef struct sgg_gemm_desc {
   int32_t nseg;
   int32_t seg_a_k[SGG_GEMM_MAX_SEG], seg_a_mn[SGG_GEMM_MAX_SEG];
   int32_t seg_b_k[SGG_GEMM_MAX_SEG], seg_b_mn[SGG_GEMM_MAX_SEG];
-  int32_t seg_klen[SGG_GEMM_MAX_SEG]; /* multiple of 64 */
+  int32_t seg_klen[SGG_GEMM_MAX_SEG]; /* k-blocks of 64; a ragged tail must fall outside both tensors */
   /* epilogue */
   float* C; int64_t ldc; int32_t atomic;        /* fp32 output (optional); atomic => red.add */
   void* Chl; int64_t ld_hl; int64_t lo_off;     /* bf16 hi/lo split output (optional) */
@@ -76,6 +76,84 @@ typedef struct sgg_gemm_desc {
 } sgg_gemm_desc_t;
 
 int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Parameters.  Each network keeps ONE flat fp32 bucket (master weights; gradients and Adam
+ * moments use the same layout) plus a bf16 "shadow" bucket holding the GEMM operands with
+ * rows padded to a 16-byte pitch.  The table reproduces the reference's TF variable names
+ * (train:262-263 splits them by the "Generator"/"Discriminator" prefix):
+ *   <scope>/attention_perceptron/{kernel [R*C+H, R], bias [R]}                  (gen:15)
+ *   <scope>/layer_norm_basic_lstm_cell/{kernel [C+U+H, 4H], <ln>/{gamma,beta}}  (gen:79)
+ *   <scope>/decoder/{kernel [H, V|1], bias}                                     (gen:88, disc:90)
+ *   Discriminator/W [V, E]                                                      (train:70)
+ * net: 0 = generator, 1 = discriminator.  Offsets are in floats / bf16 elements.
+ * -------------------------------------------------------------------------------------- */
+typedef struct sgg_param_entry {
+  char name[96];
+  int64_t offset;
+  int32_t rows, cols;
+  int64_t shadow_offset; /* -1: tensor has no bf16 shadow (used in fp32) */
+  int32_t shadow_pitch;
+  int32_t reserved;
+} sgg_param_entry_t;
+
+int sgg_param_table(int net, const sgg_dims_t* d, sgg_param_entry_t* out, int max_entries,
+                    int* n_entries, int64_t* n_floats, int64_t* n_shadow);
+
+/* Rebuilds the bf16 shadow from the fp32 master bucket (after init / load). */
+int sgg_refresh_shadow(int net, const sgg_dims_t* d, const float* theta, void* shadow, sgg_stream_t stream);
+
+/* tf.train.AdamOptimizer update (train:258-259) over the flat bucket, epsilon outside the bias
+ * correction: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps).  Also refreshes
+ * the bf16 shadow.  step is 1-based.  grad_scale multiplies the gradient (1/world after a
+ * sum-allreduce of mean-normalised shards is NOT needed: the kernels already normalise by the
+ * global batch). */
+int sgg_adam_step(int net, const sgg_dims_t* d, float* theta, const float* grad, float* m, float* v,
+                  void* shadow, int64_t step, float lr, float beta1, float beta2, float eps,
+                  float grad_scale, sgg_stream_t stream);
+
+/* Philox4x32-10 counter RNG: tf.random_normal (gen:81) / tfgan's random_uniform alpha. */
+int sgg_rng_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream);
+int sgg_rng_fill_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Training / inference steps.  The workspace (sgg_workspace_bytes) must be zero-filled once
+ * by the caller after allocation; its contents are private to the library.
+ * -------------------------------------------------------------------------------------- */
+int64_t sgg_workspace_bytes(const sgg_dims_t* d);
+
+#define SGG_FLAG_REFRESH_GEN_PROJ 1 /* recompute the generator's hoisted projection P and c0: set on
+                                       the first call for a new batch and after a generator update */
+
+typedef struct sgg_step_args {
+  sgg_dims_t dims;
+  int32_t world;          /* data-parallel world size: losses are means over B*world samples */
+  float lam;              /* gradient_penalty_weight (train:249, --lambda) */
+  const float* g_theta; const void* g_shadow; float* g_grad;
+  const float* d_theta; const void* d_shadow; float* d_grad;
+  const void* ann_g;      /* [B,R,C] bf16: generator's annotations (gen:68 self.downsampled) */
+  const void* ann_d;      /* [B,R,C] bf16: discriminator's annotations (disc:68) */
+  const int64_t* labels;  /* [B,T] class ids of the real triples (one-hot of train:173) */
+  const float* noise;     /* [B,C] N(0,1), shared by all timesteps (gen:81,86) */
+  const float* gp_alpha;  /* [B] U[0,1) interpolation coefficients (tfgan gradient penalty) */
+  void* workspace; int64_t workspace_bytes;
+  float* scalars;         /* [4] device floats: {-, w_disc, gp, gen_cost} */
+  float* logits_out;      /* optional [B,T,V] fp32 generator logits */
+  int32_t flags;
+} sgg_step_args_t;
+
+/* gen:74-91 (from self.downsampled): logits [B,T,V] into logits_out. */
+int sgg_gen_forward(const sgg_step_args_t* a, sgg_stream_t stream);
+/* disc:73-93 on caller-supplied float triples [B,T,V]: scores [B,T]. */
+int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, float* scores_out, sgg_stream_t stream);
+/* train:365 minus the optimizer: d disc_cost / d Discriminator* into d_grad (overwritten),
+ * disc_cost = scalars[1] + lam * scalars[2]  (train:245-253). */
+int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream);
+/* train:368 minus the optimizer: d gen_cost / d Generator* into g_grad, scalars[3] = gen_cost. */
+int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream);
+
+/* Test/debug accessor: byte offset of a named intermediate buffer inside the workspace. */
+int sgg_ws_lookup(const sgg_dims_t* d, const char* name, int64_t* offset_bytes, int64_t* elem_bytes);
 
 #ifdef __cplusplus
 }

@@ -62,3 +62,34 @@ def stream_ptr(stream=None) -> C.c_void_p:
     import torch
     s = stream if stream is not None else torch.cuda.current_stream()
     return C.c_void_p(s.cuda_stream)
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "T", "V", "R", "C", "H", "E")]
+
+
+class ParamEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 96), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("shadow_offset", C.c_int64), ("shadow_pitch", C.c_int32), ("reserved", C.c_int32)]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ("dims", Dims), ("world", C.c_int32), ("lam", C.c_float),
+        ("g_theta", C.c_void_p), ("g_shadow", C.c_void_p), ("g_grad", C.c_void_p),
+        ("d_theta", C.c_void_p), ("d_shadow", C.c_void_p), ("d_grad", C.c_void_p),
+        ("ann_g", C.c_void_p), ("ann_d", C.c_void_p), ("labels", C.c_void_p),
+        ("noise", C.c_void_p), ("gp_alpha", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("scalars", C.c_void_p), ("logits_out", C.c_void_p), ("flags", C.c_int32),
+    ]
+
+
+FLAG_REFRESH_GEN_PROJ = 1
+
+# every symbol include/sgg_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "sgg_last_error", "sgg_version", "sgg_gemm", "sgg_param_table", "sgg_refresh_shadow", "sgg_adam_step",
+    "sgg_rng_fill_normal", "sgg_rng_fill_uniform", "sgg_workspace_bytes", "sgg_gen_forward",
+    "sgg_disc_forward", "sgg_disc_step", "sgg_gen_step", "sgg_ws_lookup",
+]

@@ -15,14 +15,15 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    """All kernels are compiled as one unity translation unit."""
+    return [os.path.join(CSRC, "sgg_b200_all.cu")]
 
 
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(HERE, "..", "include", "sgg_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -41,7 +41,9 @@ __device__ __forceinline__ void attn_issue_chunk(AttnSmem& sm, const __nv_bfloat
 struct AttnFwdParams {
   const __nv_bfloat16* a;  // [B,R,C]
   int B, R, nv;
-  int row_blk[AT_MAXV];    // stream v uses rows row_blk[v]*B + b of E/alpha/X
+  int row_blk[AT_MAXV];    // stream v writes rows row_blk[v]*B + b of alpha_out / X
+  int e_blk[AT_MAXV];      // ... and reads rows e_blk[v]*B + b of E
+  int ain_blk;             // mode 1: saved alpha is read from rows ain_blk*B + b
   // mode 0 (softmax): E -> alpha ; mode 1 (tangent): alpha (saved) + edot -> adot
   const float* E; long long ldE;      // scores (mode 0) or edot (mode 1)
   const float* alpha_in;              // mode 1: saved alpha (same row indexing / ld as alpha_out)
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParam
   // ---- per-stream weights (softmax or its tangent), one warp per stream
   if (warp < p.nv) {
     const long long row = (long long)p.row_blk[warp] * p.B + b;
-    const float* e = p.E + row * p.ldE;
+    const float* e = p.E + ((long long)p.e_blk[warp] * p.B + b) * p.ldE;
     float v[AT_RMAX / 32];
     if (MODE == 0) {
       float mx = -INFINITY;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParam
 #pragma unroll
       for (int i = 0; i < AT_RMAX / 32; ++i) v[i] *= inv;
     } else {
-      const float* al = p.alpha_in + row * p.ldA;
+      const float* al = p.alpha_in + ((long long)p.ain_blk * p.B + b) * p.ldA;
       float m = 0.f;
       float ed[AT_RMAX / 32];
 #pragma unroll

@@ -268,13 +268,14 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
   kp.nseg = d.nseg;
   kp.total_kb = 0;
   for (int s = 0; s < d.nseg; ++s) {
-    SGG_CHECK(d.seg_klen[s] > 0 && d.seg_klen[s] % BK == 0, "sgg_gemm: segment %d length %d not a multiple of %d",
-              s, d.seg_klen[s], BK);
+    // A length that is not a multiple of 64 is only valid when the tail of the last k-block lies outside the
+    // tensors (TMA zero-fills out-of-bounds elements), e.g. a contraction over all rows of both operands.
+    SGG_CHECK(d.seg_klen[s] > 0, "sgg_gemm: segment %d has length %d", s, d.seg_klen[s]);
     kp.seg_a_k[s] = d.seg_a_k[s];
     kp.seg_a_mn[s] = d.seg_a_mn[s];
     kp.seg_b_k[s] = d.seg_b_k[s];
     kp.seg_b_mn[s] = d.seg_b_mn[s];
-    kp.seg_kb[s] = d.seg_klen[s] / BK;
+    kp.seg_kb[s] = (d.seg_klen[s] + BK - 1) / BK;
     kp.total_kb += kp.seg_kb[s];
   }
   kp.C = d.C; kp.ldc = d.ldc; kp.atomic = d.atomic;

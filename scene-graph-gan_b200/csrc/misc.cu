@@ -1,0 +1,378 @@
+// Small HBM-bound / elementwise kernels of the hot path: mean-pool initial state (gen:76-77),
+// embedding gather + interpolate mixing (disc:86-87, tfgan interpolates), hi/lo packing,
+// WGAN-GP slopes/penalty (train:245-250 via tfgan), Wasserstein losses (train:252-253),
+// TF-form Adam over flat buckets (train:258-259), Philox RNG (gen:81, tfgan alpha).
+#include "common.cuh"
+#include "../../include/sgg_b200.h"
+
+namespace sgg {
+static inline long long llmin(long long a, long long b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------ mean pool
+// c0[b,:] = mean_r a[b,r,:]  -> fp32 C0, hi/lo CH0, and h0 hi/lo into X0's h columns, replicated
+// into `nblk` stream row blocks.
+struct MeanPoolParams {
+  const __nv_bfloat16* a; int B, R, nblk;
+  float* C0;                                              // [nblk*B, 512]
+  __nv_bfloat16* CH; long long ldCH; long long ch_lo;     // [nblk*B, ...]
+  __nv_bfloat16* X; long long ldX; long long x_lo; int hoff;
+};
+
+__global__ void __launch_bounds__(256) meanpool_kernel(const MeanPoolParams p) {
+  __shared__ float red[4][512];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int cg = tid & 63, rg = tid >> 6;
+  const uint4* base = reinterpret_cast<const uint4*>(p.a + (size_t)b * p.R * 512);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 7
+  for (int r = rg; r < p.R; r += 4) {
+    const uint4 pk = __ldg(base + (size_t)r * 64 + cg);
+    const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[2 * e] += bf16lo_to_f32(w[e]);
+      acc[2 * e + 1] += bf16hi_to_f32(w[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rg][cg * 8 + e] = acc[e];
+  __syncthreads();
+  const float inv = 1.0f / p.R;
+  for (int c = tid; c < 512; c += 256) {
+    const float m = (red[0][c] + red[1][c] + red[2][c] + red[3][c]) * inv;
+    __nv_bfloat16 h, l;
+    split_bf16(m, h, l);
+    for (int s = 0; s < p.nblk; ++s) {
+      const long long row = (long long)s * p.B + b;
+      p.C0[row * 512 + c] = m;
+      if (p.CH) {
+        p.CH[row * p.ldCH + c] = h;
+        p.CH[row * p.ldCH + p.ch_lo + c] = l;
+      }
+      if (p.X) {
+        p.X[row * p.ldX + p.hoff + c] = h;
+        p.X[row * p.ldX + p.x_lo + p.hoff + c] = l;
+      }
+    }
+  }
+}
+
+int meanpool(const MeanPoolParams& p, cudaStream_t stream) {
+  meanpool_kernel<<<p.B, 256, 0, stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ pack hi/lo
+// dst[r, c] (hi) / dst[r, lo_off + c] (lo) = scale[r % smod] * (src[r, c] + mix[r % mmod] * src2[r, c])
+struct PackParams {
+  int rows, cols;
+  int rpg;                             // rows per group (row r -> group r / rpg, index r % rpg); 0 = one group
+  const float* src; long long ld; long long gstride;     // src row address = src + group*gstride + index*ld
+  const float* src2; long long ld2; long long gstride2;  // optional second source
+  const float* mix; int mmod;          // optional per-row multiplier on src2 (row % mmod)
+  const float* scale; int smod;        // optional per-row scale
+  __nv_bfloat16* dst; long long ldd; long long lo_off;
+};
+__global__ void pack_hl_kernel(const PackParams p) {
+  const long long n = (long long)p.rows * p.cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / p.cols), c = (int)(i % p.cols);
+    const int grp = p.rpg > 0 ? r / p.rpg : 0, idx = p.rpg > 0 ? r % p.rpg : r;
+    float v = p.src[grp * p.gstride + (long long)idx * p.ld + c];
+    if (p.src2) v += (p.mix ? p.mix[r % p.mmod] : 1.0f) * p.src2[grp * p.gstride2 + (long long)idx * p.ld2 + c];
+    if (p.scale) v *= p.scale[r % p.smod];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    p.dst[(long long)r * p.ldd + c] = h;
+    p.dst[(long long)r * p.ldd + p.lo_off + c] = l;
+  }
+}
+int pack_hl(const PackParams& p, cudaStream_t stream) {
+  const long long n = (long long)p.rows * p.cols;
+  if (n <= 0) return 0;
+  const int grid = (int)llmin((n + 255) / 256, 148 * 8);
+  pack_hl_kernel<<<grid, 256, 0, stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ embeddings
+// Per (t, b): u_fake (GEMM result, fp32, row t*B+b), u_real = W_emb[label] (fp32 master: exactly
+// one_hot @ W of disc:86-87), u_int = u_real + alpha_b (u_fake - u_real) (linearity of disc:87 in
+// tfgan's interpolates).  Written hi/lo into the x buffers' u columns of the stream row blocks.
+struct EmbedMixParams {
+  int B, T, E;
+  const float* Uf; long long ldUf;      // [T*B, E] or null (no fake stream)
+  const int64_t* labels;                // [B, T] or null (no real stream)
+  const float* Wemb;                    // [V, E] fp32 master
+  const float* gp_alpha;                // [B] or null (no interp stream)
+  int blk_fake, blk_real, blk_int;      // row blocks (or -1)
+  __nv_bfloat16* X; long long ldX; long long x_lo; long long strideT; int uoff; int NR;
+};
+__global__ void embed_mix_kernel(const EmbedMixParams p) {
+  const long long n = (long long)p.T * p.B * p.E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % p.E);
+    const long long tb = i / p.E;
+    const int b = (int)(tb % p.B), t = (int)(tb / p.B);
+    const float uf = p.Uf ? p.Uf[tb * p.ldUf + e] : 0.f;
+    const float ur = p.labels ? p.Wemb[p.labels[(long long)b * p.T + t] * p.E + e] : 0.f;
+    __nv_bfloat16* xt = p.X + (long long)t * p.strideT + p.uoff + e;
+    __nv_bfloat16 h, l;
+    if (p.blk_fake >= 0) {
+      split_bf16(uf, h, l);
+      const long long row = (long long)p.blk_fake * p.B + b;
+      xt[row * p.ldX] = h; xt[row * p.ldX + p.x_lo] = l;
+    }
+    if (p.blk_real >= 0) {
+      split_bf16(ur, h, l);
+      const long long row = (long long)p.blk_real * p.B + b;
+      xt[row * p.ldX] = h; xt[row * p.ldX + p.x_lo] = l;
+    }
+    if (p.blk_int >= 0) {
+      split_bf16(ur + p.gp_alpha[b] * (uf - ur), h, l);
+      const long long row = (long long)p.blk_int * p.B + b;
+      xt[row * p.ldX] = h; xt[row * p.ldX + p.x_lo] = l;
+    }
+  }
+}
+int embed_mix(const EmbedMixParams& p, cudaStream_t stream) {
+  const long long n = (long long)p.T * p.B * p.E;
+  const int grid = (int)llmin((n + 255) / 256, 148 * 8);
+  embed_mix_kernel<<<grid, 256, 0, stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dW_emb[label[b,t], :] += u_bar_real + (1 - alpha_b) u_bar_int   (one-hot rows of x^T u_bar)
+struct EmbedScatterParams {
+  int B, T, E;
+  const int64_t* labels; const float* gp_alpha;
+  const float* XB; long long ldXB; long long strideT; int uoff;   // u_bar = XB[t][row, uoff:uoff+E]
+  int blk_real, blk_int;
+  float* dWemb;
+};
+__global__ void embed_scatter_kernel(const EmbedScatterParams p) {
+  const long long n = (long long)p.T * p.B * p.E;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % p.E);
+    const long long tb = i / p.E;
+    const int b = (int)(tb % p.B), t = (int)(tb / p.B);
+    const float* xb = p.XB + (long long)t * p.strideT + p.uoff + e;
+    float v = xb[((long long)p.blk_real * p.B + b) * p.ldXB];
+    if (p.blk_int >= 0) v += (1.0f - p.gp_alpha[b]) * xb[((long long)p.blk_int * p.B + b) * p.ldXB];
+    atomicAdd(p.dWemb + p.labels[(long long)b * p.T + t] * p.E + e, v);
+  }
+}
+int embed_scatter(const EmbedScatterParams& p, cudaStream_t stream) {
+  const long long n = (long long)p.T * p.B * p.E;
+  const int grid = (int)llmin((n + 255) / 256, 148 * 8);
+  embed_scatter_kernel<<<grid, 256, 0, stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ GP slopes
+// g [T*B, ld] (row t*B+b).  slopes_b = sqrt(sum_{t,v} g^2 + 1e-10); pen = mean_b max(0, s-1)^2;
+// coef_b = lam_scale * (2/Bglobal) max(0, s-1)/s   (d pen / d g = coef * g).   scal[2] += pen part.
+struct GpSlopesParams {
+  int B, T, V; const float* g; long long ld;
+  float* slopes; float* coef; float* scal;  // scal[2] (gp) accumulated atomically
+  float inv_Bglobal;
+};
+__global__ void __launch_bounds__(256) gp_slopes_kernel(const GpSlopesParams p) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int t = 0; t < p.T; ++t) {
+    const float* row = p.g + ((long long)t * p.B + b) * p.ld;
+    for (int v = threadIdx.x; v < p.V; v += 256) s = fmaf(row[v], row[v], s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float slope = sqrtf(tot + 1e-10f);
+    const float ex = fmaxf(slope - 1.0f, 0.f);
+    p.slopes[b] = slope;
+    p.coef[b] = 2.0f * p.inv_Bglobal * ex / slope;
+    atomicAdd(p.scal + 2, ex * ex * p.inv_Bglobal);
+  }
+}
+int gp_slopes(const GpSlopesParams& p, cudaStream_t stream) {
+  gp_slopes_kernel<<<p.B, 256, 0, stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ losses
+// Y [NR, T].  scal[1] += (sum Y[blk_fake] - sum Y[blk_real]) * inv ; scal[3] += -sum Y[blk_fake] * inv
+struct LossParams { int B, T; const float* Y; int blk_fake, blk_real; float inv; float* scal; };
+__global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
+  __shared__ float red[2][8];
+  float sf = 0.f, sr = 0.f;
+  const int n = p.B * p.T;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    if (p.blk_fake >= 0) sf += p.Y[(long long)p.blk_fake * n + i];
+    if (p.blk_real >= 0) sr += p.Y[(long long)p.blk_real * n + i];
+  }
+  sf = warp_sum(sf); sr = warp_sum(sr);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sf; red[1][threadIdx.x >> 5] = sr; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    atomicAdd(p.scal + 1, (a - b) * p.inv);
+    atomicAdd(p.scal + 3, -a * p.inv);
+  }
+}
+int losses(const LossParams& p, cudaStream_t stream) {
+  loss_kernel<<<1, 256, 0, stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// column sums: out[c] += sum_r src[r, c]
+__global__ void colsum_kernel(const float* src, long long ld, int rows, int cols, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) s += src[(long long)r * ld + c];
+  atomicAdd(out + c, s);
+}
+int colsum(const float* src, long long ld, int rows, int cols, float* out, cudaStream_t stream) {
+  dim3 grid((cols + 127) / 128, min(rows, 32));
+  colsum_kernel<<<grid, 128, 0, stream>>>(src, ld, rows, cols, out);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sgg
+
+// ------------------------------------------------------------------------------------ Adam
+// tf.train.AdamOptimizer update (train:258-259): m,v moments; lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+// theta -= lr_t * m / (sqrt(v) + eps).  Flat fp32 buckets; also refreshes the bf16 shadow of
+// each tensor (the GEMM B operands), whose rows are padded to a 16-byte pitch.
+namespace sgg {
+struct AdamSeg { long long off; long long sh_off; int cols; int pitch; long long n; };
+constexpr int ADAM_MAX_SEG = 24;
+struct AdamParams {
+  float* theta; const float* grad; float* m; float* v; __nv_bfloat16* shadow;
+  float lr_t, b1, b2, eps, gscale;
+  int nseg; AdamSeg seg[ADAM_MAX_SEG];
+};
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams p) {
+  const int s = blockIdx.y;
+  const AdamSeg sg = p.seg[s];
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < sg.n; i += stride) {
+    const long long gi = sg.off + i;
+    float th[4], g[4], m[4], v[4];
+    const bool vec = (i + 4 <= sg.n) && ((gi & 3) == 0);
+    if (vec) {
+      const float4 t4 = *reinterpret_cast<const float4*>(p.theta + gi);
+      const float4 g4 = *reinterpret_cast<const float4*>(p.grad + gi);
+      const float4 m4 = *reinterpret_cast<const float4*>(p.m + gi);
+      const float4 v4 = *reinterpret_cast<const float4*>(p.v + gi);
+      th[0] = t4.x; th[1] = t4.y; th[2] = t4.z; th[3] = t4.w;
+      g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+      v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (i + e < sg.n) { th[e] = p.theta[gi + e]; g[e] = p.grad[gi + e]; m[e] = p.m[gi + e]; v[e] = p.v[gi + e]; }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gg = g[e] * p.gscale;
+      m[e] = p.b1 * m[e] + (1.0f - p.b1) * gg;
+      v[e] = p.b2 * v[e] + (1.0f - p.b2) * gg * gg;
+      th[e] -= p.lr_t * m[e] / (sqrtf(v[e]) + p.eps);
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(p.theta + gi) = make_float4(th[0], th[1], th[2], th[3]);
+      *reinterpret_cast<float4*>(p.m + gi) = make_float4(m[0], m[1], m[2], m[3]);
+      *reinterpret_cast<float4*>(p.v + gi) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (i + e < sg.n) { p.theta[gi + e] = th[e]; p.m[gi + e] = m[e]; p.v[gi + e] = v[e]; }
+    }
+    if (p.shadow && sg.sh_off >= 0) {
+      for (int e = 0; e < 4; ++e)
+        if (i + e < sg.n) {
+          const long long r = (i + e) / sg.cols, c = (i + e) % sg.cols;
+          p.shadow[sg.sh_off + r * sg.pitch + c] = __float2bfloat16_rn(th[e]);
+        }
+    }
+  }
+}
+int adam(const AdamParams& p, long long max_n, cudaStream_t stream) {
+  const int gx = (int)llmin((max_n / 4 + 255) / 256, 148 * 4);
+  dim3 grid(gx > 0 ? gx : 1, p.nseg);
+  adam_kernel<<<grid, 256, 0, stream>>>(p);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fp32 master -> bf16 shadow refresh only (initialisation / after loading parameters)
+__global__ void shadow_kernel(const float* theta, __nv_bfloat16* shadow, AdamSeg sg) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / sg.cols, c = i % sg.cols;
+    shadow[sg.sh_off + r * sg.pitch + c] = __float2bfloat16_rn(theta[sg.off + i]);
+  }
+}
+int refresh_shadow(const float* theta, __nv_bfloat16* shadow, const AdamSeg& sg, cudaStream_t stream) {
+  if (sg.sh_off < 0 || sg.n <= 0) return 0;
+  const int grid = (int)llmin((sg.n + 255) / 256, 148 * 8);
+  shadow_kernel<<<grid, 256, 0, stream>>>(theta, shadow, sg);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ Philox RNG
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+
+// mode 0: uniform [0,1) ; mode 1: standard normal (Box-Muller)
+__global__ void rng_fill_kernel(float* out, long long n, uint64_t seed, uint64_t offset, int mode) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  const uint64_t ctr = offset + (uint64_t)q;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  float o[4];
+  if (mode == 0) {
+    o[0] = (r.x >> 8) * (1.0f / 16777216.0f); o[1] = (r.y >> 8) * (1.0f / 16777216.0f);
+    o[2] = (r.z >> 8) * (1.0f / 16777216.0f); o[3] = (r.w >> 8) * (1.0f / 16777216.0f);
+  } else {
+    const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
+    sincosf(6.283185307179586f * u01(r.w), &s1, &c1);
+    o[0] = r0 * c0; o[1] = r0 * s0; o[2] = r1 * c1; o[3] = r1 * s1;
+  }
+  for (int e = 0; e < 4; ++e)
+    if (q * 4 + e < n) out[q * 4 + e] = o[e];
+}
+int rng_fill(float* out, long long n, uint64_t seed, uint64_t offset, int mode, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const long long quads = (n + 3) / 4;
+  rng_fill_kernel<<<(int)((quads + 255) / 256), 256, 0, stream>>>(out, n, seed, offset, mode);
+  SGG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sgg

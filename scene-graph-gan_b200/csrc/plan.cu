@@ -1,0 +1,812 @@
+// Execution plan of the WGAN-GP training hot path: parameter/workspace layout and the kernel
+// sequences of one discriminator step and one generator step (train:362-368), built from the
+// kernels in gemm.cu / attn.cu / lstm.cu / misc.cu.  The maths follows tests/plan_mirror.py
+// (hoisted attention projection, pass batching, reverse over a forward tangent for the
+// gradient penalty); every sequence is enqueued on the caller's stream, nothing allocates.
+#include <cstring>
+
+#include "common.cuh"
+#include "../../include/sgg_b200.h"
+
+namespace sgg {
+
+static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// ============================================================================ parameter layout
+struct ParamLayout {
+  bool gen;
+  int R, C, H, U, OUT, V, E, KX;
+  long long Watt, batt, K, lng[5], lnb[5], Wdec, bdec, Wemb, total;   // fp32 bucket offsets (floats)
+  long long sWa, sWh, sK, sWdec, sWemb, stotal;                       // bf16 shadow offsets (elements)
+  int pAtt, pK, pWdec, pWemb;                                         // shadow row pitches
+};
+
+static ParamLayout param_layout(bool gen, const sgg_dims_t& d) {
+  ParamLayout L{};
+  L.gen = gen; L.R = d.R; L.C = d.C; L.H = d.H; L.V = d.V; L.E = d.E;
+  L.U = gen ? d.C : d.E;
+  L.OUT = gen ? d.V : 1;
+  L.KX = d.C + L.U + d.H;
+  long long o = 0;
+  auto take = [&](long long n) { long long r = o; o = rup(o + n, 64); return r; };
+  L.Watt = take((long long)(d.R * d.C + d.H) * d.R);
+  L.batt = take(d.R);
+  L.K = take((long long)L.KX * 4 * d.H);
+  for (int i = 0; i < 5; ++i) { L.lng[i] = take(d.H); L.lnb[i] = take(d.H); }
+  L.Wdec = take((long long)d.H * L.OUT);
+  L.bdec = take(L.OUT);
+  L.Wemb = gen ? -1 : take((long long)d.V * d.E);
+  L.total = o;
+  long long s = 0;
+  auto stake = [&](long long n) { long long r = s; s = rup(s + n, 128); return r; };
+  L.pAtt = (int)rup(d.R, 8); L.pK = 4 * d.H; L.pWdec = (int)rup(L.OUT, 8); L.pWemb = (int)rup(d.E, 8);
+  L.sWa = stake((long long)d.R * d.C * L.pAtt);
+  L.sWh = stake((long long)d.H * L.pAtt);
+  L.sK = stake((long long)L.KX * L.pK);
+  L.sWdec = gen ? stake((long long)d.H * L.pWdec) : -1;
+  L.sWemb = gen ? -1 : stake((long long)d.V * L.pWemb);
+  L.stotal = s;
+  return L;
+}
+
+static const char* LN_NAMES[5] = {"input", "transform", "forget", "output", "state"};
+
+static int fill_adam_segs(const ParamLayout& L, AdamSeg* seg) {
+  int n = 0;
+  const long long RC = (long long)L.R * L.C;
+  seg[n++] = {L.Watt, L.sWa, L.R, L.pAtt, RC * L.R};
+  seg[n++] = {L.Watt + RC * L.R, L.sWh, L.R, L.pAtt, (long long)L.H * L.R};
+  seg[n++] = {L.batt, -1, L.R, L.R, L.R};
+  seg[n++] = {L.K, L.sK, 4 * L.H, L.pK, (long long)L.KX * 4 * L.H};
+  for (int i = 0; i < 5; ++i) {
+    seg[n++] = {L.lng[i], -1, L.H, L.H, L.H};
+    seg[n++] = {L.lnb[i], -1, L.H, L.H, L.H};
+  }
+  seg[n++] = {L.Wdec, L.sWdec, L.OUT, L.pWdec, (long long)L.H * L.OUT};
+  seg[n++] = {L.bdec, -1, L.OUT, L.OUT, L.OUT};
+  if (!L.gen) seg[n++] = {L.Wemb, L.sWemb, L.E, L.pWemb, (long long)L.V * L.E};
+  return n;
+}
+
+// ============================================================================ workspace layout
+struct NetWs {
+  int NRmax;
+  __nv_bfloat16* X; float* Cf; __nv_bfloat16* CH; float* EA; float* ED; float* Q; float* P;
+  __nv_bfloat16* QB; float* XB; __nv_bfloat16* EB; float* CB; float* PB; __nv_bfloat16* PBH;
+  float* Y;
+};
+struct Ws {
+  NetWs g, d;
+  __nv_bfloat16* FAKE;   // [T*B, 2*VP] generator logits hi/lo (row t*B+b)
+  float* DFAKE; __nv_bfloat16* DFAKEH;  // [T*B, VP] fp32 + hi/lo : d gen_cost / d fake, or the GP gradient g
+  __nv_bfloat16* VHL;    // [T*B, 2*VP] v = coef * g hi/lo
+  float* HB;             // [T*B, H]
+  float* UF;             // [T*B, EP] fp32 embedding temp
+  __nv_bfloat16* UBH;    // [T*B, 2*EP]
+  __nv_bfloat16* UDB;    // [T*B, 2*EP]
+  __nv_bfloat16* TRIH;   // [T*B, 2*VP] arbitrary float triples hi/lo (sgg_disc_forward)
+  float* slopes; float* coef;
+  long long bytes;
+};
+
+struct Dm {  // derived dimensions
+  int B, T, V, R, C, H, E, RP, VP, EP, KXG, KXD;
+};
+static Dm derive(const sgg_dims_t& d) {
+  Dm m{d.B, d.T, d.V, d.R, d.C, d.H, d.E, 0, 0, 0, 0, 0};
+  m.RP = (int)rup(d.R, 64); m.VP = (int)rup(d.V, 64); m.EP = (int)rup(d.E, 64);
+  m.KXG = (int)rup(d.C + d.C + d.H, 64); m.KXD = (int)rup(d.C + d.E + d.H, 64);
+  return m;
+}
+
+static Ws ws_layout(const sgg_dims_t& d, void* base) {
+  const Dm m = derive(d);
+  Ws w{};
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  long long o = 0;
+  auto take = [&](long long bytes) { uint8_t* r = p ? p + o : nullptr; o = rup(o + bytes, 256); return (void*)r; };
+  auto net = [&](NetWs& n, int NR, int KXP, bool disc) {
+    n.NRmax = NR;
+    const long long T = m.T;
+    n.X = (__nv_bfloat16*)take((T + 1) * NR * 2LL * KXP * 2);
+    n.Cf = (float*)take((T + 1) * NR * (long long)m.H * 4);
+    n.CH = (__nv_bfloat16*)take((T + 1) * NR * 2LL * m.H * 2);
+    n.EA = (float*)take(T * NR * (long long)m.RP * 4);
+    n.ED = disc ? (float*)take(T * (long long)m.B * m.RP * 4) : nullptr;
+    n.Q = (float*)take(T * NR * 4LL * m.H * 4);
+    n.P = (float*)take((long long)m.B * m.RP * 4);
+    n.QB = (__nv_bfloat16*)take(T * NR * 8LL * m.H * 2);
+    n.XB = (float*)take(T * NR * (long long)KXP * 4);
+    n.EB = (__nv_bfloat16*)take(T * NR * 2LL * m.RP * 2);
+    n.CB = (float*)take(T * NR * (long long)m.H * 4);
+    n.PB = (float*)take((long long)m.B * m.RP * 4);
+    n.PBH = (__nv_bfloat16*)take((long long)m.B * 2 * m.RP * 2);
+    n.Y = disc ? (float*)take((long long)NR * T * 4) : nullptr;
+  };
+  net(w.g, m.B, m.KXG, false);
+  net(w.d, 4 * m.B, m.KXD, true);
+  const long long TB = (long long)m.T * m.B;
+  w.FAKE = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
+  w.DFAKE = (float*)take(TB * m.VP * 4);
+  w.DFAKEH = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
+  w.VHL = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
+  w.HB = (float*)take(TB * m.H * 4);
+  w.UF = (float*)take(TB * m.EP * 4);
+  w.UBH = (__nv_bfloat16*)take(TB * 2 * m.EP * 2);
+  w.UDB = (__nv_bfloat16*)take(TB * 2 * m.EP * 2);
+  w.TRIH = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
+  w.slopes = (float*)take(m.B * 4);
+  w.coef = (float*)take(m.B * 4);
+  w.bytes = o;
+  return w;
+}
+
+// ============================================================================ one network
+struct Net {
+  bool gen;
+  Dm m;
+  ParamLayout L;
+  const float* theta; const __nv_bfloat16* sh; float* grad;  // grad may be null (data path only)
+  const __nv_bfloat16* a;
+  NetWs w;
+  int NR;        // active rows per timestep (streams * B)
+  int KXP, U, uoff, hoff;
+  cudaStream_t st;
+  // strides (elements) between timesteps, for the active NR
+  long long sX() const { return (long long)NR * 2 * KXP; }
+  long long sCf() const { return (long long)NR * m.H; }
+  long long sCH() const { return (long long)NR * 2 * m.H; }
+  long long sEA() const { return (long long)NR * m.RP; }
+  long long sQ() const { return (long long)NR * 4 * m.H; }
+  long long sQB() const { return (long long)NR * 8 * m.H; }
+  long long sXB() const { return (long long)NR * KXP; }
+  long long sEB() const { return (long long)NR * 2 * m.RP; }
+  LstmLN ln() const {
+    LstmLN l;
+    for (int i = 0; i < 5; ++i) { l.gamma[i] = theta + L.lng[i]; l.beta[i] = theta + L.lnb[i]; }
+    return l;
+  }
+};
+
+static Net make_net(bool gen, const sgg_dims_t& d, const float* theta, const void* sh, float* grad, const void* a,
+                    const NetWs& w, int NR, cudaStream_t st) {
+  Net n{};
+  n.gen = gen; n.m = derive(d); n.L = param_layout(gen, d);
+  n.theta = theta; n.sh = (const __nv_bfloat16*)sh; n.grad = grad; n.a = (const __nv_bfloat16*)a;
+  n.w = w; n.NR = NR; n.st = st;
+  n.KXP = gen ? n.m.KXG : n.m.KXD;
+  n.U = n.L.U; n.uoff = d.C; n.hoff = d.C + n.L.U;
+  return n;
+}
+
+static sgg_gemm_desc_t gd_zero() { sgg_gemm_desc_t g; memset(&g, 0, sizeof(g)); g.alpha = 1.0f; return g; }
+int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream);
+
+// K1: P = flat(a) W_a  (bias is added where P is consumed); hoisted out of the time loop (gen:14-15).
+static int net_attn_proj(const Net& n) {
+  const Dm& m = n.m;
+  SGG_CUDA(cudaMemsetAsync(n.w.P, 0, (size_t)m.B * m.RP * 4, n.st));
+  sgg_gemm_desc_t g = gd_zero();
+  const long long K = (long long)m.R * m.C;
+  g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 0;
+  g.B = n.sh + n.L.sWa; g.b_rows = K; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
+  g.M = m.B; g.N = m.R; g.nseg = 1; g.seg_klen[0] = (int)K;
+  g.C = n.w.P; g.ldc = m.RP; g.atomic = 1;
+  const int tiles = ((m.B + 127) / 128);
+  int splits = 148 / tiles; if (splits < 1) splits = 1;
+  g.splits = splits; g.block_n = 256;
+  return gemm(g, n.st);
+}
+
+// c0 = h0 = mean_r a (gen:76-77) replicated into `nblk` stream blocks of step 0.
+static int net_init_state(const Net& n, int nblk) {
+  MeanPoolParams p{};
+  p.a = n.a; p.B = n.m.B; p.R = n.m.R; p.nblk = nblk;
+  p.C0 = n.w.Cf; p.CH = n.w.CH; p.ldCH = 2 * n.m.H; p.ch_lo = n.m.H;
+  p.X = n.w.X; p.ldX = 2 * n.KXP; p.x_lo = n.KXP; p.hoff = n.hoff;
+  return meanpool(p, n.st);
+}
+
+// e = P + b + c W_h for rows [row0, row0+nrows) of step t (tangent: edot = cdot W_h into ED).
+static int net_scores(const Net& n, int t, int row0, int nrows, bool tangent) {
+  const Dm& m = n.m;
+  sgg_gemm_desc_t g = gd_zero();
+  g.A = n.w.CH + t * n.sCH() + (long long)row0 * 2 * m.H; g.a_rows = nrows; g.a_cols = 2 * m.H; g.a_ld = 2 * m.H;
+  g.B = n.sh + n.L.sWh; g.b_rows = m.H; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
+  g.M = nrows; g.N = m.R; g.nseg = 2;
+  g.seg_klen[0] = g.seg_klen[1] = m.H; g.seg_a_k[1] = m.H;
+  if (tangent) {
+    g.C = n.w.ED + (long long)t * m.B * m.RP; g.ldc = m.RP;
+  } else {
+    g.C = n.w.EA + t * n.sEA() + (long long)row0 * m.RP; g.ldc = m.RP;
+    g.bias = n.theta + n.L.batt;
+    g.addm = n.w.P; g.ld_addm = m.RP; g.add_mod = m.B;   // row0 is a multiple of B
+  }
+  return gemm(g, n.st);
+}
+
+// q = [z,u,h] K for rows [row0, row0+nrows) of step t.
+static int net_gates(const Net& n, int t, int row0, int nrows) {
+  const Dm& m = n.m;
+  sgg_gemm_desc_t g = gd_zero();
+  g.A = n.w.X + t * n.sX() + (long long)row0 * 2 * n.KXP; g.a_rows = nrows; g.a_cols = 2 * n.KXP; g.a_ld = 2 * n.KXP;
+  g.B = n.sh + n.L.sK; g.b_rows = n.L.KX; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 1;
+  g.M = nrows; g.N = 4 * m.H; g.nseg = 2;
+  g.seg_klen[0] = g.seg_klen[1] = n.KXP; g.seg_a_k[1] = n.KXP;
+  g.C = n.w.Q + t * n.sQ() + (long long)row0 * 4 * m.H; g.ldc = 4 * m.H;
+  return gemm(g, n.st);
+}
+
+// Primal forward over T steps for stream blocks [0, nblk).  Needs: X[t] u-columns filled, P, state 0.
+static int net_forward(const Net& n, int nblk) {
+  const Dm& m = n.m;
+  const int rows = nblk * m.B;
+  for (int t = 0; t < m.T; ++t) {
+    SGG_TRY(net_scores(n, t, 0, rows, false));
+    AttnFwdParams ap{};
+    ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk;
+    for (int v = 0; v < nblk; ++v) { ap.row_blk[v] = v; ap.e_blk[v] = v; }
+    ap.E = n.w.EA + t * n.sEA(); ap.ldE = m.RP;
+    ap.alpha_out = n.w.EA + t * n.sEA(); ap.ldA = m.RP;
+    ap.X = n.w.X + t * n.sX(); ap.ldX = 2 * n.KXP; ap.lo_off = n.KXP;
+    SGG_TRY(attn_fwd(ap, 0, n.st));
+    SGG_TRY(net_gates(n, t, 0, rows));
+    LstmFwdParams lp{};
+    lp.nrows = rows;
+    lp.Q = n.w.Q + t * n.sQ(); lp.ldQ = 4 * m.H;
+    lp.Cin = n.w.Cf + t * n.sCf();
+    lp.ln = n.ln();
+    lp.Cout = n.w.Cf + (t + 1) * n.sCf();
+    lp.CH = n.w.CH + (t + 1) * n.sCH(); lp.ldCH = 2 * m.H; lp.ch_lo = m.H;
+    lp.Xn = n.w.X + (t + 1) * n.sX(); lp.ldX = 2 * n.KXP; lp.x_lo = n.KXP; lp.hoff = n.hoff;
+    if (!n.gen) {
+      lp.wdec = n.theta + n.L.Wdec; lp.bdec = n.theta + n.L.bdec;
+      lp.Y = n.w.Y + t; lp.ldY = m.T;
+    }
+    SGG_TRY(lstm_fwd(lp, n.st));
+  }
+  return 0;
+}
+
+// Tangent forward (D only): tangent rows are block `tblk`, their primal partner block `pblk`.
+static int net_tangent(const Net& n, int pblk, int tblk) {
+  const Dm& m = n.m;
+  for (int t = 0; t < m.T; ++t) {
+    if (t > 0) {  // cdot_0 = 0 => edot_0 = adot_0 = zdot_0 = 0 (z columns of X[0] tangent rows stay zero)
+      SGG_TRY(net_scores(n, t, tblk * m.B, m.B, true));
+      AttnFwdParams ap{};
+      ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = 1;
+      ap.row_blk[0] = tblk; ap.e_blk[0] = 0; ap.ain_blk = pblk;
+      ap.E = n.w.ED + (long long)t * m.B * m.RP; ap.ldE = m.RP;
+      ap.alpha_in = n.w.EA + t * n.sEA();
+      ap.alpha_out = n.w.EA + t * n.sEA(); ap.ldA = m.RP;
+      ap.X = n.w.X + t * n.sX(); ap.ldX = 2 * n.KXP; ap.lo_off = n.KXP;
+      SGG_TRY(attn_fwd(ap, 1, n.st));
+    }
+    SGG_TRY(net_gates(n, t, tblk * m.B, m.B));
+    LstmTanParams lp{};
+    lp.nrows = m.B; lp.prow0 = pblk * m.B; lp.trow0 = tblk * m.B;
+    lp.Q = n.w.Q + t * n.sQ(); lp.ldQ = 4 * m.H;
+    lp.C = n.w.Cf + t * n.sCf();
+    lp.ln = n.ln();
+    lp.Cout = n.w.Cf + (t + 1) * n.sCf();
+    lp.CH = n.w.CH + (t + 1) * n.sCH(); lp.ldCH = 2 * m.H; lp.ch_lo = m.H;
+    lp.Xn = n.w.X + (t + 1) * n.sX(); lp.ldX = 2 * n.KXP; lp.x_lo = n.KXP; lp.hoff = n.hoff;
+    SGG_TRY(lstm_tan(lp, n.st));
+  }
+  return 0;
+}
+
+struct RevCfg {
+  int blk0, nblk;        // primal stream blocks [blk0, blk0+nblk)
+  int tan_pblk, tan_blk; // tangent pairing (or -1)
+  float ybar_blk[4];     // D head upstream per block
+  float ydot_bar;        // D head tangent upstream (lambda)
+  const float* HB;       // G: [T*B, H] h_bar contributions from the logits (row t*B+b), or null
+  bool wgrad;            // accumulate parameter gradients
+};
+
+// Reverse pass over T steps.  With wgrad: LN / head gradients inside lstm_rev, P_bar in attn_rev, and
+// the weight-gradient GEMMs afterwards (contraction over all rows and timesteps at once).
+static int net_reverse(const Net& n, const RevCfg& rc) {
+  const Dm& m = n.m;
+  const bool tan = rc.tan_blk >= 0;
+  const int row0 = rc.blk0 * m.B;
+  const int nrows_p = rc.nblk * m.B;                       // primal rows
+  const int nrows_all = nrows_p + (tan ? m.B : 0);         // tangent block directly follows
+  if (rc.wgrad) SGG_CUDA(cudaMemsetAsync(n.w.PB, 0, (size_t)m.B * m.RP * 4, n.st));
+  for (int t = m.T - 1; t >= 0; --t) {
+    const bool last = (t == m.T - 1);
+    LstmRevParams lp{};
+    lp.B = m.B;
+    lp.Q = n.w.Q + t * n.sQ(); lp.ldQ = 4 * m.H;
+    lp.C = n.w.Cf + t * n.sCf();
+    lp.ln = n.ln();
+    lp.XBn = last ? nullptr : n.w.XB + (t + 1) * n.sXB(); lp.ldXB = n.KXP; lp.hoff = n.hoff;
+    lp.HB = rc.HB ? rc.HB + (long long)t * m.B * m.H : nullptr; lp.ldHB = m.H;
+    lp.CBn = last ? nullptr : n.w.CB + (t + 1) * n.sCf();
+    for (int i = 0; i < 4; ++i) lp.ybar_blk[i] = rc.ybar_blk[i];
+    lp.ydot_bar = rc.ydot_bar;
+    lp.wdec = n.gen ? nullptr : n.theta + n.L.Wdec;
+    lp.QB = n.w.QB + t * n.sQB(); lp.ldQB = 8 * m.H; lp.qb_lo = 4 * m.H;
+    lp.CB = n.w.CB + t * n.sCf();
+    if (rc.wgrad) {
+      for (int i = 0; i < 5; ++i) { lp.dgamma[i] = n.grad + n.L.lng[i]; lp.dbeta[i] = n.grad + n.L.lnb[i]; }
+      if (!n.gen) { lp.dwdec = n.grad + n.L.Wdec; lp.dbdec = n.grad + n.L.bdec; }
+    }
+    // rows without tangent
+    const int plain_blks = tan ? (rc.tan_pblk - rc.blk0) : rc.nblk;
+    if (plain_blks > 0) {
+      lp.nrows = plain_blks * m.B; lp.prow0 = row0; lp.trow0 = 0;
+      SGG_TRY(lstm_rev(lp, false, n.st));
+    }
+    if (tan) {
+      lp.nrows = m.B; lp.prow0 = rc.tan_pblk * m.B; lp.trow0 = rc.tan_blk * m.B;
+      SGG_TRY(lstm_rev(lp, true, n.st));
+    }
+    // x_bar = q_bar K^T  (rows incl. tangent)
+    {
+      sgg_gemm_desc_t g = gd_zero();
+      g.A = n.w.QB + t * n.sQB() + (long long)row0 * 8 * m.H; g.a_rows = nrows_all; g.a_cols = 8 * m.H; g.a_ld = 8 * m.H;
+      g.B = n.sh + n.L.sK; g.b_rows = n.L.KX; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 0;
+      g.M = nrows_all; g.N = n.L.KX; g.nseg = 2;
+      g.seg_klen[0] = g.seg_klen[1] = 4 * m.H; g.seg_a_k[1] = 4 * m.H;
+      g.C = n.w.XB + t * n.sXB() + (long long)row0 * n.KXP; g.ldc = n.KXP;
+      SGG_TRY(gemm(g, n.st));
+    }
+    if (t == 0 && !rc.wgrad) break;  // data path: nothing upstream of the step-0 attention is needed
+    AttnRevParams ap{};
+    ap.a = n.a; ap.B = m.B; ap.R = m.R;
+    ap.nv = rc.nblk + (tan ? 1 : 0);
+    ap.tan_stream = tan ? (rc.tan_pblk - rc.blk0) : -1;
+    for (int v = 0; v < rc.nblk; ++v) ap.row_blk[v] = rc.blk0 + v;
+    if (tan) ap.row_blk[rc.nblk] = rc.tan_blk;
+    ap.XB = n.w.XB + t * n.sXB(); ap.ldXB = n.KXP;
+    ap.alpha = n.w.EA + t * n.sEA(); ap.ldA = m.RP;
+    ap.edot = tan ? n.w.ED + (long long)t * m.B * m.RP : nullptr;
+    ap.EB = n.w.EB + t * n.sEB(); ap.ldEB = 2 * m.RP; ap.lo_off = m.RP;
+    ap.Pbar = rc.wgrad ? n.w.PB : nullptr; ap.ldP = m.RP;
+    SGG_TRY(attn_rev(ap, n.st));
+    if (t > 0) {  // c_bar of step t (in place) += e_bar W_h^T
+      sgg_gemm_desc_t g = gd_zero();
+      g.A = n.w.EB + t * n.sEB() + (long long)row0 * 2 * m.RP; g.a_rows = nrows_all; g.a_cols = 2 * m.RP; g.a_ld = 2 * m.RP;
+      g.B = n.sh + n.L.sWh; g.b_rows = m.H; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 0;
+      g.M = nrows_all; g.N = m.H; g.nseg = 2;
+      g.seg_klen[0] = g.seg_klen[1] = m.RP; g.seg_a_k[1] = m.RP;
+      float* cb = n.w.CB + t * n.sCf() + (long long)row0 * m.H;
+      g.C = cb; g.ldc = m.H; g.addm = cb; g.ld_addm = m.H; g.add_mod = nrows_all;
+      SGG_TRY(gemm(g, n.st));
+    }
+  }
+  if (!rc.wgrad) return 0;
+  // ---------------- weight gradients: one GEMM per kernel over all timesteps / streams
+  const long long rowsT = (long long)m.T * n.NR;   // requires blk0 == 0 and nrows_all == NR
+  SGG_CHECK(rc.blk0 == 0 && nrows_all == n.NR, "net_reverse: weight gradients need all active rows");
+  {  // dK = X^T QB   [KX, 4H], three hi/lo products
+    sgg_gemm_desc_t g = gd_zero();
+    g.A = n.w.X; g.a_rows = rowsT; g.a_cols = 2 * n.KXP; g.a_ld = 2 * n.KXP; g.a_mn_major = 1;
+    g.B = n.w.QB; g.b_rows = rowsT; g.b_cols = 8 * m.H; g.b_ld = 8 * m.H; g.b_mn_major = 1;
+    g.M = n.L.KX; g.N = 4 * m.H; g.nseg = 3;
+    for (int s = 0; s < 3; ++s) g.seg_klen[s] = (int)rowsT;
+    g.seg_b_mn[1] = 4 * m.H; g.seg_a_mn[2] = n.KXP;
+    g.C = n.grad + n.L.K; g.ldc = 4 * m.H; g.atomic = 1; g.splits = 2; g.block_n = 256;
+    SGG_TRY(gemm(g, n.st));
+  }
+  {  // dW_h = C^T EB   [H, R]
+    sgg_gemm_desc_t g = gd_zero();
+    g.A = n.w.CH; g.a_rows = rowsT; g.a_cols = 2 * m.H; g.a_ld = 2 * m.H; g.a_mn_major = 1;
+    g.B = n.w.EB; g.b_rows = rowsT; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
+    g.M = m.H; g.N = m.R; g.nseg = 3;
+    for (int s = 0; s < 3; ++s) g.seg_klen[s] = (int)rowsT;
+    g.seg_b_mn[1] = m.RP; g.seg_a_mn[2] = m.H;
+    g.C = n.grad + n.L.Watt + (long long)m.R * m.C * m.R; g.ldc = m.R; g.atomic = 1; g.block_n = 256;
+    int kb = (int)((rowsT + 63) / 64) * 3;
+    g.splits = kb >= 32 ? 32 : kb;
+    SGG_TRY(gemm(g, n.st));
+  }
+  {  // dW_a = flat(a)^T P_bar  [R*C, R] ; db_att = column sums of P_bar
+    PackParams pk{};
+    pk.rows = m.B; pk.cols = m.R; pk.src = n.w.PB; pk.ld = m.RP;
+    pk.dst = n.w.PBH; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
+    SGG_TRY(pack_hl(pk, n.st));
+    sgg_gemm_desc_t g = gd_zero();
+    const long long K = (long long)m.R * m.C;
+    g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 1;
+    g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
+    g.M = (int)K; g.N = m.R; g.nseg = 2;
+    g.seg_klen[0] = g.seg_klen[1] = m.B; g.seg_b_mn[1] = m.RP;
+    g.C = n.grad + n.L.Watt; g.ldc = m.R; g.atomic = 0; g.block_n = 256;
+    SGG_TRY(gemm(g, n.st));
+    SGG_TRY(colsum(n.w.PB, m.RP, m.B, m.R, n.grad + n.L.batt, n.st));
+  }
+  return 0;
+}
+
+// ============================================================================ generator forward
+static int gen_forward(const Net& g, const Ws& w, const float* noise, bool recompute_proj, float* logits_out) {
+  const Dm& m = g.m;
+  if (recompute_proj) {
+    SGG_TRY(net_attn_proj(g));
+    SGG_TRY(net_init_state(g, 1));
+  }
+  // u_t = noise for every t (gen:81,86): hi/lo into the u columns of X[0..T-1]
+  for (int t = 0; t < m.T; ++t) {
+    PackParams pk{};
+    pk.rows = m.B; pk.cols = m.C; pk.src = noise; pk.ld = m.C;
+    pk.dst = g.w.X + t * g.sX() + g.uoff; pk.ldd = 2 * g.KXP; pk.lo_off = g.KXP;
+    SGG_TRY(pack_hl(pk, g.st));
+  }
+  SGG_TRY(net_forward(g, 1));
+  // logits for all timesteps in one GEMM: rows t*B+b, h_{t+1} lives in X[t+1] (gen:88)
+  sgg_gemm_desc_t d = gd_zero();
+  d.A = g.w.X + g.sX(); d.a_rows = (long long)m.T * m.B; d.a_cols = 2 * g.KXP; d.a_ld = 2 * g.KXP;
+  d.B = g.sh + g.L.sWdec; d.b_rows = m.H; d.b_cols = m.V; d.b_ld = g.L.pWdec; d.b_mn_major = 1;
+  d.M = m.T * m.B; d.N = m.V; d.nseg = 2;
+  d.seg_klen[0] = d.seg_klen[1] = m.H; d.seg_a_k[0] = g.hoff; d.seg_a_k[1] = g.KXP + g.hoff;
+  d.bias = g.theta + g.L.bdec;
+  d.Chl = w.FAKE; d.ld_hl = 2 * m.VP; d.lo_off = m.VP;
+  SGG_TRY(gemm(d, g.st));
+  if (logits_out) {  // [B,T,V] fp32 for the caller: one strided store per timestep
+    for (int t = 0; t < m.T; ++t) {
+      sgg_gemm_desc_t e = d;
+      e.A = g.w.X + (t + 1) * g.sX(); e.a_rows = m.B; e.M = m.B;
+      e.Chl = nullptr; e.C = logits_out + (long long)t * m.V; e.ldc = (long long)m.T * m.V;
+      SGG_TRY(gemm(e, g.st));
+    }
+  }
+  return 0;
+}
+
+// u = x W_emb for a dense [T*B, 2*VP] hi/lo input; result fp32 in w.UF
+static int embed_dense(const Net& d, const Ws& w, const __nv_bfloat16* xhl) {
+  const Dm& m = d.m;
+  sgg_gemm_desc_t g = gd_zero();
+  g.A = xhl; g.a_rows = (long long)m.T * m.B; g.a_cols = 2 * m.VP; g.a_ld = 2 * m.VP;
+  g.B = d.sh + d.L.sWemb; g.b_rows = m.V; g.b_cols = m.E; g.b_ld = d.L.pWemb; g.b_mn_major = 1;
+  g.M = m.T * m.B; g.N = m.E; g.nseg = 2;
+  g.seg_klen[0] = g.seg_klen[1] = m.VP; g.seg_a_k[1] = m.VP;
+  g.C = w.UF; g.ldc = m.EP;
+  return gemm(g, d.st);
+}
+
+// g = u_bar W_emb^T for rows t*B+b, u_bar taken from XB[t][blk] ; result fp32 in w.DFAKE (+hi/lo)
+static int embed_input_grad(const Net& d, const Ws& w, int blk, bool want_hl) {
+  const Dm& m = d.m;
+  PackParams pk{};
+  pk.rows = m.T * m.B; pk.cols = m.E; pk.rpg = m.B;
+  pk.src = d.w.XB + (long long)blk * m.B * d.KXP + d.uoff; pk.ld = d.KXP; pk.gstride = d.sXB();
+  pk.dst = w.UBH; pk.ldd = 2 * m.EP; pk.lo_off = m.EP;
+  SGG_TRY(pack_hl(pk, d.st));
+  sgg_gemm_desc_t g = gd_zero();
+  g.A = w.UBH; g.a_rows = (long long)m.T * m.B; g.a_cols = 2 * m.EP; g.a_ld = 2 * m.EP;
+  g.B = d.sh + d.L.sWemb; g.b_rows = m.V; g.b_cols = m.E; g.b_ld = d.L.pWemb; g.b_mn_major = 0;
+  g.M = m.T * m.B; g.N = m.V; g.nseg = 2;
+  g.seg_klen[0] = g.seg_klen[1] = m.EP; g.seg_a_k[1] = m.EP;
+  g.C = w.DFAKE; g.ldc = m.VP;
+  if (want_hl) { g.Chl = w.DFAKEH; g.ld_hl = 2 * m.VP; g.lo_off = m.VP; }
+  return gemm(g, d.st);
+}
+
+}  // namespace sgg
+
+// ============================================================================ C ABI
+using namespace sgg;
+
+static int check_dims(const sgg_dims_t& d) {
+  SGG_CHECK(d.C == 512 && d.H == 512, "dims: C and H must be 512 (reference gen:68,79); got C=%d H=%d", d.C, d.H);
+  SGG_CHECK(d.R >= 1 && d.R <= 256, "dims: R=%d out of range 1..256", d.R);
+  SGG_CHECK(d.B >= 1 && d.T >= 1 && d.V >= 1 && d.E >= 1, "dims: non-positive B/T/V/E");
+  return 0;
+}
+
+extern "C" int sgg_param_table(int net, const sgg_dims_t* d, sgg_param_entry_t* out, int max_entries,
+                               int* n_entries, int64_t* n_floats, int64_t* n_shadow) {
+  SGG_CHECK(d != nullptr, "sgg_param_table: null dims");
+  SGG_TRY(check_dims(*d));
+  const bool gen = net == 0;
+  const ParamLayout L = param_layout(gen, *d);
+  const char* pre = gen ? "Generator/Generator" : "Discriminator/Discriminator";
+  int n = 0;
+  auto add = [&](const char* suffix, long long off, int rows, int cols, long long soff, int pitch, bool full_name) {
+    if (out && n < max_entries) {
+      sgg_param_entry_t& e = out[n];
+      memset(&e, 0, sizeof(e));
+      if (full_name) snprintf(e.name, sizeof(e.name), "%s", suffix);
+      else snprintf(e.name, sizeof(e.name), "%s/%s", pre, suffix);
+      e.offset = off; e.rows = rows; e.cols = cols; e.shadow_offset = soff; e.shadow_pitch = pitch;
+    }
+    ++n;
+  };
+  char buf[96];
+  add("attention_perceptron/kernel", L.Watt, L.R * L.C + L.H, L.R, L.sWa, L.pAtt, false);
+  add("attention_perceptron/bias", L.batt, 1, L.R, -1, 0, false);
+  add("layer_norm_basic_lstm_cell/kernel", L.K, L.KX, 4 * L.H, L.sK, L.pK, false);
+  for (int i = 0; i < 5; ++i) {
+    snprintf(buf, sizeof(buf), "layer_norm_basic_lstm_cell/%s/gamma", LN_NAMES[i]);
+    add(buf, L.lng[i], 1, L.H, -1, 0, false);
+    snprintf(buf, sizeof(buf), "layer_norm_basic_lstm_cell/%s/beta", LN_NAMES[i]);
+    add(buf, L.lnb[i], 1, L.H, -1, 0, false);
+  }
+  add("decoder/kernel", L.Wdec, L.H, L.OUT, L.sWdec, L.pWdec, false);
+  add("decoder/bias", L.bdec, 1, L.OUT, -1, 0, false);
+  if (!gen) add("Discriminator/W", L.Wemb, L.V, L.E, L.sWemb, L.pWemb, true);
+  if (n_entries) *n_entries = n;
+  if (n_floats) *n_floats = L.total;
+  if (n_shadow) *n_shadow = L.stotal;
+  return 0;
+}
+
+extern "C" int64_t sgg_workspace_bytes(const sgg_dims_t* d) {
+  if (!d || check_dims(*d) != 0) return -1;
+  return ws_layout(*d, nullptr).bytes;
+}
+
+extern "C" int sgg_refresh_shadow(int net, const sgg_dims_t* d, const float* theta, void* shadow, sgg_stream_t stream) {
+  SGG_CHECK(d && theta && shadow, "sgg_refresh_shadow: null argument");
+  SGG_TRY(check_dims(*d));
+  const ParamLayout L = param_layout(net == 0, *d);
+  AdamSeg seg[ADAM_MAX_SEG];
+  const int n = fill_adam_segs(L, seg);
+  for (int i = 0; i < n; ++i) SGG_TRY(refresh_shadow(theta, (__nv_bfloat16*)shadow, seg[i], (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int sgg_adam_step(int net, const sgg_dims_t* d, float* theta, const float* grad, float* m, float* v,
+                             void* shadow, int64_t step, float lr, float beta1, float beta2, float eps,
+                             float grad_scale, sgg_stream_t stream) {
+  SGG_CHECK(d && theta && grad && m && v, "sgg_adam_step: null argument");
+  SGG_CHECK(step >= 1, "sgg_adam_step: step must be >= 1");
+  SGG_TRY(check_dims(*d));
+  const ParamLayout L = param_layout(net == 0, *d);
+  AdamParams p{};
+  p.theta = theta; p.grad = grad; p.m = m; p.v = v; p.shadow = (__nv_bfloat16*)shadow;
+  p.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
+  p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.gscale = grad_scale;
+  p.nseg = fill_adam_segs(L, p.seg);
+  long long mx = 0;
+  for (int i = 0; i < p.nseg; ++i) mx = p.seg[i].n > mx ? p.seg[i].n : mx;
+  return adam(p, mx, (cudaStream_t)stream);
+}
+
+extern "C" int sgg_rng_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream) {
+  SGG_CHECK(out || n == 0, "sgg_rng_fill_normal: null output");
+  return rng_fill(out, n, seed, offset, 1, (cudaStream_t)stream);
+}
+extern "C" int sgg_rng_fill_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream) {
+  SGG_CHECK(out || n == 0, "sgg_rng_fill_uniform: null output");
+  return rng_fill(out, n, seed, offset, 0, (cudaStream_t)stream);
+}
+
+static int check_step(const sgg_step_args_t* a, bool need_d, bool need_labels) {
+  SGG_CHECK(a != nullptr, "step: null args");
+  SGG_TRY(check_dims(a->dims));
+  SGG_CHECK(a->workspace && a->workspace_bytes >= ws_layout(a->dims, nullptr).bytes,
+            "step: workspace too small (%lld < %lld)", (long long)a->workspace_bytes,
+            (long long)ws_layout(a->dims, nullptr).bytes);
+  SGG_CHECK(a->g_theta && a->g_shadow && a->ann_g && a->noise, "step: missing generator inputs");
+  if (need_d) SGG_CHECK(a->d_theta && a->d_shadow && a->ann_d, "step: missing discriminator inputs");
+  if (need_labels) SGG_CHECK(a->labels && a->gp_alpha, "step: missing labels / gp_alpha");
+  SGG_CHECK(a->world >= 1, "step: world must be >= 1");
+  return 0;
+}
+
+// G forward only (gen:74-91 from self.downsampled): logits [B,T,V].
+extern "C" int sgg_gen_forward(const sgg_step_args_t* a, sgg_stream_t stream) {
+  SGG_TRY(check_step(a, false, false));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = ws_layout(a->dims, a->workspace);
+  const Net g = make_net(true, a->dims, a->g_theta, a->g_shadow, nullptr, a->ann_g, w.g, a->dims.B, st);
+  return gen_forward(g, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out);
+}
+
+// D forward on caller-supplied float triples [B,T,V] (disc:73-93): scores [B,T].
+extern "C" int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, float* scores_out, sgg_stream_t stream) {
+  SGG_CHECK(a && triples && scores_out, "sgg_disc_forward: null argument");
+  SGG_TRY(check_dims(a->dims));
+  SGG_CHECK(a->d_theta && a->d_shadow && a->ann_d && a->workspace, "sgg_disc_forward: missing inputs");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ws w = ws_layout(a->dims, a->workspace);
+  const Net d = make_net(false, a->dims, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, a->dims.B, st);
+  const Dm& m = d.m;
+  // triples [B,T,V] -> hi/lo rows t*B+b
+  for (int t = 0; t < m.T; ++t) {
+    PackParams pk{};
+    pk.rows = m.B; pk.cols = m.V; pk.src = triples + (long long)t * m.V; pk.ld = (long long)m.T * m.V;
+    pk.dst = w.TRIH + (long long)t * m.B * 2 * m.VP; pk.ldd = 2 * m.VP; pk.lo_off = m.VP;
+    SGG_TRY(pack_hl(pk, st));
+  }
+  SGG_TRY(embed_dense(d, w, w.TRIH));
+  EmbedMixParams em{};
+  em.B = m.B; em.T = m.T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
+  em.blk_fake = 0; em.blk_real = -1; em.blk_int = -1;
+  em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
+  SGG_TRY(embed_mix(em, st));
+  SGG_TRY(net_attn_proj(d));
+  SGG_TRY(net_init_state(d, 1));
+  SGG_TRY(net_forward(d, 1));
+  SGG_CUDA(cudaMemcpyAsync(scores_out, d.w.Y, (size_t)m.B * m.T * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// One discriminator step (train:365): grads of disc_cost = mean D(G(z)) - mean D(real) + lam * GP
+// w.r.t. every Discriminator* variable into d_grad; scalars[1] = w_disc, scalars[2] = gp.
+extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
+  SGG_TRY(check_step(a, true, true));
+  SGG_CHECK(a->d_grad && a->scalars, "sgg_disc_step: missing d_grad / scalars");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sgg_dims_t& dd = a->dims;
+  const Ws w = ws_layout(dd, a->workspace);
+  const Net g = make_net(true, dd, a->g_theta, a->g_shadow, nullptr, a->ann_g, w.g, dd.B, st);
+  const Net d = make_net(false, dd, a->d_theta, a->d_shadow, a->d_grad, a->ann_d, w.d, 4 * dd.B, st);
+  const Dm& m = d.m;
+  const int B = m.B, T = m.T;
+  const float invBT = 1.0f / ((float)B * a->world * T);
+  SGG_CUDA(cudaMemsetAsync(a->d_grad, 0, (size_t)d.L.total * 4, st));
+  SGG_CUDA(cudaMemsetAsync(a->scalars, 0, 4 * sizeof(float), st));
+  // 1. fake = G(a_g, noise)  (constant for this step)
+  SGG_TRY(gen_forward(g, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out));
+  // 2. embeddings of the three streams
+  SGG_TRY(embed_dense(d, w, w.FAKE));
+  EmbedMixParams em{};
+  em.B = B; em.T = T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
+  em.labels = a->labels; em.Wemb = a->d_theta + d.L.Wemb; em.gp_alpha = a->gp_alpha;
+  em.blk_fake = 0; em.blk_real = 1; em.blk_int = 2;
+  em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
+  SGG_TRY(embed_mix(em, st));
+  // 3. D forward on fake | real | interp (one annotation read per timestep)
+  SGG_TRY(net_attn_proj(d));
+  SGG_TRY(net_init_state(d, 3));
+  SGG_TRY(net_forward(d, 3));
+  LossParams lp{B, T, d.w.Y, 0, 1, invBT, a->scalars};
+  SGG_TRY(losses(lp, st));
+  // 4. g = d sum D(x_hat) / d x_hat : data-path reverse on the interp block
+  RevCfg ig{};
+  ig.blk0 = 2; ig.nblk = 1; ig.tan_pblk = -1; ig.tan_blk = -1; ig.ybar_blk[2] = 1.0f; ig.wgrad = false;
+  SGG_TRY(net_reverse(d, ig));
+  SGG_TRY(embed_input_grad(d, w, 2, false));
+  GpSlopesParams sp{B, T, m.V, w.DFAKE, m.VP, w.slopes, w.coef, a->scalars, 1.0f / ((float)B * a->world)};
+  SGG_TRY(gp_slopes(sp, st));
+  // 5. tangent forward along v = coef * g
+  {
+    // The tangent state at t = 0 is zero (c0/h0 do not depend on the triples); the generator step uses
+    // the same workspace with another row count, so clear those rows explicitly.
+    SGG_CUDA(cudaMemsetAsync(d.w.X + 3LL * B * 2 * d.KXP, 0, (size_t)B * 2 * d.KXP * 2, st));
+    SGG_CUDA(cudaMemsetAsync(d.w.Cf + 3LL * B * m.H, 0, (size_t)B * m.H * 4, st));
+    SGG_CUDA(cudaMemsetAsync(d.w.CH + 3LL * B * 2 * m.H, 0, (size_t)B * 2 * m.H * 2, st));
+    SGG_CUDA(cudaMemsetAsync(d.w.ED, 0, (size_t)B * m.RP * 4, st));
+    PackParams pk{};
+    pk.rows = T * B; pk.cols = m.V; pk.src = w.DFAKE; pk.ld = m.VP;
+    pk.scale = w.coef; pk.smod = B;
+    pk.dst = w.VHL; pk.ldd = 2 * m.VP; pk.lo_off = m.VP;
+    SGG_TRY(pack_hl(pk, st));
+    SGG_TRY(embed_dense(d, w, w.VHL));
+    EmbedMixParams et{};
+    et.B = B; et.T = T; et.E = m.E; et.Uf = w.UF; et.ldUf = m.EP;
+    et.blk_fake = 3; et.blk_real = -1; et.blk_int = -1;
+    et.X = d.w.X; et.ldX = 2 * d.KXP; et.x_lo = d.KXP; et.strideT = d.sX(); et.uoff = d.uoff;
+    SGG_TRY(embed_mix(et, st));
+    SGG_TRY(net_tangent(d, 2, 3));
+  }
+  // 6. one reverse pass over the three primal streams and the tangent
+  RevCfg rv{};
+  rv.blk0 = 0; rv.nblk = 3; rv.tan_pblk = 2; rv.tan_blk = 3;
+  rv.ybar_blk[0] = invBT; rv.ybar_blk[1] = -invBT; rv.ybar_blk[2] = 0.f; rv.ydot_bar = a->lam;
+  rv.wgrad = true;
+  SGG_TRY(net_reverse(d, rv));
+  // 7. embedding gradient: fake^T (ub_f + al ub_i) + scatter(labels, ub_r + (1-al) ub_i) + v^T udot_bar
+  {
+    PackParams pk{};
+    pk.rows = T * B; pk.cols = m.E; pk.rpg = B;
+    pk.src = d.w.XB + d.uoff; pk.ld = d.KXP; pk.gstride = d.sXB();
+    pk.src2 = d.w.XB + 2LL * B * d.KXP + d.uoff; pk.ld2 = d.KXP; pk.gstride2 = d.sXB();
+    pk.mix = a->gp_alpha; pk.mmod = B;
+    pk.dst = w.UBH; pk.ldd = 2 * m.EP; pk.lo_off = m.EP;
+    SGG_TRY(pack_hl(pk, st));
+    PackParams pt{};
+    pt.rows = T * B; pt.cols = m.E; pt.rpg = B;
+    pt.src = d.w.XB + 3LL * B * d.KXP + d.uoff; pt.ld = d.KXP; pt.gstride = d.sXB();
+    pt.dst = w.UDB; pt.ldd = 2 * m.EP; pt.lo_off = m.EP;
+    SGG_TRY(pack_hl(pt, st));
+    for (int which = 0; which < 2; ++which) {
+      sgg_gemm_desc_t q = gd_zero();
+      q.A = which == 0 ? w.FAKE : w.VHL; q.a_rows = (long long)T * B; q.a_cols = 2 * m.VP; q.a_ld = 2 * m.VP; q.a_mn_major = 1;
+      q.B = which == 0 ? w.UBH : w.UDB; q.b_rows = (long long)T * B; q.b_cols = 2 * m.EP; q.b_ld = 2 * m.EP; q.b_mn_major = 1;
+      q.M = m.V; q.N = m.E; q.nseg = 3;
+      for (int s = 0; s < 3; ++s) q.seg_klen[s] = T * B;
+      q.seg_b_mn[1] = m.EP; q.seg_a_mn[2] = m.VP;
+      q.C = a->d_grad + d.L.Wemb; q.ldc = m.E; q.atomic = 1;
+      SGG_TRY(gemm(q, st));
+    }
+    EmbedScatterParams es{};
+    es.B = B; es.T = T; es.E = m.E; es.labels = a->labels; es.gp_alpha = a->gp_alpha;
+    es.XB = d.w.XB; es.ldXB = d.KXP; es.strideT = d.sXB(); es.uoff = d.uoff;
+    es.blk_real = 1; es.blk_int = 2; es.dWemb = a->d_grad + d.L.Wemb;
+    SGG_TRY(embed_scatter(es, st));
+  }
+  return 0;
+}
+
+// One generator step (train:368): grads of gen_cost = -mean D(G(z)) w.r.t. every Generator*
+// variable into g_grad; scalars[3] = gen_cost.
+extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
+  SGG_TRY(check_step(a, true, false));
+  SGG_CHECK(a->g_grad && a->scalars, "sgg_gen_step: missing g_grad / scalars");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sgg_dims_t& dd = a->dims;
+  const Ws w = ws_layout(dd, a->workspace);
+  const Net g = make_net(true, dd, a->g_theta, a->g_shadow, a->g_grad, a->ann_g, w.g, dd.B, st);
+  const Net d = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, dd.B, st);
+  const Dm& m = d.m;
+  const int B = m.B, T = m.T;
+  const float invBT = 1.0f / ((float)B * a->world * T);
+  SGG_CUDA(cudaMemsetAsync(a->g_grad, 0, (size_t)g.L.total * 4, st));
+  SGG_CUDA(cudaMemsetAsync(a->scalars, 0, 4 * sizeof(float), st));
+  SGG_TRY(gen_forward(g, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out));
+  // D(fake), single stream
+  SGG_TRY(embed_dense(d, w, w.FAKE));
+  EmbedMixParams em{};
+  em.B = B; em.T = T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
+  em.blk_fake = 0; em.blk_real = -1; em.blk_int = -1;
+  em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
+  SGG_TRY(embed_mix(em, st));
+  SGG_TRY(net_attn_proj(d));
+  SGG_TRY(net_init_state(d, 1));
+  SGG_TRY(net_forward(d, 1));
+  LossParams lp{B, T, d.w.Y, 0, -1, invBT, a->scalars};
+  SGG_TRY(losses(lp, st));
+  // d gen_cost / d fake through D's data path
+  RevCfg rd{};
+  rd.blk0 = 0; rd.nblk = 1; rd.tan_pblk = -1; rd.tan_blk = -1; rd.ybar_blk[0] = -invBT; rd.wgrad = false;
+  SGG_TRY(net_reverse(d, rd));
+  SGG_TRY(embed_input_grad(d, w, 0, true));
+  // G reverse: h_bar from the logits for all t in one GEMM, then the time loop, then weight grads
+  {
+    sgg_gemm_desc_t q = gd_zero();
+    q.A = w.DFAKEH; q.a_rows = (long long)T * B; q.a_cols = 2 * m.VP; q.a_ld = 2 * m.VP;
+    q.B = g.sh + g.L.sWdec; q.b_rows = m.H; q.b_cols = m.V; q.b_ld = g.L.pWdec; q.b_mn_major = 0;
+    q.M = T * B; q.N = m.H; q.nseg = 2;
+    q.seg_klen[0] = q.seg_klen[1] = m.VP; q.seg_a_k[1] = m.VP;
+    q.C = w.HB; q.ldc = m.H;
+    SGG_TRY(gemm(q, st));
+  }
+  RevCfg rg{};
+  rg.blk0 = 0; rg.nblk = 1; rg.tan_pblk = -1; rg.tan_blk = -1; rg.HB = w.HB; rg.wgrad = true;
+  SGG_TRY(net_reverse(g, rg));
+  {  // dW_dec = H^T dfake [H, V], db_dec = column sums of dfake
+    sgg_gemm_desc_t q = gd_zero();
+    q.A = g.w.X + g.sX(); q.a_rows = (long long)T * B; q.a_cols = 2 * g.KXP; q.a_ld = 2 * g.KXP; q.a_mn_major = 1;
+    q.B = w.DFAKEH; q.b_rows = (long long)T * B; q.b_cols = 2 * m.VP; q.b_ld = 2 * m.VP; q.b_mn_major = 1;
+    q.M = m.H; q.N = m.V; q.nseg = 3;
+    for (int s = 0; s < 3; ++s) { q.seg_klen[s] = T * B; q.seg_a_mn[s] = g.hoff; }
+    q.seg_b_mn[1] = m.VP; q.seg_a_mn[2] = g.KXP + g.hoff;
+    q.C = a->g_grad + g.L.Wdec; q.ldc = m.V; q.atomic = 1; q.splits = 2;
+    SGG_TRY(gemm(q, st));
+    SGG_TRY(colsum(w.DFAKE, m.VP, T * B, m.V, a->g_grad + g.L.bdec, st));
+  }
+  return 0;
+}
+
+// Debug / test accessor: location of an intermediate buffer inside the workspace.
+extern "C" int sgg_ws_lookup(const sgg_dims_t* d, const char* name, int64_t* offset_bytes, int64_t* elem_bytes) {
+  SGG_CHECK(d && name && offset_bytes, "sgg_ws_lookup: null argument");
+  SGG_TRY(check_dims(*d));
+  uint8_t* base = reinterpret_cast<uint8_t*>(uintptr_t(1) << 40);
+  const Ws w = ws_layout(*d, base);
+  struct { const char* n; const void* p; int eb; } tab[] = {
+      {"g.X", w.g.X, 2}, {"g.Cf", w.g.Cf, 4}, {"g.CH", w.g.CH, 2}, {"g.EA", w.g.EA, 4}, {"g.Q", w.g.Q, 4},
+      {"g.P", w.g.P, 4}, {"g.QB", w.g.QB, 2}, {"g.XB", w.g.XB, 4}, {"g.EB", w.g.EB, 2}, {"g.CB", w.g.CB, 4},
+      {"g.PB", w.g.PB, 4},
+      {"d.X", w.d.X, 2}, {"d.Cf", w.d.Cf, 4}, {"d.CH", w.d.CH, 2}, {"d.EA", w.d.EA, 4}, {"d.ED", w.d.ED, 4},
+      {"d.Q", w.d.Q, 4}, {"d.P", w.d.P, 4}, {"d.QB", w.d.QB, 2}, {"d.XB", w.d.XB, 4}, {"d.EB", w.d.EB, 2},
+      {"d.CB", w.d.CB, 4}, {"d.PB", w.d.PB, 4}, {"d.Y", w.d.Y, 4},
+      {"FAKE", w.FAKE, 2}, {"DFAKE", w.DFAKE, 4}, {"DFAKEH", w.DFAKEH, 2}, {"VHL", w.VHL, 2}, {"HB", w.HB, 4},
+      {"UF", w.UF, 4}, {"UBH", w.UBH, 2}, {"UDB", w.UDB, 2}, {"slopes", w.slopes, 4}, {"coef", w.coef, 4}};
+  for (auto& e : tab)
+    if (strcmp(e.n, name) == 0) {
+      *offset_bytes = (int64_t)((const uint8_t*)e.p - base);
+      if (elem_bytes) *elem_bytes = e.eb;
+      return 0;
+    }
+  set_error("sgg_ws_lookup: unknown buffer '%s'", name);
+  return -1;
+}

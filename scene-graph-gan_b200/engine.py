@@ -1,0 +1,114 @@
+"""Step engine: owns the workspace and drives the C-ABI step functions on the current stream."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from ._lib import FLAG_REFRESH_GEN_PROJ, Dims, StepArgs, check, lib, stream_ptr
+from .params import DISC, GEN, ParamBucket, make_dims
+
+
+def _p(t: Optional[torch.Tensor]):
+    return t.data_ptr() if t is not None else None
+
+
+class Engine:
+    """One data-parallel rank of the WGAN-GP hot path (train.py:231-266, 362-368)."""
+
+    def __init__(self, B: int, T: int = 3, V: int = 2000, R: int = 196, E: int = 300, lam: float = 10.0,
+                 world: int = 1, seed: int = 0, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sgg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.dims: Dims = make_dims(B, T, V, R, 512, 512, E)
+        self.B, self.T, self.V, self.R, self.E = B, T, V, R, E
+        self.lam, self.world, self.device = float(lam), int(world), device
+        nbytes = lib().sgg_workspace_bytes
+        nbytes.restype = C.c_int64
+        self.ws_bytes = nbytes(C.byref(self.dims))
+        if self.ws_bytes <= 0:
+            raise RuntimeError("sgg_workspace_bytes: " + lib().sgg_last_error().decode())
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.g = ParamBucket(GEN, self.dims, device)
+        self.d = ParamBucket(DISC, self.dims, device)
+        self.scalars = torch.zeros(4, dtype=torch.float32, device=device)
+        self.noise = torch.zeros(B, 512, dtype=torch.float32, device=device)
+        self.gp_alpha = torch.zeros(B, dtype=torch.float32, device=device)
+        self.logits = torch.zeros(B, T, V, dtype=torch.float32, device=device)
+        self.ann_g = self.ann_d = self.labels = None
+        self._refresh = True
+        self.seed, self._rng_off = seed, 0
+
+    # ------------------------------------------------------------------ inputs
+    def set_batch(self, ann_g: torch.Tensor, ann_d: torch.Tensor, labels: Optional[torch.Tensor]) -> None:
+        """Annotations [B,R,512] (or [B,14,14,512]) bf16 on device; labels [B,T] int64.  The same batch
+        serves the n_critic + 1 steps of an iteration (train.py:185-187)."""
+        for a in (ann_g, ann_d):
+            assert a.dtype == torch.bfloat16 and a.is_cuda and a.is_contiguous()
+            assert a.numel() == self.B * self.R * 512, "annotation shape mismatch"
+        self.ann_g, self.ann_d = ann_g, ann_d
+        if labels is not None:
+            assert labels.dtype == torch.int64 and labels.shape == (self.B, self.T) and labels.is_contiguous()
+        self.labels = labels
+        self._refresh = True
+
+    def sample_noise(self, stream=None) -> None:
+        check(lib().sgg_rng_fill_normal(C.c_void_p(self.noise.data_ptr()), C.c_int64(self.noise.numel()),
+                                        C.c_uint64(self.seed), C.c_uint64(self._rng_off), stream_ptr(stream)), "rng")
+        self._rng_off += (self.noise.numel() + 3) // 4
+
+    def sample_gp_alpha(self, stream=None) -> None:
+        check(lib().sgg_rng_fill_uniform(C.c_void_p(self.gp_alpha.data_ptr()), C.c_int64(self.B),
+                                         C.c_uint64(self.seed ^ 0x9E3779B97F4A7C15), C.c_uint64(self._rng_off),
+                                         stream_ptr(stream)), "rng")
+        self._rng_off += (self.B + 3) // 4
+
+    def _args(self, want_logits=False) -> StepArgs:
+        a = StepArgs()
+        a.dims, a.world, a.lam = self.dims, self.world, self.lam
+        a.g_theta, a.g_shadow, a.g_grad = self.g.theta.data_ptr(), self.g.shadow.data_ptr(), self.g.grad.data_ptr()
+        a.d_theta, a.d_shadow, a.d_grad = self.d.theta.data_ptr(), self.d.shadow.data_ptr(), self.d.grad.data_ptr()
+        a.ann_g, a.ann_d, a.labels = _p(self.ann_g), _p(self.ann_d), _p(self.labels)
+        a.noise, a.gp_alpha = self.noise.data_ptr(), self.gp_alpha.data_ptr()
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
+        a.scalars = self.scalars.data_ptr()
+        a.logits_out = self.logits.data_ptr() if want_logits else None
+        a.flags = FLAG_REFRESH_GEN_PROJ if self._refresh else 0
+        return a
+
+    # ------------------------------------------------------------------ steps
+    def gen_forward(self, stream=None) -> torch.Tensor:
+        a = self._args(want_logits=True)
+        check(lib().sgg_gen_forward(C.byref(a), stream_ptr(stream)), "sgg_gen_forward")
+        self._refresh = False
+        return self.logits
+
+    def disc_forward(self, triples: torch.Tensor, stream=None) -> torch.Tensor:
+        assert triples.dtype == torch.float32 and triples.shape == (self.B, self.T, self.V) and triples.is_contiguous()
+        out = torch.empty(self.B, self.T, dtype=torch.float32, device=self.device)
+        a = self._args()
+        check(lib().sgg_disc_forward(C.byref(a), C.c_void_p(triples.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     stream_ptr(stream)), "sgg_disc_forward")
+        return out
+
+    def disc_step(self, stream=None) -> None:
+        """Gradients of disc_cost into self.d.grad; scalars[1] = w_disc, scalars[2] = gp."""
+        a = self._args()
+        check(lib().sgg_disc_step(C.byref(a), stream_ptr(stream)), "sgg_disc_step")
+        self._refresh = False
+
+    def gen_step(self, stream=None) -> None:
+        """Gradients of gen_cost into self.g.grad; scalars[3] = gen_cost."""
+        a = self._args()
+        check(lib().sgg_gen_step(C.byref(a), stream_ptr(stream)), "sgg_gen_step")
+        self._refresh = False
+
+    def ws_view(self, name: str, shape, dtype) -> torch.Tensor:
+        """Test accessor: a view of a named workspace buffer."""
+        off, eb = C.c_int64(0), C.c_int64(0)
+        check(lib().sgg_ws_lookup(C.byref(self.dims), name.encode(), C.byref(off), C.byref(eb)), "sgg_ws_lookup")
+        n = 1
+        for s in shape:
+            n *= s
+        return self.ws[off.value:off.value + n * eb.value].view(dtype).view(*shape)

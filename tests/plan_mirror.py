@@ -434,7 +434,9 @@ def disc_step(gp, dp, ann_g, ann_d, labels, noise, gp_alpha, lam, T):
         gW += v[:, t].T @ rv["udot_bar"][t]
     grads["Discriminator/W"] = gW
     return {"disc_cost": w_disc + lam * pen, "w_disc": w_disc, "gp": pen, "slopes": slopes,
-            "gp_gradients": g, "grads": grads, "fake": fake}
+            "gp_gradients": g, "grads": grads, "fake": fake,
+            "debug": {"steps": steps, "tans": tans, "rv": rv, "ig": ig, "P": P, "c0": c0, "y": y, "coef": coef,
+                      "v": v, "u_list": u_list, "udot": udot}}
 
 
 def gen_step(gp, dp, ann_g, ann_d, noise, T):
@@ -450,4 +452,5 @@ def gen_step(gp, dp, ann_g, ann_d, noise, T):
     rd = net_reverse(ann_d, wd, dsteps, 1, [ybar] * T, need_weight_grads=False)
     dfake = [ub @ Wemb.T for ub in rd["ubar"]]                           # [B,V] per t
     rg = net_reverse(ann_g, wg, gsteps, 1, dfake)
-    return {"gen_cost": gen_cost, "grads": pack_grads(rg["grads"], "Generator/Generator"), "fake": fake}
+    return {"gen_cost": gen_cost, "grads": pack_grads(rg["grads"], "Generator/Generator"), "fake": fake,
+            "debug": {"gsteps": gsteps, "dsteps": dsteps, "rd": rd, "rg": rg, "dfake": dfake, "y": y}}
