@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the Scene-Graph-GAN WGAN-GP training hot path on B200 (BASELINE.json metric:
+train images/sec for a full G+D iteration = critic_iters D steps + 1 G step on one batch).
+
+    python bench.py --gpus N --steps K --warmup W          # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference ...                    # the reference arithmetic on the host CPU cores
+
+A "step" is one training iteration (train.py:362-368) on one batch of synthetic input of config 2's
+shape (B=256 per GPU, 196x512 annotations, 1 triple, vocab 2000, n_critic=5).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train images/sec (G+D WGAN-GP step)"
+UNIT = "images/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (config 2: 256)")
+    ap.add_argument("--timesteps", type=int, default=3, help="3 x triples (config 2: 1 triple)")
+    ap.add_argument("--vocab", type=int, default=2000)
+    ap.add_argument("--critic-iters", type=int, default=5)
+    ap.add_argument("--lam", type=float, default=10.0)
+    ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample: images per CPU iteration (config 1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-profile", action="store_true", help="only run the roofline kernel micro-timing")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "bf16": float(p["bf16_tflops"]), "bf16_sustained": float(p["bf16_tflops_sustained"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_iterations(args, n_iters: int, warmup: int):
+    """The literal CPU restatement of the reference arithmetic (oracle/sgg_oracle.py: concat-form attention
+    re-evaluated every timestep, autograd double backward for the GP, TF-form Adam), fp32, all host threads.
+    Returns (images/s, seconds per iteration list)."""
+    import torch
+    from oracle import sgg_oracle as O          # allowed here: cpu_baseline / --impl reference legs only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, T, V = args.cpu_batch, args.timesteps, args.vocab
+    gp, dp = O.init_generator_params(V, seed=1), O.init_discriminator_params(V, seed=2)
+    ann_g, ann_d, labels, real = O.synthetic_batch(B, V, T, seed=1234)
+    ag, ad = O.TFAdam(gp), O.TFAdam(dp)
+    g = torch.Generator().manual_seed(0)
+    times = []
+    for it in range(warmup + n_iters):
+        noises = [torch.randn(B, 512, generator=g) for _ in range(args.critic_iters + 1)]
+        alphas = [torch.rand(B, generator=g) for _ in range(args.critic_iters)]
+        t0 = time.perf_counter()
+        O.train_iteration(gp, dp, ag, ad, ann_g, ann_d, real, noises, alphas, args.lam, args.critic_iters, T)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return B * len(times) / sum(times), times, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    val, times, cores = cpu_reference_iterations(args, args.steps, args.warmup)
+    sample = (f"{args.steps} iterations of {args.cpu_batch} images (config 1 batch; n_critic={args.critic_iters}, T={args.timesteps}, "
+              f"V={args.vocab}) after {args.warmup} warm-up; literal un-hoisted restatement, torch fp32, {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": config_name(args), "cpu_sample_batch": args.cpu_batch},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_name(args):
+    return (f"BASELINE configs[1]: full G+D WGAN-GP iteration, batch {args.batch}/GPU, 196x512 annotations, "
+            f"{args.timesteps // 3 if args.timesteps % 3 == 0 else args.timesteps / 3} triple(s) (T={args.timesteps}), "
+            f"vocab {args.vocab}, n_critic={args.critic_iters}")
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def synthetic_host_batches(n, B, T, V, R, seed):
+    """Pinned host batches: bf16 annotations ~ N(0,1) for G and D, uniform labels."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        ag = torch.randn(B, R, 512, generator=g).to(torch.bfloat16).pin_memory()
+        ad = torch.randn(B, R, 512, generator=g).to(torch.bfloat16).pin_memory()
+        lb = torch.randint(0, V, (B, T), generator=g).pin_memory()
+        out.append((ag, ad, lb))
+    return out
+
+
+def launches_per_iteration(trainer):
+    """Counts kernels launched by one iteration with the CUDA profiler-free method: the library keeps a
+    launch counter (sgg_launch_count)."""
+    import ctypes as C
+    from sgg_b200._lib import lib
+    fn = getattr(lib(), "sgg_launch_count", None)
+    if fn is None:
+        return None
+    fn.restype = C.c_int64
+    before = fn()
+    trainer.iteration()
+    return int(fn() - before)
+
+
+def attention_roofline(trainer, args, pk):
+    """Times the dominant HBM-bound kernel family of the step, the attention step forward (K2: softmax over R and
+    context reduction over one read of the annotation tile), alone, with CUDA events on the launching stream, between
+    L2 flushes.  Algorithmic bytes per launch: B * (R*C*2 [bf16 tile] + 4*(R [e] + R [alpha]) * nv + 4*C*nv)."""
+    import ctypes as C
+    import torch
+    from sgg_b200._lib import lib
+    fn = getattr(lib(), "sgg_attn_forward", None)
+    if fn is None:
+        return None
+    B, R = args.batch, 196
+    nv = 3
+    dev = trainer.device
+    a = trainer.eng.ann_d
+    E = torch.randn(nv * B, 256, device=dev)
+    alpha = torch.empty_like(E)
+    X = torch.empty(nv * B, 2 * 1344, dtype=torch.bfloat16, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    times = []
+    for i in range(13):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        rc = fn(C.c_void_p(a.data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv), C.c_void_p(E.data_ptr()),
+                C.c_void_p(alpha.data_ptr()), C.c_int64(256), C.c_void_p(X.data_ptr()), C.c_int64(2 * 1344), C.c_int64(1344),
+                C.c_void_p(st.cuda_stream))
+        e1.record(st)
+        torch.cuda.synchronize()
+        if rc != 0:
+            return None
+        if i >= 3:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    t = statistics.median(times)
+    bytes_alg = B * (R * 512 * 2 + nv * (4 * R + 4 * R + 2 * 2 * 512))
+    ach = bytes_alg / t / 1e9
+    return {"bound": "hbm", "kernel": "attn_fwd_kernel<0> (3 streams share one annotation read)", "achieved": ach, "peak": pk["hbm"],
+            "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "us_per_launch": t * 1e6, "algorithmic_bytes": bytes_alg,
+            "peak_source": pk["source"], "l2": "flushed between launches"}
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sgg_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from sgg_b200.trainer import HotPathTrainer
+    pk = peaks()
+    B, T, V, R = args.batch, args.timesteps, args.vocab, 196
+    tr = HotPathTrainer(B, T, V, critic_iters=args.critic_iters, lam=args.lam, seed=0)
+    n_host = 3
+    host = synthetic_host_batches(n_host, B, T, V, R, seed=1234 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident timing: inputs already in HBM (`value`)
+    dev_batches = [tuple(t.cuda(non_blocking=True) for t in hb) for hb in host]
+    torch.cuda.synchronize()
+    tr.set_batch(*dev_batches[0])
+    launches = launches_per_iteration(tr)
+    for i in range(args.warmup):
+        tr.set_batch(*dev_batches[i % n_host])
+        tr.iteration()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(args.steps):
+        tr.set_batch(*dev_batches[i % n_host])      # a fresh batch every iteration; per-iteration working set >> L2 (126 MB)
+        tr.iteration()
+    e1.record(st)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    secs = e0.elapsed_time(e1) * 1e-3
+    losses = tr.losses()
+
+    # ---------------- end to end: pinned host batches through HotPathTrainer.fit (H2D + loss D2H inside the region)
+    e2e_secs = None
+    if not args.no_e2e:
+        def stream_batches(n):
+            for i in range(n):
+                yield host[i % n_host]
+        for _ in tr.fit(stream_batches(max(1, min(args.warmup, 2)))):
+            pass
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(st)
+        for _loss in tr.fit(stream_batches(args.steps)):
+            pass
+        f1.record(st)
+        barrier()
+        e2e_secs = f0.elapsed_time(f1) * 1e-3
+
+    if world > 1:
+        t = torch.tensor([secs, e2e_secs or 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs, e2e_max = t[0].item(), t[1].item()
+        e2e_secs = e2e_max if e2e_secs is not None else None
+
+    roof = attention_roofline(tr, args, pk) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, times, cores = cpu_reference_iterations(args, 4, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"4 iterations of {args.cpu_batch} images (config 1 batch, same T/V/n_critic) after 1 warm-up; literal "
+                         f"un-hoisted restatement of the reference (oracle/sgg_oracle.py), torch fp32, {cores} threads",
+               "s_per_iteration": sum(times) / len(times)}
+    if rank == 0:
+        images = B * world * args.steps
+        line = {
+            "metric": METRIC, "value": images / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 tensor-core operands (hi/lo split activations), fp32 accumulate/statistics/master weights",
+            "data": "synthetic",
+            "config": {"workload": config_name(args), "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "a different batch every iteration; one iteration streams > 1 GB (>> 126 MB L2), no explicit flush"},
+            "clocks": clocks,
+            "e2e": None if e2e_secs is None else {
+                "value": images / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": tr.h2d_bytes_per_batch,
+                "d2h_bytes_per_step": tr.d2h_bytes_per_iteration,
+                "api": "HotPathTrainer.fit(pinned host batches): double-buffered H2D on a copy stream + 16 B loss read per iteration"},
+            "gpu_launches": None if launches is None else launches * args.steps,
+            "gpu_launches_per_step": launches,
+            "roofline": roof, "cpu_baseline": cpu,
+            "losses_last": losses,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,9 @@ typedef void* sgg_stream_t; /* cudaStream_t */
  * -------------------------------------------------------------------------------------- */
 const char* sgg_last_error(void);
 int sgg_version(void);
+/* Number of CUDA kernels this library has launched (or recorded into a stream capture) in this
+ * process so far.  Lets a caller report how much of a timed region ran in these kernels. */
+int64_t sgg_launch_count(void);
 
 /* ----------------------------------------------------------------------------------------
  * Problem dimensions.  Reference values: R=196 (14x14, gen:74-75), C=512 (gen:68), H=512
@@ -76,6 +79,17 @@ typedef struct sgg_gemm_desc {
 } sgg_gemm_desc_t;
 
 int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Attention step (gen:16-17 / disc:16-17): for each of `nv` streams that share the annotation tile
+ * of sample b (fake / real / interpolate rows v*B+b), alpha = softmax(e) over R and
+ * z_hat = sum_r alpha_r a[b,r,:].  One pass over `a` ([B,R,512] bf16) serves all streams.
+ *   e      [nv*B, ld_e] fp32 scores (= P + c W_h + bias, from sgg_gemm)
+ *   alpha  [nv*B, ld_e] fp32 out (may alias e)
+ *   z_hl   [nv*B, ld_z] bf16 out: z_hat hi part at columns [0,512), lo part at [lo_off, lo_off+512)
+ * -------------------------------------------------------------------------------------- */
+int sgg_attn_forward(const void* a, int32_t B, int32_t R, int32_t nv, const float* e, float* alpha, int64_t ld_e,
+                     void* z_hl, int64_t ld_z, int64_t lo_off, sgg_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------
  * Parameters.  Each network keeps ONE flat fp32 bucket (master weights; gradients and Adam

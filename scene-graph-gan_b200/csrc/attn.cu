@@ -305,7 +305,7 @@ int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
     attn_fwd_kernel<0><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
   else
     attn_fwd_kernel<1><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -318,8 +318,25 @@ int attn_rev(const AttnRevParams& p, cudaStream_t stream) {
     configured = true;
   }
   attn_rev_kernel<<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
 }  // namespace sgg
+
+// Op-level entry point (include/sgg_b200.h): softmax + context reduction for nv streams sharing a tile.
+extern "C" int sgg_attn_forward(const void* a, int32_t B, int32_t R, int32_t nv, const float* e, float* alpha,
+                                int64_t ld_e, void* z_hl, int64_t ld_z, int64_t lo_off, sgg_stream_t stream) {
+  using namespace sgg;
+  SGG_CHECK(a && e && alpha && z_hl, "sgg_attn_forward: null argument");
+  SGG_CHECK(B >= 1 && ld_e >= R && ld_z >= lo_off + AT_C && lo_off >= AT_C, "sgg_attn_forward: bad shape/pitch");
+  SGG_CHECK((ld_z % 2) == 0 && (lo_off % 2) == 0, "sgg_attn_forward: z pitch / lo offset must be even");
+  AttnFwdParams p{};
+  p.a = reinterpret_cast<const __nv_bfloat16*>(a);
+  p.B = B; p.R = R; p.nv = nv;
+  for (int v = 0; v < AT_MAXV; ++v) { p.row_blk[v] = v; p.e_blk[v] = v; }
+  p.E = e; p.ldE = ld_e;
+  p.alpha_out = alpha; p.ldA = ld_e;
+  p.X = reinterpret_cast<__nv_bfloat16*>(z_hl); p.ldX = ld_z; p.lo_off = lo_off;
+  return attn_fwd(p, 0, reinterpret_cast<cudaStream_t>(stream));
+}

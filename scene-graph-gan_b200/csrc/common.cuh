@@ -9,6 +9,7 @@ namespace sgg {
 
 // ---------------------------------------------------------------- error plumbing (host)
 void set_error(const char* fmt, ...);
+void note_launch();  // counts kernels launched by this library (sgg_launch_count)
 #define SGG_CHECK(cond, ...)                      \
   do {                                            \
     if (!(cond)) {                                \
@@ -24,6 +25,12 @@ void set_error(const char* fmt, ...);
                        __FILE__, __LINE__);                                         \
       return -2;                                                                    \
     }                                                                               \
+  } while (0)
+// After every <<<>>>: checks the launch and counts it.
+#define SGG_LAUNCHED()                 \
+  do {                                 \
+    SGG_CUDA(cudaGetLastError());      \
+    ::sgg::note_launch();              \
   } while (0)
 #define SGG_TRY(call)          \
   do {                         \

@@ -244,7 +244,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   dim3 grid((kp.M + BM - 1) / BM, (kp.N + BN - 1) / BN, splits);
   kern<<<grid, GEMM_THREADS, S::BYTES, stream>>>(tmA, tmB, kp);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 

@@ -1,4 +1,5 @@
 // Host-side plumbing of libsgg_b200: error string, version, TMA tensor-map encoding.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cudaTypedefs.h>
@@ -16,6 +17,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -53,3 +58,4 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* gptr, uint64_t rows, uint64_
 
 extern "C" const char* sgg_last_error(void) { return sgg::g_err; }
 extern "C" int sgg_version(void) { return 100; }
+extern "C" int64_t sgg_launch_count(void) { return (int64_t)sgg::launch_count(); }

@@ -472,13 +472,13 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_rev_kernel(const LstmRevParam
 int lstm_fwd(const LstmFwdParams& p, cudaStream_t stream) {
   if (p.nrows <= 0) return 0;
   lstm_fwd_kernel<<<(p.nrows + LS_WARPS - 1) / LS_WARPS, LS_THREADS, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 int lstm_tan(const LstmTanParams& p, cudaStream_t stream) {
   if (p.nrows <= 0) return 0;
   lstm_tan_kernel<<<(p.nrows + LS_WARPS - 1) / LS_WARPS, LS_THREADS, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 int lstm_rev(const LstmRevParams& p, bool tan, cudaStream_t stream) {
@@ -488,7 +488,7 @@ int lstm_rev(const LstmRevParams& p, bool tan, cudaStream_t stream) {
     lstm_rev_kernel<true><<<grid, LS_THREADS, 0, stream>>>(p);
   else
     lstm_rev_kernel<false><<<grid, LS_THREADS, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 

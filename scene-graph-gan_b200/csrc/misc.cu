@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) meanpool_kernel(const MeanPoolParams p) {
 
 int meanpool(const MeanPoolParams& p, cudaStream_t stream) {
   meanpool_kernel<<<p.B, 256, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -93,7 +93,7 @@ int pack_hl(const PackParams& p, cudaStream_t stream) {
   if (n <= 0) return 0;
   const int grid = (int)llmin((n + 255) / 256, 148 * 8);
   pack_hl_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -141,7 +141,7 @@ int embed_mix(const EmbedMixParams& p, cudaStream_t stream) {
   const long long n = (long long)p.T * p.B * p.E;
   const int grid = (int)llmin((n + 255) / 256, 148 * 8);
   embed_mix_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -169,7 +169,7 @@ int embed_scatter(const EmbedScatterParams& p, cudaStream_t stream) {
   const long long n = (long long)p.T * p.B * p.E;
   const int grid = (int)llmin((n + 255) / 256, 148 * 8);
   embed_scatter_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) gp_slopes_kernel(const GpSlopesParams p) 
 }
 int gp_slopes(const GpSlopesParams& p, cudaStream_t stream) {
   gp_slopes_kernel<<<p.B, 256, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
 }
 int losses(const LossParams& p, cudaStream_t stream) {
   loss_kernel<<<1, 256, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -246,7 +246,7 @@ __global__ void colsum_kernel(const float* src, long long ld, int rows, int cols
 int colsum(const float* src, long long ld, int rows, int cols, float* out, cudaStream_t stream) {
   dim3 grid((cols + 127) / 128, min(rows, 32));
   colsum_kernel<<<grid, 128, 0, stream>>>(src, ld, rows, cols, out);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -313,7 +313,7 @@ int adam(const AdamParams& p, long long max_n, cudaStream_t stream) {
   const int gx = (int)llmin((max_n / 4 + 255) / 256, 148 * 4);
   dim3 grid(gx > 0 ? gx : 1, p.nseg);
   adam_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -328,7 +328,7 @@ int refresh_shadow(const float* theta, __nv_bfloat16* shadow, const AdamSeg& sg,
   if (sg.sh_off < 0 || sg.n <= 0) return 0;
   const int grid = (int)llmin((sg.n + 255) / 256, 148 * 8);
   shadow_kernel<<<grid, 256, 0, stream>>>(theta, shadow, sg);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 
@@ -371,7 +371,7 @@ int rng_fill(float* out, long long n, uint64_t seed, uint64_t offset, int mode, 
   if (n <= 0) return 0;
   const long long quads = (n + 3) / 4;
   rng_fill_kernel<<<(int)((quads + 255) / 256), 256, 0, stream>>>(out, n, seed, offset, mode);
-  SGG_CUDA(cudaGetLastError());
+  SGG_LAUNCHED();
   return 0;
 }
 

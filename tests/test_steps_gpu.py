@@ -1,0 +1,321 @@
+"""Parity of the CUDA hot path (through the C ABI) with the CPU oracle on identical weights and inputs.
+
+Tolerance (BASELINE.json north_star): 1e-3 relative, fp32 reference vs bf16-operand / fp32-accumulate
+kernels.  We compare against the oracle in fp64 and use the per-tensor relative L2 error
+||g - g_ref|| / ||g_ref|| (hard part 6); losses / GP are compared as scalars.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _scalar_close(got, ref, tol=TOL):
+    return abs(float(got) - float(ref)) <= tol * (abs(float(ref)) + 1e-2)
+
+
+def _setup(B, T, V, R=196, seed=0, lam=10.0):
+    from tests.util import make_engine, make_problem
+    prob = make_problem(B, T, V, R=R, seed=seed, dtype=torch.float64)
+    return prob, make_engine(prob, B, T, V, R=R, lam=lam)
+
+
+CASES = [(8, 3, 96, 196), (5, 4, 130, 196), (130, 3, 200, 196), (3, 2, 2000, 100), (1, 1, 8, 1)]
+
+
+@pytest.mark.parametrize("B,T,V,R", CASES)
+def test_generator_forward_logits(B, T, V, R):
+    """gen:74-91: raw logits [B,T,V]."""
+    from oracle import sgg_oracle as O
+    from tests.util import rel
+    prob, eng = _setup(B, T, V, R)
+    ref = O.generator_forward(prob["gp"], prob["ann_g"], prob["noise"], T)
+    got = eng.gen_forward()
+    torch.cuda.synchronize()
+    assert got.shape == (B, T, V)
+    assert rel(got, ref) < TOL
+
+
+@pytest.mark.parametrize("B,T,V,R", CASES[:4])
+def test_discriminator_forward_scores(B, T, V, R):
+    """disc:73-93 on arbitrary float triples (soft one-hot inputs, disc:86-87)."""
+    from oracle import sgg_oracle as O
+    from tests.util import rel
+    prob, eng = _setup(B, T, V, R)
+    g = torch.Generator().manual_seed(3)
+    tri = torch.randn(B, T, V, generator=g, dtype=torch.float64)
+    ref = O.discriminator_forward(prob["dp"], tri, prob["ann_d"], T).squeeze(-1)
+    got = eng.disc_forward(tri.float().cuda().contiguous())
+    torch.cuda.synchronize()
+    assert rel(got, ref) < TOL
+    # one-hot reals (train:173)
+    ref = O.discriminator_forward(prob["dp"], prob["real"], prob["ann_d"], T).squeeze(-1)
+    got = eng.disc_forward(prob["real"].float().cuda().contiguous())
+    torch.cuda.synchronize()
+    assert rel(got, ref) < TOL
+
+
+@pytest.mark.parametrize("B,T,V,R", CASES)
+def test_disc_step_matches_oracle(B, T, V, R):
+    """train:365 (minus Adam): w_disc, GP and every Discriminator* gradient, incl. the double backward."""
+    from oracle import sgg_oracle as O
+    from tests.util import rel
+    lam = 10.0
+    prob, eng = _setup(B, T, V, R, lam=lam)
+    ref = O.disc_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["real"], prob["noise"],
+                            prob["alpha"], lam, T)
+    eng.disc_step()
+    torch.cuda.synchronize()
+    sc = eng.scalars.cpu()
+    assert _scalar_close(sc[1], ref["w_disc"])
+    assert _scalar_close(sc[2], ref["gp"])
+    assert rel(eng.ws_view("slopes", (B,), torch.float32), ref["slopes"]) < TOL
+    gv = eng.d.grad_views()
+    assert set(gv) == set(ref["grads"])
+    bias_key = "Discriminator/Discriminator/decoder/bias"       # analytically zero: absolute check
+    for k, v in ref["grads"].items():
+        if k == bias_key:
+            assert abs(float(gv[k])) < 1e-5
+        else:
+            assert rel(gv[k], v) < TOL, k
+
+
+@pytest.mark.parametrize("B,T,V,R", CASES)
+def test_gen_step_matches_oracle(B, T, V, R):
+    """train:368 (minus Adam): gen_cost and every Generator* gradient (through D's input path)."""
+    from oracle import sgg_oracle as O
+    from tests.util import rel
+    prob, eng = _setup(B, T, V, R)
+    ref = O.gen_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["noise"], T)
+    eng.gen_step()
+    torch.cuda.synchronize()
+    assert _scalar_close(eng.scalars[3].item(), ref["gen_cost"])
+    gv = eng.g.grad_views()
+    for k, v in ref["grads"].items():
+        assert rel(gv[k], v) < TOL, k
+
+
+def test_steps_can_interleave_on_one_workspace():
+    """D step, G step, D step on the same engine (train:362-368 order) give the same answers as fresh engines."""
+    prob, eng = _setup(6, 3, 50)
+    eng.disc_step(); torch.cuda.synchronize()
+    d1 = eng.d.grad.clone(); s1 = eng.scalars.clone()
+    eng.gen_step(); torch.cuda.synchronize()
+    g1 = eng.g.grad.clone()
+    eng.disc_step(); torch.cuda.synchronize()
+    assert ((eng.d.grad - d1).norm() / d1.norm()).item() < 1e-5
+    assert torch.allclose(eng.scalars[1:3], s1[1:3], rtol=1e-5, atol=1e-7)
+    eng.gen_step(); torch.cuda.synchronize()
+    assert ((eng.g.grad - g1).norm() / g1.norm()).item() < 1e-5
+
+
+def test_one_sided_penalty_inactive():
+    """Slopes below the target: GP = 0 and the step reduces to the plain Wasserstein gradient."""
+    from oracle import sgg_oracle as O
+    from tests.util import make_engine, make_problem, rel
+    B, T, V = 6, 3, 50
+    prob = make_problem(B, T, V, dtype=torch.float64)
+    prob["dp"]["Discriminator/W"] = (prob["dp"]["Discriminator/W"] * 1e-3).bfloat16().double()
+    eng = make_engine(prob, B, T, V)
+    ref = O.disc_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["real"], prob["noise"],
+                            prob["alpha"], 10.0, T)
+    assert float(ref["gp"]) == 0.0
+    eng.disc_step()
+    torch.cuda.synchronize()
+    assert eng.scalars[2].item() == 0.0
+    gv = eng.d.grad_views()
+    for k, v in ref["grads"].items():
+        if v.norm() > 0 and not k.endswith("decoder/bias"):
+            assert rel(gv[k], v) < TOL, k
+
+
+@pytest.mark.parametrize("fixture", ["step_B4_T3_V64_R12.json", "step_B3_T5_V40_R30.json"])
+def test_against_committed_golden_vectors(fixture):
+    """CUDA path vs tests/golden (oracle fp64 outputs; inputs regenerated from the recorded seeds)."""
+    from tests.golden.make_golden import sample_index
+    with open(os.path.join(HERE, "golden", fixture)) as f:
+        gold = json.load(f)
+    c = gold["config"]
+    prob, eng = _setup(c["B"], c["T"], c["V"], c["R"], seed=c["seed"], lam=c["lam"])
+    logits = eng.gen_forward().cpu().double().reshape(-1)
+    ref = torch.tensor(gold["logits"], dtype=torch.float64)
+    assert ((logits - ref).norm() / ref.norm()).item() < TOL
+    eng.disc_step(); torch.cuda.synchronize()
+    assert _scalar_close(eng.scalars[1].item(), gold["w_disc"])
+    assert _scalar_close(eng.scalars[2].item(), gold["gp"])
+    sl = eng.ws_view("slopes", (c["B"],), torch.float32).cpu().double()
+    assert ((sl - torch.tensor(gold["slopes"])).norm() / torch.tensor(gold["slopes"]).norm()).item() < TOL
+    dgv = {k: v.clone() for k, v in eng.d.grad_views().items()}
+    eng.gen_step(); torch.cuda.synchronize()
+    assert _scalar_close(eng.scalars[3].item(), gold["gen_cost"])
+    for views, recs in ((dgv, gold["d_grads"]), (eng.g.grad_views(), gold["g_grads"])):
+        for k, rec in recs.items():
+            flat = views[k].detach().cpu().double().reshape(-1)
+            if rec["norm"] < 1e-12:
+                continue
+            assert abs(flat.norm().item() - rec["norm"]) <= TOL * rec["norm"], k
+            idx = torch.from_numpy(sample_index(k, flat.numel()))
+            got, want = flat[idx], torch.tensor(rec["samples"], dtype=torch.float64)
+            # sampled entries: error measured against the tensor's RMS magnitude
+            rms = rec["norm"] / math.sqrt(flat.numel())
+            assert ((got - want).abs().max() / rms).item() < 20 * TOL, k
+
+
+def test_adam_matches_tf_update_rule():
+    """sgg_adam_step vs oracle TFAdam (train:258-259) over 3 steps, plus the bf16 shadow refresh."""
+    from oracle import sgg_oracle as O
+    from tests.util import rel
+    prob, eng = _setup(2, 3, 40, R=8)
+    for bucket, params in ((eng.d, prob["dp"]), (eng.g, prob["gp"])):
+        p = {k: v.clone().float() for k, v in params.items()}
+        opt = O.TFAdam(p)
+        gen = torch.Generator().manual_seed(9)
+        for step in range(3):
+            grads = {k: torch.randn(v.shape, generator=gen) * (10.0 ** (step - 3)) for k, v in p.items()}
+            for k, v in bucket.grad_views().items():
+                v.copy_(grads[k])
+            bucket.adam_step()
+            opt.step(p, grads)
+        torch.cuda.synchronize()
+        for k, v in bucket.views().items():
+            assert rel(v, p[k]) < 1e-6, k
+        # shadow == bf16(theta) for every GEMM operand
+        for name, off, rows, cols, soff, pitch in bucket.entries:
+            if soff < 0 or name.endswith("attention_perceptron/kernel"):
+                continue
+            sh = bucket.shadow[soff:soff + rows * pitch].view(rows, pitch)[:, :cols]
+            th = bucket.theta[off:off + rows * cols].view(rows, cols)
+            assert torch.equal(sh, th.to(torch.bfloat16)), name
+
+
+def test_rng_streams():
+    """Philox fills (gen:81 noise, tfgan alpha): moments, range, determinism, offset continuity."""
+    import ctypes as C
+    from sgg_b200._lib import lib, stream_ptr
+    n = 1 << 20
+    a = torch.empty(n, device="cuda"); b = torch.empty(n, device="cuda")
+    lib().sgg_rng_fill_normal(C.c_void_p(a.data_ptr()), C.c_int64(n), C.c_uint64(7), C.c_uint64(0), stream_ptr())
+    lib().sgg_rng_fill_normal(C.c_void_p(b.data_ptr()), C.c_int64(n), C.c_uint64(7), C.c_uint64(0), stream_ptr())
+    assert torch.equal(a, b)
+    assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1) < 5e-3
+    assert abs((a ** 4).mean().item() - 3.0) < 0.1
+    lib().sgg_rng_fill_normal(C.c_void_p(b.data_ptr()), C.c_int64(n // 2), C.c_uint64(7), C.c_uint64(n // 8), stream_ptr())
+    assert torch.equal(b[: n // 2], a[n // 2:])           # offset counts 4-value Philox blocks
+    lib().sgg_rng_fill_normal(C.c_void_p(b.data_ptr()), C.c_int64(n), C.c_uint64(8), C.c_uint64(0), stream_ptr())
+    assert not torch.equal(a, b)
+    lib().sgg_rng_fill_uniform(C.c_void_p(a.data_ptr()), C.c_int64(n), C.c_uint64(7), C.c_uint64(0), stream_ptr())
+    assert a.min().item() >= 0.0 and a.max().item() < 1.0
+    assert abs(a.mean().item() - 0.5) < 2e-3 and abs(a.var().item() - 1 / 12) < 2e-3
+
+
+def test_two_training_iterations_track_the_oracle():
+    """train:362-368 with Adam: 2 iterations x (2 critic steps + 1 G step) on one batch (train:185-187)."""
+    from oracle import sgg_oracle as O
+    B, T, V, R, n_critic, lam = 4, 3, 48, 20, 2, 10.0
+    prob, eng = _setup(B, T, V, R, lam=lam)
+    gp = {k: v.clone().float() for k, v in prob["gp"].items()}
+    dp = {k: v.clone().float() for k, v in prob["dp"].items()}
+    ag, ad = O.TFAdam(gp), O.TFAdam(dp)
+    gen = torch.Generator().manual_seed(21)
+    for it in range(2):
+        noises = [torch.randn(B, 512, generator=gen) for _ in range(n_critic + 1)]
+        alphas = [torch.rand(B, generator=gen) for _ in range(n_critic)]
+        log = O.train_iteration(gp, dp, ag, ad, prob["ann_g"].float(), prob["ann_d"].float(), prob["real"].float(),
+                                noises, alphas, lam, n_critic, T)
+        eng._refresh = True
+        for i in range(n_critic):
+            eng.noise.copy_(noises[i]); eng.gp_alpha.copy_(alphas[i])
+            eng.disc_step()
+            cost = eng.scalars[1].item() + lam * eng.scalars[2].item()
+            assert _scalar_close(cost, log["disc_cost"][i], 5e-3)
+            eng.d.adam_step()
+        eng.noise.copy_(noises[n_critic])
+        eng.gen_step()
+        assert _scalar_close(eng.scalars[3].item(), log["gen_cost"], 5e-3)
+        eng.g.adam_step()
+        eng._refresh = True
+    torch.cuda.synchronize()
+    # Adam's first steps are sign-like (m / sqrt(v)): entries whose gradient is at rounding level may flip,
+    # so the applied UPDATE is compared loosely and the weights themselves tightly.
+    for bucket, ref, ref0 in ((eng.g, gp, prob["gp"]), (eng.d, dp, prob["dp"])):
+        for k, v in bucket.views().items():
+            th, r, r0 = v.cpu().double(), ref[k].double(), ref0[k].double()
+            assert ((th - r).norm() / (r.norm() + 1e-30)).item() < 1e-4, k
+            upd = (r - r0).norm().item()
+            if upd > 0 and not k.endswith("decoder/bias"):
+                assert ((th - r).norm().item() / upd) < 0.1, k
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 sizes (B=256, T=3, V=2000): size-independent properties instead of the oracle.
+    (1) attention rows sum to 1; (2) a global batch split over two data-parallel shards (world=2) gives
+    gradients that SUM to the single-shard gradients (the data-parallel contract of SURVEY 8e);
+    (3) the real-stream scores of the D step equal sgg_disc_forward on the one-hot triples."""
+    from sgg_b200.engine import Engine
+    B, T, V, R = 256, 3, 2000, 196
+    g = torch.Generator().manual_seed(5)
+    ann_g = torch.randn(B, R, 512, generator=g).bfloat16().cuda()
+    ann_d = torch.randn(B, R, 512, generator=g).bfloat16().cuda()
+    labels = torch.randint(0, V, (B, T), generator=g).cuda()
+    noise = torch.randn(B, 512, generator=g).cuda()
+    alpha = torch.rand(B, generator=g).cuda()
+    full = Engine(B, T, V, R, lam=10.0, world=1)
+    full.g.init_reference(1); full.d.init_reference(2)
+    full.set_batch(ann_g, ann_d, labels); full.noise.copy_(noise); full.gp_alpha.copy_(alpha)
+    full.disc_step(); torch.cuda.synchronize()
+    dfull, sfull = full.d.grad.clone(), full.scalars.clone()
+    NR = 4 * B
+    al = full.ws_view("d.EA", (T, NR, 256), torch.float32)[:, :3 * B, :R]
+    assert torch.allclose(al.sum(-1), torch.ones_like(al[..., 0]), atol=1e-5)
+    assert (al >= 0).all()
+    y_real = full.ws_view("d.Y", (NR, T), torch.float32)[B:2 * B].clone()
+    onehot = torch.nn.functional.one_hot(labels, V).float().contiguous()
+    y2 = full.disc_forward(onehot); torch.cuda.synchronize()
+    assert ((y2 - y_real).norm() / y_real.norm()).item() < 1e-4
+    full.gen_step(); torch.cuda.synchronize()
+    gfull, cost_full = full.g.grad.clone(), full.scalars[3].item()
+    half = Engine(B // 2, T, V, R, lam=10.0, world=2)
+    half.g.load_state_dict(full.g.state_dict()); half.d.load_state_dict(full.d.state_dict())
+    dsum, gsum, ssum = torch.zeros_like(dfull), torch.zeros_like(gfull), torch.zeros(4, device="cuda")
+    for s in range(2):
+        sl = slice(s * B // 2, (s + 1) * B // 2)
+        half.set_batch(ann_g[sl].contiguous(), ann_d[sl].contiguous(), labels[sl].contiguous())
+        half.noise.copy_(noise[sl]); half.gp_alpha.copy_(alpha[sl])
+        half.disc_step(); torch.cuda.synchronize()
+        dsum += half.d.grad; ssum[1:3] += half.scalars[1:3]
+        half.gen_step(); torch.cuda.synchronize()
+        gsum += half.g.grad; ssum[3] += half.scalars[3]
+    assert ((dsum - dfull).norm() / dfull.norm()).item() < 1e-4
+    assert ((gsum - gfull).norm() / gfull.norm()).item() < 1e-4
+    assert torch.allclose(ssum[1:3], sfull[1:3], rtol=1e-4, atol=1e-6)
+    assert abs(ssum[3].item() - cost_full) < 1e-4 * (abs(cost_full) + 1e-2)
+
+
+@pytest.mark.parametrize("B,R,nv", [(7, 196, 3), (3, 100, 1), (2, 29, 4)])
+def test_attention_step_kernel(B, R, nv):
+    """sgg_attn_forward vs gen:16-17: alpha = softmax(e), z_hat = sum_r alpha_r a_r; nv streams share one tile."""
+    import ctypes as C
+    from sgg_b200._lib import check, lib, stream_ptr
+    g = torch.Generator().manual_seed(B * 1000 + R)
+    a = torch.randn(B, R, 512, generator=g).bfloat16()
+    e = torch.randn(nv * B, 256, generator=g) * 3
+    a_d, e_d = a.cuda(), e.cuda()
+    alpha = torch.empty_like(e_d)
+    z = torch.zeros(nv * B, 1024, dtype=torch.bfloat16, device="cuda")
+    check(lib().sgg_attn_forward(C.c_void_p(a_d.data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv),
+                                 C.c_void_p(e_d.data_ptr()), C.c_void_p(alpha.data_ptr()), C.c_int64(256),
+                                 C.c_void_p(z.data_ptr()), C.c_int64(1024), C.c_int64(512), stream_ptr()), "attn")
+    torch.cuda.synchronize()
+    ref_al = torch.softmax(e[:, :R].double(), -1)
+    ref_z = torch.einsum("sbr,brc->sbc", ref_al.reshape(nv, B, R), a.double()).reshape(nv * B, 512)
+    got_z = z[:, :512].float().double() + z[:, 512:].float().double()
+    assert (alpha[:, :R].cpu().double() - ref_al).abs().max().item() < 1e-6
+    assert ((got_z.cpu() - ref_z).norm() / ref_z.norm()).item() < 1e-5
