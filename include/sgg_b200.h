@@ -47,6 +47,7 @@ typedef struct sgg_dims {
   int32_t C; /* annotation channels */
   int32_t H; /* LSTM units */
   int32_t E; /* embedding width */
+  int32_t S; /* fake-logit slots kept in the workspace = max critic steps per sgg_train_iteration (0/1: one) */
 } sgg_dims_t;
 
 /* ----------------------------------------------------------------------------------------
@@ -76,6 +77,11 @@ typedef struct sgg_gemm_desc {
   float alpha;
   int32_t block_n; /* 0 = auto, else 64/128/256 */
   int32_t splits;  /* 0/1 = none; >1 requires atomic */
+  /* optional output row permutation (out_d0 > 0): result row m is stored at row
+   *   (m / out_d0) * out_s0 + ((m % out_d0) / out_d1) * out_s1 + (m % out_d1)
+   * of C / Chl (e.g. [t][stream][b] rows -> [stream][t][b]). */
+  int32_t out_d0, out_d1;
+  int64_t out_s0, out_s1;
 } sgg_gemm_desc_t;
 
 int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream);
@@ -93,7 +99,8 @@ int sgg_attn_forward(const void* a, int32_t B, int32_t R, int32_t nv, const floa
 
 /* ----------------------------------------------------------------------------------------
  * Parameters.  Each network keeps ONE flat fp32 bucket (master weights; gradients and Adam
- * moments use the same layout) plus a bf16 "shadow" bucket holding the GEMM operands with
+ * moments use the same layout) plus a bf16 "shadow" bucket holding the GEMM operands as a
+ * hi/lo pair (w ~= hi + lo to 2^-17: three bf16 tensor-core products reproduce the fp32 product),
  * rows padded to a 16-byte pitch.  The table reproduces the reference's TF variable names
  * (train:262-263 splits them by the "Generator"/"Discriminator" prefix):
  *   <scope>/attention_perceptron/{kernel [R*C+H, R], bias [R]}                  (gen:15)
@@ -107,8 +114,8 @@ typedef struct sgg_param_entry {
   int64_t offset;
   int32_t rows, cols;
   int64_t shadow_offset; /* -1: tensor has no bf16 shadow (used in fp32) */
-  int32_t shadow_pitch;
-  int32_t reserved;
+  int32_t shadow_pitch;  /* row pitch (elements) of the shadow */
+  int32_t shadow_rows;   /* hi part = shadow rows [0, rows); lo part = rows [shadow_rows, shadow_rows + rows) */
 } sgg_param_entry_t;
 
 int sgg_param_table(int net, const sgg_dims_t* d, sgg_param_entry_t* out, int max_entries,
@@ -165,6 +172,46 @@ int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, float* scor
 int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream);
 /* train:368 minus the optimizer: d gen_cost / d Generator* into g_grad, scalars[3] = gen_cost. */
 int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Data-parallel exchange (the reference is single-GPU).  One process per GPU; the
+ * batch is sharded over ranks and every loss is normalised by the GLOBAL batch (args.world), so
+ * the only exchange is a sum of the flat gradient bucket before each optimiser step.  The
+ * communicator is an NCCL communicator owned by this library (libnccl.so.2 is resolved at run
+ * time from the process, i.e. the copy PyTorch ships); the 128-byte unique id is created on
+ * rank 0 and distributed by the caller (torch.distributed broadcast).
+ * -------------------------------------------------------------------------------------- */
+#define SGG_COMM_ID_BYTES 128
+int sgg_comm_unique_id(void* id_out /* SGG_COMM_ID_BYTES */);
+int sgg_comm_init(const void* id, int32_t rank, int32_t world, void** comm_out);
+int sgg_comm_destroy(void* comm);
+int sgg_comm_allreduce_sum(void* comm, float* buf, int64_t n, sgg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
+ * One training iteration (train:362-368 on one batch, train:185-187): critic_iters x
+ * { D step, [allreduce], Adam(D) } then { G step, [allreduce], Adam(G) }.  Noise (gen:81) and
+ * the gradient-penalty interpolation coefficients are drawn on the device, fresh for every
+ * step.  The generator forwards of all critic steps are batched (the generator is constant
+ * while the critic trains).  step.noise / step.gp_alpha / step.scalars / step.flags are ignored.
+ * The call depends on the host only through its arguments: the iteration counter that drives
+ * the RNG position and the Adam step numbers lives in `counters`, so a stream capture of one
+ * call can be replayed as a CUDA graph.
+ * -------------------------------------------------------------------------------------- */
+typedef struct sgg_iter_args {
+  sgg_step_args_t step;
+  int32_t critic_iters;              /* train:30 CRITIC_ITERS; <= step.dims.S */
+  float* g_m; float* g_v;            /* Adam moments, generator bucket layout */
+  float* d_m; float* d_v;            /* Adam moments, discriminator bucket layout */
+  float lr, beta1, beta2, eps;       /* train:258-259: 1e-4, 0.5, 0.9 (eps 1e-8, TF form) */
+  uint64_t seed;                     /* Philox key of this rank */
+  int64_t* counters;                 /* device int64[1]: iterations done so far (zero-initialised by the caller) */
+  float* noise_all;                  /* device [(critic_iters+1), B, C] scratch */
+  float* gp_alpha_all;               /* device [critic_iters, B] scratch */
+  float* scalars_all;                /* device [(critic_iters+1), 4]: per-step {-, w_disc, gp, gen_cost} */
+  void* comm;                        /* sgg_comm_init handle, or NULL for a single GPU */
+} sgg_iter_args_t;
+
+int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t stream);
 
 /* Test/debug accessor: byte offset of a named intermediate buffer inside the workspace. */
 int sgg_ws_lookup(const sgg_dims_t* d, const char* name, int64_t* offset_bytes, int64_t* elem_bytes);

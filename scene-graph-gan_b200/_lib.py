@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("block_n", C.c_int32),
         ("splits", C.c_int32),
+        ("out_d0", C.c_int32), ("out_d1", C.c_int32), ("out_s0", C.c_int64), ("out_s1", C.c_int64),
     ]
 
 
@@ -65,12 +66,12 @@ def stream_ptr(stream=None) -> C.c_void_p:
 
 
 class Dims(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "T", "V", "R", "C", "H", "E")]
+    _fields_ = [(n, C.c_int32) for n in ("B", "T", "V", "R", "C", "H", "E", "S")]
 
 
 class ParamEntry(C.Structure):
     _fields_ = [("name", C.c_char * 96), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32),
-                ("shadow_offset", C.c_int64), ("shadow_pitch", C.c_int32), ("reserved", C.c_int32)]
+                ("shadow_offset", C.c_int64), ("shadow_pitch", C.c_int32), ("shadow_rows", C.c_int32)]
 
 
 class StepArgs(C.Structure):
@@ -85,11 +86,23 @@ class StepArgs(C.Structure):
     ]
 
 
+class IterArgs(C.Structure):
+    _fields_ = [
+        ("step", StepArgs), ("critic_iters", C.c_int32),
+        ("g_m", C.c_void_p), ("g_v", C.c_void_p), ("d_m", C.c_void_p), ("d_v", C.c_void_p),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("seed", C.c_uint64), ("counters", C.c_void_p),
+        ("noise_all", C.c_void_p), ("gp_alpha_all", C.c_void_p), ("scalars_all", C.c_void_p),
+        ("comm", C.c_void_p),
+    ]
+
+
 FLAG_REFRESH_GEN_PROJ = 1
 
 # every symbol include/sgg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "sgg_last_error", "sgg_version", "sgg_launch_count", "sgg_gemm", "sgg_attn_forward", "sgg_param_table", "sgg_refresh_shadow", "sgg_adam_step",
     "sgg_rng_fill_normal", "sgg_rng_fill_uniform", "sgg_workspace_bytes", "sgg_gen_forward",
-    "sgg_disc_forward", "sgg_disc_step", "sgg_gen_step", "sgg_ws_lookup",
+    "sgg_disc_forward", "sgg_disc_step", "sgg_gen_step", "sgg_ws_lookup", "sgg_train_iteration",
+    "sgg_comm_unique_id", "sgg_comm_init", "sgg_comm_destroy", "sgg_comm_allreduce_sum",
 ]

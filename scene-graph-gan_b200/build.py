@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + ["-ldl"]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

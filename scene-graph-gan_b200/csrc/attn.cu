@@ -18,13 +18,14 @@ constexpr int AT_THREADS = 256;
 constexpr int AT_CHUNK_ROWS = 28;   // 196 = 7 * 28
 constexpr int AT_STAGES = 3;
 constexpr int AT_RMAX = 256;
-constexpr int AT_MAXV = 4;
+constexpr int AT_MAXV = 8;          // streams served by one forward tile read (generator: n_critic+1 noise draws)
+constexpr int AT_MAXV_REV = 4;      // streams served by one reverse tile read
 constexpr int AT_STAGE_BYTES = AT_CHUNK_ROWS * AT_C * 2;  // 28 KB
 
 struct AttnSmem {
   __align__(128) uint8_t stage[AT_STAGES][AT_STAGE_BYTES];
-  __align__(16) float w[AT_RMAX][AT_MAXV];   // fwd: weights per region and stream; rev: alpha_bar
-  __align__(16) float eb[AT_MAXV][AT_RMAX];  // rev: e_bar per stream
+  __align__(16) float w[AT_RMAX][AT_MAXV];       // fwd: weights per region and stream; rev: alpha_bar (first 4)
+  __align__(16) float eb[AT_MAXV_REV][AT_RMAX];  // rev: e_bar per stream
   __align__(8) uint64_t full[AT_STAGES];
 };
 
@@ -51,7 +52,7 @@ struct AttnFwdParams {
   __nv_bfloat16* X; long long ldX; long long lo_off;  // z written at X[row, 0:C] (hi) and +lo_off (lo)
 };
 
-template <int MODE>
+template <int MODE, int NV>
 __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -65,7 +66,10 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParam
     mbar_fence_init();
     for (int c = 0; c < min(AT_STAGES, nchunks); ++c) attn_issue_chunk(sm, a_b, c, R);
   }
-  // ---- per-stream weights (softmax or its tangent), one warp per stream
+  // ---- per-stream weights (softmax or its tangent), one warp per stream (8 warps >= AT_MAXV streams)
+  if (warp >= p.nv && warp < NV) {
+    for (int r = lane; r < R; r += 32) sm.w[r][warp] = 0.f;   // unused stream slots of the float4 reads
+  }
   if (warp < p.nv) {
     const long long row = (long long)p.row_blk[warp] * p.B + b;
     const float* e = p.E + ((long long)p.e_blk[warp] * p.B + b) * p.ldE;
@@ -116,9 +120,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParam
   }
   __syncthreads();
   // ---- z_v = sum_r w_v[r] a[r,:] ; thread owns channels 2*tid, 2*tid+1
-  float acc[AT_MAXV][2];
+  float acc[NV][2];
 #pragma unroll
-  for (int v = 0; v < AT_MAXV; ++v) acc[v][0] = acc[v][1] = 0.f;
+  for (int v = 0; v < NV; ++v) acc[v][0] = acc[v][1] = 0.f;
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % AT_STAGES;
     mbar_wait(&sm.full[st], (c / AT_STAGES) & 1);
@@ -129,17 +133,20 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParam
     for (int r = 0; r < rows; ++r) {
       const uint32_t pk = tile[r * (AT_C / 2) + tid];
       const float a0 = bf16lo_to_f32(pk), a1 = bf16hi_to_f32(pk);
-      const float4 w = *reinterpret_cast<const float4*>(sm.w[r0 + r]);
-      acc[0][0] = fmaf(w.x, a0, acc[0][0]); acc[0][1] = fmaf(w.x, a1, acc[0][1]);
-      acc[1][0] = fmaf(w.y, a0, acc[1][0]); acc[1][1] = fmaf(w.y, a1, acc[1][1]);
-      acc[2][0] = fmaf(w.z, a0, acc[2][0]); acc[2][1] = fmaf(w.z, a1, acc[2][1]);
-      acc[3][0] = fmaf(w.w, a0, acc[3][0]); acc[3][1] = fmaf(w.w, a1, acc[3][1]);
+#pragma unroll
+      for (int v4 = 0; v4 < NV / 4; ++v4) {
+        const float4 w = *reinterpret_cast<const float4*>(&sm.w[r0 + r][4 * v4]);
+        acc[4 * v4 + 0][0] = fmaf(w.x, a0, acc[4 * v4 + 0][0]); acc[4 * v4 + 0][1] = fmaf(w.x, a1, acc[4 * v4 + 0][1]);
+        acc[4 * v4 + 1][0] = fmaf(w.y, a0, acc[4 * v4 + 1][0]); acc[4 * v4 + 1][1] = fmaf(w.y, a1, acc[4 * v4 + 1][1]);
+        acc[4 * v4 + 2][0] = fmaf(w.z, a0, acc[4 * v4 + 2][0]); acc[4 * v4 + 2][1] = fmaf(w.z, a1, acc[4 * v4 + 2][1]);
+        acc[4 * v4 + 3][0] = fmaf(w.w, a0, acc[4 * v4 + 3][0]); acc[4 * v4 + 3][1] = fmaf(w.w, a1, acc[4 * v4 + 3][1]);
+      }
     }
     __syncthreads();
     if (tid == 0 && c + AT_STAGES < nchunks) attn_issue_chunk(sm, a_b, c + AT_STAGES, R);
   }
 #pragma unroll
-  for (int v = 0; v < AT_MAXV; ++v) {
+  for (int v = 0; v < NV; ++v) {
     if (v < p.nv) {
       const long long row = (long long)p.row_blk[v] * p.B + b;
       __nv_bfloat16 h0, l0, h1, l1;
@@ -159,7 +166,7 @@ struct AttnRevParams {
   int B, R;
   int nv;                   // number of z_bar vectors (primal streams [+ 1 tangent adjoint, last])
   int tan_stream;           // index v of the stream that carries the tangent, or -1
-  int row_blk[AT_MAXV];     // row block of each vector in XB / alpha / EB
+  int row_blk[AT_MAXV_REV]; // row block of each vector in XB / alpha / EB
   const float* XB; long long ldXB;        // z_bar = XB[row, 0:C]
   const float* alpha; long long ldA;      // saved alpha
   const float* edot;                      // [B, ldA] tangent of e for tan_stream (row b)
@@ -181,9 +188,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParam
     for (int c = 0; c < min(AT_STAGES, nchunks); ++c) attn_issue_chunk(sm, a_b, c, R);
   }
   // z_bar slices: lane owns channels [lane*8, +8) and [256 + lane*8, +8)
-  float zb[AT_MAXV][16];
+  float zb[AT_MAXV_REV][16];
 #pragma unroll
-  for (int v = 0; v < AT_MAXV; ++v) {
+  for (int v = 0; v < AT_MAXV_REV; ++v) {
     if (v < p.nv) {
       const float* z = p.XB + ((long long)p.row_blk[v] * p.B + b) * p.ldXB;
 #pragma unroll
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParam
     const int rows = min(AT_CHUNK_ROWS, R - r0);
     for (int r = warp; r < rows; r += AT_THREADS / 32) {
       const uint4* rowp = reinterpret_cast<const uint4*>(sm.stage[st] + (size_t)r * AT_C * 2);
-      float d[AT_MAXV] = {0.f, 0.f, 0.f, 0.f};
+      float d[AT_MAXV_REV] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint4 pk = rowp[h * 32 + lane];
@@ -215,14 +222,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParam
         for (int e = 0; e < 4; ++e) {
           const float a0 = bf16lo_to_f32(w4[e]), a1 = bf16hi_to_f32(w4[e]);
 #pragma unroll
-          for (int v = 0; v < AT_MAXV; ++v) {
+          for (int v = 0; v < AT_MAXV_REV; ++v) {
             d[v] = fmaf(a0, zb[v][h * 8 + 2 * e], d[v]);
             d[v] = fmaf(a1, zb[v][h * 8 + 2 * e + 1], d[v]);
           }
         }
       }
 #pragma unroll
-      for (int v = 0; v < AT_MAXV; ++v) d[v] = warp_sum(d[v]);
+      for (int v = 0; v < AT_MAXV_REV; ++v) d[v] = warp_sum(d[v]);
       if (lane == 0) *reinterpret_cast<float4*>(sm.w[r0 + r]) = make_float4(d[0], d[1], d[2], d[3]);
     }
     __syncthreads();
@@ -294,24 +301,27 @@ static size_t attn_smem_bytes() { return sizeof(AttnSmem) + 128; }
 
 int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
   SGG_CHECK(p.R > 0 && p.R <= AT_RMAX, "attn_fwd: R=%d out of range (1..%d)", p.R, AT_RMAX);
-  SGG_CHECK(p.nv >= 1 && p.nv <= AT_MAXV, "attn_fwd: nv=%d out of range", p.nv);
+  SGG_CHECK(p.nv >= 1 && p.nv <= (mode == 0 ? AT_MAXV : 4), "attn_fwd: nv=%d out of range", p.nv);
   static bool configured = false;
   if (!configured) {
-    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
-    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
     configured = true;
   }
-  if (mode == 0)
-    attn_fwd_kernel<0><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+  if (mode == 0 && p.nv > 4)
+    attn_fwd_kernel<0, 8><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+  else if (mode == 0)
+    attn_fwd_kernel<0, 4><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
   else
-    attn_fwd_kernel<1><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+    attn_fwd_kernel<1, 4><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
   SGG_LAUNCHED();
   return 0;
 }
 
 int attn_rev(const AttnRevParams& p, cudaStream_t stream) {
   SGG_CHECK(p.R > 0 && p.R <= AT_RMAX, "attn_rev: R=%d out of range (1..%d)", p.R, AT_RMAX);
-  SGG_CHECK(p.nv >= 1 && p.nv <= AT_MAXV, "attn_rev: nv=%d out of range", p.nv);
+  SGG_CHECK(p.nv >= 1 && p.nv <= AT_MAXV_REV, "attn_rev: nv=%d out of range", p.nv);
   static bool configured = false;
   if (!configured) {
     SGG_CUDA(cudaFuncSetAttribute(attn_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));

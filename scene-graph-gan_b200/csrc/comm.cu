@@ -1,0 +1,106 @@
+// Data-parallel gradient exchange: a thin NCCL communicator owned by the library.
+// The reference is single-GPU (train:412-418); this is the one exchange step data parallelism adds:
+// sum of the flat gradient bucket over ranks before every optimiser step, over NVLink 5 / NVSwitch.
+// libnccl.so.2 is resolved at run time (dlopen) so that the library loads on machines without NCCL and uses the
+// same NCCL build as the hosting PyTorch process.
+#include <dlfcn.h>
+
+#include "common.cuh"
+#include "../../include/sgg_b200.h"
+
+namespace sgg {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[SGG_COMM_ID_BYTES]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclSum = 0 };
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok;
+};
+
+static NcclApi* nccl() {
+  static NcclApi api{};
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    }
+  }
+  return api.ok ? &api : nullptr;
+}
+
+#define SGG_NCCL(call)                                                                       \
+  do {                                                                                       \
+    ncclResult_t r__ = (call);                                                               \
+    if (r__ != 0) {                                                                          \
+      ::sgg::set_error("%s failed: %s", #call, nccl()->GetErrorString(r__));                 \
+      return -3;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+struct Comm {
+  ncclComm_t nccl;
+  int rank, world;
+};
+
+int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  SGG_CHECK(c && buf && n >= 0, "comm_allreduce: bad argument");
+  if (c->world == 1 || n == 0) return 0;
+  SGG_NCCL(nccl()->AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, c->nccl, st));
+  return 0;
+}
+
+}  // namespace sgg
+
+using namespace sgg;
+
+extern "C" int sgg_comm_unique_id(void* id_out) {
+  SGG_CHECK(id_out != nullptr, "sgg_comm_unique_id: null output");
+  SGG_CHECK(nccl() != nullptr, "sgg_comm_unique_id: libnccl.so.2 not found in this process");
+  SGG_NCCL(nccl()->GetUniqueId(reinterpret_cast<ncclUniqueId*>(id_out)));
+  return 0;
+}
+
+extern "C" int sgg_comm_init(const void* id, int32_t rank, int32_t world, void** comm_out) {
+  SGG_CHECK(id && comm_out, "sgg_comm_init: null argument");
+  SGG_CHECK(world >= 1 && rank >= 0 && rank < world, "sgg_comm_init: bad rank %d / world %d", rank, world);
+  SGG_CHECK(nccl() != nullptr, "sgg_comm_init: libnccl.so.2 not found in this process");
+  Comm* c = new Comm{nullptr, rank, world};
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  ncclResult_t r = nccl()->CommInitRank(&c->nccl, world, uid, rank);
+  if (r != 0) {
+    set_error("ncclCommInitRank failed: %s", nccl()->GetErrorString(r));
+    delete c;
+    return -3;
+  }
+  *comm_out = c;
+  return 0;
+}
+
+extern "C" int sgg_comm_destroy(void* comm) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  if (!c) return 0;
+  if (c->nccl && nccl()) nccl()->CommDestroy(c->nccl);
+  delete c;
+  return 0;
+}
+
+extern "C" int sgg_comm_allreduce_sum(void* comm, float* buf, int64_t n, sgg_stream_t stream) {
+  return comm_allreduce(comm, buf, (long long)n, reinterpret_cast<cudaStream_t>(stream));
+}

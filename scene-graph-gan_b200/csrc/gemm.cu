@@ -25,6 +25,7 @@ struct GemmKParams {
   const float* bias;
   const float* addm; long long ld_addm; int add_mod;
   float alpha;
+  int rm_d0, rm_d1; long long rm_s0, rm_s1;   // output row permutation (rm_d0 == 0: identity)
 };
 
 template <int BN>
@@ -156,6 +157,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const bool row_ok = row < p.M;
+    long long orow = row;
+    if (p.rm_d0 > 0) {
+      const int rem = row % p.rm_d0;
+      orow = (long long)(row / p.rm_d0) * p.rm_s0 + (long long)(rem / p.rm_d1) * p.rm_s1 + (rem % p.rm_d1);
+    }
     const float* addrow = p.addm ? p.addm + (long long)(row % p.add_mod) * p.ld_addm : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -180,7 +186,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (full || col0 + j < p.N) v[j] += __ldg(addrow + col0 + j);
       }
       if (p.C) {
-        float* crow = p.C + (long long)row * p.ldc + col0;
+        float* crow = p.C + orow * p.ldc + col0;
         if (p.atomic) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -196,7 +202,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if (p.Chl) {
-        __nv_bfloat16* hrow = p.Chl + (long long)row * p.ld_hl + col0;
+        __nv_bfloat16* hrow = p.Chl + orow * p.ld_hl + col0;
         __nv_bfloat16* lrow = hrow + p.lo_off;
         if (full && ((p.ld_hl & 7) == 0) && ((p.lo_off & 7) == 0) &&
             ((reinterpret_cast<uintptr_t>(p.Chl) & 15) == 0)) {
@@ -283,6 +289,7 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
   kp.bias = d.bias;
   kp.addm = d.addm; kp.ld_addm = d.ld_addm; kp.add_mod = d.add_mod > 0 ? d.add_mod : 1;
   kp.alpha = d.alpha;
+  kp.rm_d0 = d.out_d0; kp.rm_d1 = d.out_d1 > 0 ? d.out_d1 : 1; kp.rm_s0 = d.out_s0; kp.rm_s1 = d.out_s1;
   int splits = d.splits > 1 ? d.splits : 1;
   if (splits > kp.total_kb) splits = kp.total_kb;
   SGG_CHECK(splits == 1 || (d.atomic && d.C && !d.Chl && !d.bias && !d.addm),

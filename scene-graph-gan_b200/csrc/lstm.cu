@@ -216,9 +216,14 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_tan_kernel(const LstmTanParam
 }
 
 // ------------------------------------------------------------------------------------ reverse
+// One launch handles `n_plain` first-order rows (row = prow0 + i) and `n_tan` rows that carry a tangent
+// (primal row tan_prow0 + j, tangent row trow0 + j).  One warp per row, rows strided over the grid.
+// Parameter gradients (5 LN gammas/betas, D head) are reduced without shared-memory atomics: every warp
+// owns a [11][512] fp32 slab in shared memory, the CTA sums its slabs, and only the CTA totals go to
+// global memory as fp32 reductions.
 struct LstmRevParams {
-  int nrows;                 // primal rows handled: row = prow0 + i ; tangent partner = trow0 + i (TAN only)
-  int prow0, trow0;
+  int n_plain, prow0;
+  int n_tan, tan_prow0, trow0;
   int B;                     // rows per stream block (for ybar_blk lookup)
   const float* Q; long long ldQ;
   const float* C;            // [rows,H] c_in (primal and tangent rows)
@@ -227,7 +232,7 @@ struct LstmRevParams {
   const float* XBn; long long ldXB; int hoff;   // next step's x_bar (h columns), nullable
   const float* HB; long long ldHB;              // extra h_bar [rows,H] (G: dfake W_dec^T), nullable
   const float* CBn;                             // next step's total c_bar [rows,H], nullable
-  float ybar_blk[4];                            // D head: y_bar per stream block (0 if unused)
+  float ybar_blk[8];                            // D head: y_bar per stream block (0 if unused)
   float ydot_bar;                               // D head tangent adjoint (lambda) for the tangent rows
   const float* wdec;                            // D head weights (nullable)
   // outputs
@@ -238,234 +243,254 @@ struct LstmRevParams {
   float* dwdec; float* dbdec;
 };
 
-struct LstmRevSmem {
-  float dg[5][LH];
-  float db[5][LH];
-  float dw[LH];
-  float dbd;
-};
+constexpr int LR_WARPS = 8;
+constexpr int LR_THREADS = LR_WARPS * 32;
+constexpr int LR_SLAB = 11 * LH;   // dgamma[5], dbeta[5], dwdec
+
+// slab accumulate: lane owns columns lane*4 + 128*i (conflict-free float4 accesses)
+__device__ __forceinline__ void slab_acc(float* slab_vec, const V16& v, bool first) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4* p = reinterpret_cast<float4*>(slab_vec + lane * 4 + 128 * i);
+    float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    if (!first) {
+      const float4 o = *p;
+      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+    }
+    *p = t;
+  }
+}
 
 template <bool TAN>
-__global__ void __launch_bounds__(LS_THREADS) lstm_rev_kernel(const LstmRevParams p) {
-  __shared__ LstmRevSmem sm;
-  const bool wgrad = p.dgamma[0] != nullptr;
-  const int lane = threadIdx.x & 31;
-  if (wgrad) {
-    for (int k = threadIdx.x; k < (int)(sizeof(LstmRevSmem) / 4); k += LS_THREADS) reinterpret_cast<float*>(&sm)[k] = 0.f;
-    __syncthreads();
-  }
-  const int i = blockIdx.x * LS_WARPS + (threadIdx.x >> 5);
-  if (i < p.nrows) {
-    const long long prow = p.prow0 + i, trow = p.trow0 + i;
-    const float* q = p.Q + prow * p.ldQ;
-    const float* qd = p.Q + trow * p.ldQ;
-    V16 x, n, g, bt, act[4], actd[4], ad[4];
-    float r;
-    // ---- phase A: recompute forward (and tangent) gate activations
+__device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, long long prow, long long trow, float* slab,
+                                             bool first, float& dbd_acc) {
+  const bool wgrad = slab != nullptr;
+  const float* q = p.Q + prow * p.ldQ;
+  const float* qd = p.Q + trow * p.ldQ;
+  V16 x, n, g, bt, act[4], actd[4], ad[4];
+  float r;
+  // ---- phase A: recompute forward (and tangent) gate activations
 #pragma unroll
-    for (int G = 0; G < 4; ++G) {
-      ld16(q + G * LH, x);
-      ln_norm(x, n, r);
-      ld16(p.ln.gamma[G], g);
-      ld16(p.ln.beta[G], bt);
-      V16 nd;
-      if (TAN) {
-        V16 xd;
-        ld16(qd + G * LH, xd);
-        ln_proj(n, r, xd, nd);
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float a = fmaf(n[j], g[j], bt[j]);
-        if (TAN) ad[G][j] = nd[j] * g[j];
-        if (G == 1) {
-          const float t = tanhf_(a);
-          act[G][j] = t;
-          if (TAN) actd[G][j] = (1.f - t * t) * ad[G][j];
-        } else {
-          const float s = sigmoidf_(G == 2 ? a + FORGET_BIAS_F : a);
-          act[G][j] = s;
-          if (TAN) actd[G][j] = s * (1.f - s) * ad[G][j];
-        }
-      }
+  for (int G = 0; G < 4; ++G) {
+    ld16(q + G * LH, x);
+    ln_norm(x, n, r);
+    ld16(p.ln.gamma[G], g);
+    ld16(p.ln.beta[G], bt);
+    V16 nd;
+    if (TAN) {
+      V16 xd;
+      ld16(qd + G * LH, xd);
+      ln_proj(n, r, xd, nd);
     }
-    V16 c, cd, cp, cpd, nc, ncd;
-    float rc;
-    ld16(p.C + prow * LH, c);
-    if (TAN) ld16(p.C + trow * LH, cd);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      cp[j] = fmaf(c[j], act[2][j], act[0][j] * act[1][j]);
-      if (TAN) cpd[j] = cd[j] * act[2][j] + c[j] * actd[2][j] + actd[0][j] * act[1][j] + act[0][j] * actd[1][j];
+      const float a = fmaf(n[j], g[j], bt[j]);
+      if (TAN) ad[G][j] = nd[j] * g[j];
+      if (G == 1) {
+        const float t = tanhf_(a);
+        act[G][j] = t;
+        if (TAN) actd[G][j] = (1.f - t * t) * ad[G][j];
+      } else {
+        const float s = sigmoidf_(G == 2 ? a + FORGET_BIAS_F : a);
+        act[G][j] = s;
+        if (TAN) actd[G][j] = s * (1.f - s) * ad[G][j];
+      }
     }
-    ln_norm(cp, nc, rc);
-    if (TAN) ln_proj(nc, rc, cpd, ncd);
-    ld16(p.ln.gamma[4], g);
-    ld16(p.ln.beta[4], bt);
-    // ---- phase B: cell-level reverse
-    V16 hb, cnb, hdb, cndb;
-    ld16_or_zero(p.XBn ? p.XBn + prow * p.ldXB + p.hoff : nullptr, hb);
-    if (p.HB) {
-      ld16(p.HB + prow * p.ldHB, x);
+  }
+  V16 c, cd, cp, cpd, nc, ncd;
+  float rc;
+  ld16(p.C + prow * LH, c);
+  if (TAN) ld16(p.C + trow * LH, cd);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) hb[j] += x[j];
-    }
-    const float yb = p.ybar_blk[(int)(prow / p.B) & 3];
-    V16 wd;
+  for (int j = 0; j < 16; ++j) {
+    cp[j] = fmaf(c[j], act[2][j], act[0][j] * act[1][j]);
+    if (TAN) cpd[j] = cd[j] * act[2][j] + c[j] * actd[2][j] + actd[0][j] * act[1][j] + act[0][j] * actd[1][j];
+  }
+  ln_norm(cp, nc, rc);
+  if (TAN) ln_proj(nc, rc, cpd, ncd);
+  ld16(p.ln.gamma[4], g);
+  ld16(p.ln.beta[4], bt);
+  // ---- phase B: cell-level reverse
+  V16 hb, cnb, hdb, cndb;
+  ld16_or_zero(p.XBn ? p.XBn + prow * p.ldXB + p.hoff : nullptr, hb);
+  if (p.HB) {
+    ld16(p.HB + prow * p.ldHB, x);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) hb[j] += x[j];
+  }
+  const float yb = p.ybar_blk[(int)(prow / p.B) & 7];
+  V16 wd;
+  if (p.wdec) {
+    ld16(p.wdec, wd);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) hb[j] = fmaf(yb, wd[j], hb[j]);
+  }
+  ld16_or_zero(p.CBn ? p.CBn + prow * LH : nullptr, cnb);
+  if (TAN) {
+    ld16_or_zero(p.XBn ? p.XBn + trow * p.ldXB + p.hoff : nullptr, hdb);
     if (p.wdec) {
-      ld16(p.wdec, wd);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) hb[j] = fmaf(yb, wd[j], hb[j]);
+      for (int j = 0; j < 16; ++j) hdb[j] = fmaf(p.ydot_bar, wd[j], hdb[j]);
     }
-    ld16_or_zero(p.CBn ? p.CBn + prow * LH : nullptr, cnb);
-    if (TAN) {
-      ld16_or_zero(p.XBn ? p.XBn + trow * p.ldXB + p.hoff : nullptr, hdb);
-      if (p.wdec) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) hdb[j] = fmaf(p.ydot_bar, wd[j], hdb[j]);
-      }
-      ld16_or_zero(p.CBn ? p.CBn + trow * LH : nullptr, cndb);
-    }
-    V16 ncb, ncdb;      // adjoints of nc (normalised state) and its tangent
-    V16 yb_[4], ydb_[4];  // adjoints of the gate activations (and of their tangents)
-    {
-      V16 dgs, dbs, dwv;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float cn = fmaf(nc[j], g[j], bt[j]);
-        const float tc = tanhf_(cn);
-        const float dt = 1.f - tc * tc;
-        const float so = act[3][j];
-        float tcb = hb[j] * so;
-        float sob = hb[j] * tc;
-        float cnbar = cnb[j];
-        float tcdb = 0.f, cndbar = 0.f;
-        float h = tc * so;
-        float hd = 0.f;
-        if (TAN) {
-          const float cnd = ncd[j] * g[j];
-          const float tcd = dt * cnd;
-          hd = tcd * so + tc * actd[3][j];
-          tcb += hdb[j] * actd[3][j];
-          sob += hdb[j] * tcd;
-          tcdb = hdb[j] * so;
-          ydb_[3][j] = hdb[j] * tc;
-          cnbar += tcdb * (-2.f * tc * dt) * cnd;
-          cndbar = cndb[j] + tcdb * dt;
-        }
-        cnbar += tcb * dt;
-        yb_[3][j] = sob;
-        ncb[j] = cnbar * g[j];
-        dgs[j] = cnbar * nc[j];
-        dbs[j] = cnbar;
-        dwv[j] = h * yb;
-        if (TAN) {
-          ncdb[j] = cndbar * g[j];
-          dgs[j] += cndbar * ncd[j];
-          dwv[j] += hd * p.ydot_bar;
-        }
-      }
-      if (wgrad) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int col = lane * 4 + 128 * (k >> 2) + (k & 3);
-          atomicAdd(&sm.dg[4][col], dgs[k]);
-          atomicAdd(&sm.db[4][col], dbs[k]);
-          if (p.dwdec) atomicAdd(&sm.dw[col], dwv[k]);
-        }
-        if (p.dbdec && lane == 0) atomicAdd(&sm.dbd, yb);
-      }
-    }
-    // LN(state) reverse -> adjoint of c' (and of its tangent)
-    V16 cpb, cpdb;
-    ln_proj(nc, rc, ncb, cpb);
-    if (TAN) {
-      ln_proj(nc, rc, ncdb, cpdb);
-      const float pp = dot16(nc, ncdb), qq = dot16(nc, cpd), ss = dot16(ncdb, ncd);
-      const float k = rc * (1.0f / LH);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) cpb[j] -= k * (nc[j] * ss + qq * cpdb[j] + pp * ncd[j]);
-    }
-    // c' = c*sf + si*tj
-    V16 cbar, cdbar;
+    ld16_or_zero(p.CBn ? p.CBn + trow * LH : nullptr, cndb);
+  }
+  V16 ncb, ncdb;        // adjoints of nc (normalised state) and its tangent
+  V16 yb_[4], ydb_[4];  // adjoints of the gate activations (and of their tangents)
+  {
+    V16 dgs, dbs, dwv;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      cbar[j] = cpb[j] * act[2][j];
-      yb_[2][j] = cpb[j] * c[j];
-      yb_[0][j] = cpb[j] * act[1][j];
-      yb_[1][j] = cpb[j] * act[0][j];
+      const float cn = fmaf(nc[j], g[j], bt[j]);
+      const float tc = tanhf_(cn);
+      const float dt = 1.f - tc * tc;
+      const float so = act[3][j];
+      float tcb = hb[j] * so;
+      float sob = hb[j] * tc;
+      float cnbar = cnb[j];
+      float tcdb = 0.f, cndbar = 0.f;
+      float h = tc * so;
+      float hd = 0.f;
       if (TAN) {
-        cbar[j] += cpdb[j] * actd[2][j];
-        yb_[2][j] += cpdb[j] * cd[j];
-        yb_[0][j] += cpdb[j] * actd[1][j];
-        yb_[1][j] += cpdb[j] * actd[0][j];
-        cdbar[j] = cpdb[j] * act[2][j];
-        ydb_[2][j] = cpdb[j] * c[j];
-        ydb_[0][j] = cpdb[j] * act[1][j];
-        ydb_[1][j] = cpdb[j] * act[0][j];
+        const float cnd = ncd[j] * g[j];
+        const float tcd = dt * cnd;
+        hd = tcd * so + tc * actd[3][j];
+        tcb += hdb[j] * actd[3][j];
+        sob += hdb[j] * tcd;
+        tcdb = hdb[j] * so;
+        ydb_[3][j] = hdb[j] * tc;
+        cnbar += tcdb * (-2.f * tc * dt) * cnd;
+        cndbar = cndb[j] + tcdb * dt;
+      }
+      cnbar += tcb * dt;
+      yb_[3][j] = sob;
+      ncb[j] = cnbar * g[j];
+      dgs[j] = cnbar * nc[j];
+      dbs[j] = cnbar;
+      dwv[j] = h * yb;
+      if (TAN) {
+        ncdb[j] = cndbar * g[j];
+        dgs[j] += cndbar * ncd[j];
+        dwv[j] += hd * p.ydot_bar;
       }
     }
-    st16(p.CB + prow * LH, cbar);
-    if (TAN) st16(p.CB + trow * LH, cdbar);
-    // ---- phase C: per-gate reverse through the nonlinearity and its LayerNorm
-#pragma unroll
-    for (int G = 0; G < 4; ++G) {
-      ld16(q + G * LH, x);
-      ln_norm(x, n, r);
-      ld16(p.ln.gamma[G], g);
-      V16 nb, xb, xd, nd, ndb, xdb;
-      if (TAN) {
-        ld16(qd + G * LH, xd);
-        ln_proj(n, r, xd, nd);
-      }
-      V16 dgs, dbs;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float y = act[G][j];
-        const float d1 = (G == 1) ? (1.f - y * y) : y * (1.f - y);
-        float abar = yb_[G][j] * d1;
-        if (TAN) {
-          const float d2 = (G == 1) ? (-2.f * y * d1) : d1 * (1.f - 2.f * y);
-          abar += ydb_[G][j] * d2 * ad[G][j];
-          const float adb = ydb_[G][j] * d1;
-          ndb[j] = adb * g[j];
-          dgs[j] = abar * n[j] + adb * nd[j];
-        } else {
-          dgs[j] = abar * n[j];
-        }
-        dbs[j] = abar;
-        nb[j] = abar * g[j];
-      }
-      if (wgrad) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int col = lane * 4 + 128 * (k >> 2) + (k & 3);
-          atomicAdd(&sm.dg[G][col], dgs[k]);
-          atomicAdd(&sm.db[G][col], dbs[k]);
-        }
-      }
-      ln_proj(n, r, nb, xb);
-      if (TAN) {
-        ln_proj(n, r, ndb, xdb);
-        const float pp = dot16(n, ndb), qq = dot16(n, xd), ss = dot16(ndb, nd);
-        const float k = r * (1.0f / LH);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) xb[j] -= k * (n[j] * ss + qq * xdb[j] + pp * nd[j]);
-        st16_hl(p.QB + trow * p.ldQB + G * LH, p.qb_lo, xdb);
-      }
-      st16_hl(p.QB + prow * p.ldQB + G * LH, p.qb_lo, xb);
+    if (wgrad) {
+      slab_acc(slab + 4 * LH, dgs, first);
+      slab_acc(slab + 9 * LH, dbs, first);
+      slab_acc(slab + 10 * LH, dwv, first);
+      dbd_acc += yb;
     }
   }
-  if (wgrad) {
-    __syncthreads();
-    for (int k = threadIdx.x; k < 5 * LH; k += LS_THREADS) {
-      const int G = k / LH, col = k % LH;
-      atomicAdd(p.dgamma[G] + col, sm.dg[G][col]);
-      atomicAdd(p.dbeta[G] + col, sm.db[G][col]);
+  // LN(state) reverse -> adjoint of c' (and of its tangent)
+  V16 cpb, cpdb;
+  ln_proj(nc, rc, ncb, cpb);
+  if (TAN) {
+    ln_proj(nc, rc, ncdb, cpdb);
+    const float pp = dot16(nc, ncdb), qq = dot16(nc, cpd), ss = dot16(ncdb, ncd);
+    const float k = rc * (1.0f / LH);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cpb[j] -= k * (nc[j] * ss + qq * cpdb[j] + pp * ncd[j]);
+  }
+  // c' = c*sf + si*tj
+  V16 cbar, cdbar;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    cbar[j] = cpb[j] * act[2][j];
+    yb_[2][j] = cpb[j] * c[j];
+    yb_[0][j] = cpb[j] * act[1][j];
+    yb_[1][j] = cpb[j] * act[0][j];
+    if (TAN) {
+      cbar[j] += cpdb[j] * actd[2][j];
+      yb_[2][j] += cpdb[j] * cd[j];
+      yb_[0][j] += cpdb[j] * actd[1][j];
+      yb_[1][j] += cpdb[j] * actd[0][j];
+      cdbar[j] = cpdb[j] * act[2][j];
+      ydb_[2][j] = cpdb[j] * c[j];
+      ydb_[0][j] = cpdb[j] * act[1][j];
+      ydb_[1][j] = cpdb[j] * act[0][j];
     }
-    if (p.dwdec)
-      for (int k = threadIdx.x; k < LH; k += LS_THREADS) atomicAdd(p.dwdec + k, sm.dw[k]);
-    if (p.dbdec && threadIdx.x == 0) atomicAdd(p.dbdec, sm.dbd);
+  }
+  st16(p.CB + prow * LH, cbar);
+  if (TAN) st16(p.CB + trow * LH, cdbar);
+  // ---- phase C: per-gate reverse through the nonlinearity and its LayerNorm
+#pragma unroll
+  for (int G = 0; G < 4; ++G) {
+    ld16(q + G * LH, x);
+    ln_norm(x, n, r);
+    ld16(p.ln.gamma[G], g);
+    V16 nb, xb, xd, nd, ndb, xdb;
+    if (TAN) {
+      ld16(qd + G * LH, xd);
+      ln_proj(n, r, xd, nd);
+    }
+    V16 dgs, dbs;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float y = act[G][j];
+      const float d1 = (G == 1) ? (1.f - y * y) : y * (1.f - y);
+      float abar = yb_[G][j] * d1;
+      if (TAN) {
+        const float d2 = (G == 1) ? (-2.f * y * d1) : d1 * (1.f - 2.f * y);
+        abar += ydb_[G][j] * d2 * ad[G][j];
+        const float adb = ydb_[G][j] * d1;
+        ndb[j] = adb * g[j];
+        dgs[j] = abar * n[j] + adb * nd[j];
+      } else {
+        dgs[j] = abar * n[j];
+      }
+      dbs[j] = abar;
+      nb[j] = abar * g[j];
+    }
+    if (wgrad) {
+      slab_acc(slab + G * LH, dgs, first);
+      slab_acc(slab + (5 + G) * LH, dbs, first);
+    }
+    ln_proj(n, r, nb, xb);
+    if (TAN) {
+      ln_proj(n, r, ndb, xdb);
+      const float pp = dot16(n, ndb), qq = dot16(n, xd), ss = dot16(ndb, nd);
+      const float k = r * (1.0f / LH);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) xb[j] -= k * (n[j] * ss + qq * xdb[j] + pp * nd[j]);
+      st16_hl(p.QB + trow * p.ldQB + G * LH, p.qb_lo, xdb);
+    }
+    st16_hl(p.QB + prow * p.ldQB + G * LH, p.qb_lo, xb);
+  }
+}
+
+__global__ void __launch_bounds__(LR_THREADS, 1) lstm_rev_kernel(const LstmRevParams p) {
+  extern __shared__ __align__(16) float lr_smem[];   // [LR_WARPS][11][512] + [LR_WARPS] (only with parameter gradients)
+  const bool wgrad = p.dgamma[0] != nullptr;
+  const int warp = threadIdx.x >> 5;
+  float* slab = wgrad ? lr_smem + warp * LR_SLAB : nullptr;
+  const int nrows = p.n_plain + p.n_tan;
+  const int gw = blockIdx.x * LR_WARPS + warp;
+  const int stride = gridDim.x * LR_WARPS;
+  bool first = true;
+  float dbd = 0.f;
+  // tangent rows first: they are the longest, so they start earliest
+  for (int i = gw; i < nrows; i += stride) {
+    if (i < p.n_tan) lstm_rev_row<true>(p, p.tan_prow0 + i, p.trow0 + i, slab, first, dbd);
+    else lstm_rev_row<false>(p, p.prow0 + (i - p.n_tan), 0, slab, first, dbd);
+    first = false;
+  }
+  if (!wgrad) return;
+  float* dbds = lr_smem + LR_WARPS * LR_SLAB;
+  if ((threadIdx.x & 31) == 0) dbds[warp] = dbd;
+  __syncthreads();
+  int nact = min(LR_WARPS, nrows - blockIdx.x * LR_WARPS);   // warps of this CTA that processed >= 1 row
+  if (nact <= 0) return;
+  for (int k = threadIdx.x; k < LR_SLAB; k += LR_THREADS) {
+    float s = 0.f;
+    for (int w = 0; w < nact; ++w) s += lr_smem[w * LR_SLAB + k];
+    const int vec = k / LH, col = k % LH;
+    float* dst = vec < 5 ? p.dgamma[vec] : (vec < 10 ? p.dbeta[vec - 5] : p.dwdec);
+    if (dst) atomicAdd(dst + col, s);
+  }
+  if (p.dbdec && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < nact; ++w) s += dbds[w];
+    atomicAdd(p.dbdec, s);
   }
 }
 
@@ -481,13 +506,20 @@ int lstm_tan(const LstmTanParams& p, cudaStream_t stream) {
   SGG_LAUNCHED();
   return 0;
 }
-int lstm_rev(const LstmRevParams& p, bool tan, cudaStream_t stream) {
-  if (p.nrows <= 0) return 0;
-  const int grid = (p.nrows + LS_WARPS - 1) / LS_WARPS;
-  if (tan)
-    lstm_rev_kernel<true><<<grid, LS_THREADS, 0, stream>>>(p);
-  else
-    lstm_rev_kernel<false><<<grid, LS_THREADS, 0, stream>>>(p);
+int lstm_rev(const LstmRevParams& p, cudaStream_t stream) {
+  const int nrows = p.n_plain + p.n_tan;
+  if (nrows <= 0) return 0;
+  const bool wgrad = p.dgamma[0] != nullptr;
+  const size_t smem = wgrad ? (size_t)(LR_WARPS * LR_SLAB + LR_WARPS) * sizeof(float) : 0;
+  static bool configured = false;
+  if (!configured) {
+    SGG_CUDA(cudaFuncSetAttribute(lstm_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((LR_WARPS * LR_SLAB + LR_WARPS) * sizeof(float))));
+    configured = true;
+  }
+  int grid = (nrows + LR_WARPS - 1) / LR_WARPS;
+  if (grid > 148) grid = 148;
+  lstm_rev_kernel<<<grid, LR_THREADS, smem, stream>>>(p);
   SGG_LAUNCHED();
   return 0;
 }

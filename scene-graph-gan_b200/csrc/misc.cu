@@ -73,6 +73,7 @@ struct PackParams {
   const float* mix; int mmod;          // optional per-row multiplier on src2 (row % mmod)
   const float* scale; int smod;        // optional per-row scale
   __nv_bfloat16* dst; long long ldd; long long lo_off;
+  int reps; long long rep_stride;      // the result is written `reps` times, rep_stride elements apart (0/1 = once)
 };
 __global__ void pack_hl_kernel(const PackParams p) {
   const long long n = (long long)p.rows * p.cols;
@@ -84,8 +85,11 @@ __global__ void pack_hl_kernel(const PackParams p) {
     if (p.scale) v *= p.scale[r % p.smod];
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
-    p.dst[(long long)r * p.ldd + c] = h;
-    p.dst[(long long)r * p.ldd + p.lo_off + c] = l;
+    const int reps = p.reps > 1 ? p.reps : 1;
+    for (int k = 0; k < reps; ++k) {
+      p.dst[k * p.rep_stride + (long long)r * p.ldd + c] = h;
+      p.dst[k * p.rep_stride + (long long)r * p.ldd + p.lo_off + c] = l;
+    }
   }
 }
 int pack_hl(const PackParams& p, cudaStream_t stream) {
@@ -257,17 +261,24 @@ int colsum(const float* src, long long ld, int rows, int cols, float* out, cudaS
 // theta -= lr_t * m / (sqrt(v) + eps).  Flat fp32 buckets; also refreshes the bf16 shadow of
 // each tensor (the GEMM B operands), whose rows are padded to a 16-byte pitch.
 namespace sgg {
-struct AdamSeg { long long off; long long sh_off; int cols; int pitch; long long n; };
+struct AdamSeg { long long off; long long sh_off; int cols; int pitch; long long n; long long lo_off; };
 constexpr int ADAM_MAX_SEG = 24;
 struct AdamParams {
   float* theta; const float* grad; float* m; float* v; __nv_bfloat16* shadow;
   float lr_t, b1, b2, eps, gscale;
+  // device-side step counter (graph replay): step = iter[0] * step_mul + step_add, lr_t recomputed in the kernel
+  const long long* iter; long long step_mul, step_add; float lr;
   int nseg; AdamSeg seg[ADAM_MAX_SEG];
 };
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams p) {
   const int s = blockIdx.y;
   const AdamSeg sg = p.seg[s];
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  float lr_t = p.lr_t;
+  if (p.iter) {
+    const double step = (double)(p.iter[0] * p.step_mul + p.step_add);
+    lr_t = (float)((double)p.lr * sqrt(1.0 - pow((double)p.b2, step)) / (1.0 - pow((double)p.b1, step)));
+  }
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < sg.n; i += stride) {
     const long long gi = sg.off + i;
     float th[4], g[4], m[4], v[4];
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
       const float gg = g[e] * p.gscale;
       m[e] = p.b1 * m[e] + (1.0f - p.b1) * gg;
       v[e] = p.b2 * v[e] + (1.0f - p.b2) * gg * gg;
-      th[e] -= p.lr_t * m[e] / (sqrtf(v[e]) + p.eps);
+      th[e] -= lr_t * m[e] / (sqrtf(v[e]) + p.eps);
     }
     if (vec) {
       *reinterpret_cast<float4*>(p.theta + gi) = make_float4(th[0], th[1], th[2], th[3]);
@@ -304,7 +315,10 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
       for (int e = 0; e < 4; ++e)
         if (i + e < sg.n) {
           const long long r = (i + e) / sg.cols, c = (i + e) % sg.cols;
-          p.shadow[sg.sh_off + r * sg.pitch + c] = __float2bfloat16_rn(th[e]);
+          __nv_bfloat16 h, l;
+          split_bf16(th[e], h, l);
+          p.shadow[sg.sh_off + r * sg.pitch + c] = h;
+          p.shadow[sg.sh_off + sg.lo_off + r * sg.pitch + c] = l;
         }
     }
   }
@@ -321,7 +335,10 @@ int adam(const AdamParams& p, long long max_n, cudaStream_t stream) {
 __global__ void shadow_kernel(const float* theta, __nv_bfloat16* shadow, AdamSeg sg) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / sg.cols, c = i % sg.cols;
-    shadow[sg.sh_off + r * sg.pitch + c] = __float2bfloat16_rn(theta[sg.off + i]);
+    __nv_bfloat16 h, l;
+    split_bf16(theta[sg.off + i], h, l);
+    shadow[sg.sh_off + r * sg.pitch + c] = h;
+    shadow[sg.sh_off + sg.lo_off + r * sg.pitch + c] = l;
   }
 }
 int refresh_shadow(const float* theta, __nv_bfloat16* shadow, const AdamSeg& sg, cudaStream_t stream) {
@@ -347,9 +364,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
 
 // mode 0: uniform [0,1) ; mode 1: standard normal (Box-Muller)
-__global__ void rng_fill_kernel(float* out, long long n, uint64_t seed, uint64_t offset, int mode) {
+__global__ void rng_fill_kernel(float* out, long long n, uint64_t seed, uint64_t offset, int mode,
+                                const long long* iter, uint64_t per_iter) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q * 4 >= n) return;
+  if (iter) offset += (uint64_t)iter[0] * per_iter;   // device-side stream position (graph replay)
   const uint64_t ctr = offset + (uint64_t)q;
   const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -367,10 +386,19 @@ __global__ void rng_fill_kernel(float* out, long long n, uint64_t seed, uint64_t
   for (int e = 0; e < 4; ++e)
     if (q * 4 + e < n) out[q * 4 + e] = o[e];
 }
-int rng_fill(float* out, long long n, uint64_t seed, uint64_t offset, int mode, cudaStream_t stream) {
+int rng_fill(float* out, long long n, uint64_t seed, uint64_t offset, int mode, cudaStream_t stream,
+             const long long* iter = nullptr, uint64_t per_iter = 0) {
   if (n <= 0) return 0;
   const long long quads = (n + 3) / 4;
-  rng_fill_kernel<<<(int)((quads + 255) / 256), 256, 0, stream>>>(out, n, seed, offset, mode);
+  rng_fill_kernel<<<(int)((quads + 255) / 256), 256, 0, stream>>>(out, n, seed, offset, mode, iter, per_iter);
+  SGG_LAUNCHED();
+  return 0;
+}
+
+// iteration counter that drives the device-side RNG position and Adam step numbers
+__global__ void bump_counter_kernel(long long* ctr) { ctr[0] += 1; }
+int bump_counter(long long* ctr, cudaStream_t stream) {
+  bump_counter_kernel<<<1, 1, 0, stream>>>(ctr);
   SGG_LAUNCHED();
   return 0;
 }

@@ -17,8 +17,11 @@ struct ParamLayout {
   bool gen;
   int R, C, H, U, OUT, V, E, KX;
   long long Watt, batt, K, lng[5], lnb[5], Wdec, bdec, Wemb, total;   // fp32 bucket offsets (floats)
+  // bf16 shadow: each GEMM weight is stored as [hi rows | lo rows] (w ~= hi + lo, 2^-17 relative), rows padded
+  // to a multiple of 64 with zeros, so that one tensor map serves both parts and a k-block never straddles them.
   long long sWa, sWh, sK, sWdec, sWemb, stotal;                       // bf16 shadow offsets (elements)
   int pAtt, pK, pWdec, pWemb;                                         // shadow row pitches
+  int rWa, rWh, rK, rWdec, rWemb;                                     // padded row counts (lo part starts at row r*)
 };
 
 static ParamLayout param_layout(bool gen, const sgg_dims_t& d) {
@@ -40,11 +43,13 @@ static ParamLayout param_layout(bool gen, const sgg_dims_t& d) {
   long long s = 0;
   auto stake = [&](long long n) { long long r = s; s = rup(s + n, 128); return r; };
   L.pAtt = (int)rup(d.R, 8); L.pK = 4 * d.H; L.pWdec = (int)rup(L.OUT, 8); L.pWemb = (int)rup(d.E, 8);
-  L.sWa = stake((long long)d.R * d.C * L.pAtt);
-  L.sWh = stake((long long)d.H * L.pAtt);
-  L.sK = stake((long long)L.KX * L.pK);
-  L.sWdec = gen ? stake((long long)d.H * L.pWdec) : -1;
-  L.sWemb = gen ? -1 : stake((long long)d.V * L.pWemb);
+  L.rWa = (int)rup((long long)d.R * d.C, 64); L.rWh = (int)rup(d.H, 64); L.rK = (int)rup(L.KX, 64);
+  L.rWdec = (int)rup(d.H, 64); L.rWemb = (int)rup(d.V, 64);
+  L.sWa = stake(2LL * L.rWa * L.pAtt);
+  L.sWh = stake(2LL * L.rWh * L.pAtt);
+  L.sK = stake(2LL * L.rK * L.pK);
+  L.sWdec = gen ? stake(2LL * L.rWdec * L.pWdec) : -1;
+  L.sWemb = gen ? -1 : stake(2LL * L.rWemb * L.pWemb);
   L.stotal = s;
   return L;
 }
@@ -54,17 +59,17 @@ static const char* LN_NAMES[5] = {"input", "transform", "forget", "output", "sta
 static int fill_adam_segs(const ParamLayout& L, AdamSeg* seg) {
   int n = 0;
   const long long RC = (long long)L.R * L.C;
-  seg[n++] = {L.Watt, L.sWa, L.R, L.pAtt, RC * L.R};
-  seg[n++] = {L.Watt + RC * L.R, L.sWh, L.R, L.pAtt, (long long)L.H * L.R};
-  seg[n++] = {L.batt, -1, L.R, L.R, L.R};
-  seg[n++] = {L.K, L.sK, 4 * L.H, L.pK, (long long)L.KX * 4 * L.H};
+  seg[n++] = {L.Watt, L.sWa, L.R, L.pAtt, RC * L.R, (long long)L.rWa * L.pAtt};
+  seg[n++] = {L.Watt + RC * L.R, L.sWh, L.R, L.pAtt, (long long)L.H * L.R, (long long)L.rWh * L.pAtt};
+  seg[n++] = {L.batt, -1, L.R, L.R, L.R, 0};
+  seg[n++] = {L.K, L.sK, 4 * L.H, L.pK, (long long)L.KX * 4 * L.H, (long long)L.rK * L.pK};
   for (int i = 0; i < 5; ++i) {
-    seg[n++] = {L.lng[i], -1, L.H, L.H, L.H};
-    seg[n++] = {L.lnb[i], -1, L.H, L.H, L.H};
+    seg[n++] = {L.lng[i], -1, L.H, L.H, L.H, 0};
+    seg[n++] = {L.lnb[i], -1, L.H, L.H, L.H, 0};
   }
-  seg[n++] = {L.Wdec, L.sWdec, L.OUT, L.pWdec, (long long)L.H * L.OUT};
-  seg[n++] = {L.bdec, -1, L.OUT, L.OUT, L.OUT};
-  if (!L.gen) seg[n++] = {L.Wemb, L.sWemb, L.E, L.pWemb, (long long)L.V * L.E};
+  seg[n++] = {L.Wdec, L.sWdec, L.OUT, L.pWdec, (long long)L.H * L.OUT, (long long)L.rWdec * L.pWdec};
+  seg[n++] = {L.bdec, -1, L.OUT, L.OUT, L.OUT, 0};
+  if (!L.gen) seg[n++] = {L.Wemb, L.sWemb, L.E, L.pWemb, (long long)L.V * L.E, (long long)L.rWemb * L.pWemb};
   return n;
 }
 
@@ -77,7 +82,7 @@ struct NetWs {
 };
 struct Ws {
   NetWs g, d;
-  __nv_bfloat16* FAKE;   // [T*B, 2*VP] generator logits hi/lo (row t*B+b)
+  __nv_bfloat16* FAKE;   // [FS][T*B, 2*VP] generator logits hi/lo (row t*B+b), one slot per noise draw
   float* DFAKE; __nv_bfloat16* DFAKEH;  // [T*B, VP] fp32 + hi/lo : d gen_cost / d fake, or the GP gradient g
   __nv_bfloat16* VHL;    // [T*B, 2*VP] v = coef * g hi/lo
   float* HB;             // [T*B, H]
@@ -89,11 +94,14 @@ struct Ws {
   long long bytes;
 };
 
+constexpr int MAX_GEN_STREAMS = 8;   // noise draws served by one generator forward (= attention streams per tile read)
 struct Dm {  // derived dimensions
-  int B, T, V, R, C, H, E, RP, VP, EP, KXG, KXD;
+  int B, T, V, R, C, H, E, RP, VP, EP, KXG, KXD, GS, FS;
 };
 static Dm derive(const sgg_dims_t& d) {
-  Dm m{d.B, d.T, d.V, d.R, d.C, d.H, d.E, 0, 0, 0, 0, 0};
+  Dm m{d.B, d.T, d.V, d.R, d.C, d.H, d.E, 0, 0, 0, 0, 0, 1, 1};
+  m.FS = d.S > 1 ? d.S : 1;                                   // fake-logit slots kept in the workspace
+  m.GS = m.FS < MAX_GEN_STREAMS ? m.FS : MAX_GEN_STREAMS;     // generator rows = GS * B
   m.RP = (int)rup(d.R, 64); m.VP = (int)rup(d.V, 64); m.EP = (int)rup(d.E, 64);
   m.KXG = (int)rup(d.C + d.C + d.H, 64); m.KXD = (int)rup(d.C + d.E + d.H, 64);
   return m;
@@ -123,10 +131,10 @@ static Ws ws_layout(const sgg_dims_t& d, void* base) {
     n.PBH = (__nv_bfloat16*)take((long long)m.B * 2 * m.RP * 2);
     n.Y = disc ? (float*)take((long long)NR * T * 4) : nullptr;
   };
-  net(w.g, m.B, m.KXG, false);
+  net(w.g, m.GS * m.B, m.KXG, false);
   net(w.d, 4 * m.B, m.KXD, true);
   const long long TB = (long long)m.T * m.B;
-  w.FAKE = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
+  w.FAKE = (__nv_bfloat16*)take(m.FS * TB * 2 * m.VP * 2);
   w.DFAKE = (float*)take(TB * m.VP * 4);
   w.DFAKEH = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
   w.VHL = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
@@ -179,6 +187,17 @@ static Net make_net(bool gen, const sgg_dims_t& d, const float* theta, const voi
   return n;
 }
 
+// Three bf16 products of an fp32-faithful contraction  (x_hi + x_lo)(w_hi + w_lo) ~= x_hi w_hi + x_lo w_hi + x_hi w_lo.
+// Activation x: [rows, 2*a_lo] with the lo part at column a0 + a_lo.  Weight (shadow): hi rows [0, r), lo rows [r, 2r).
+//   weight used MN-major (forward, TF [in,out] layout): its rows are the contraction index  -> lo at k  offset b_lo
+//   weight used K-major  (backward, x_bar = y_bar W^T): its rows are the output index       -> lo at mn offset b_lo
+static void segs_act_weight(sgg_gemm_desc_t& g, int a0, int a_lo, int b_lo, bool weight_rows_are_k, int klen) {
+  g.nseg = 3;
+  for (int s = 0; s < 3; ++s) { g.seg_klen[s] = klen; g.seg_a_k[s] = a0; g.seg_b_k[s] = 0; g.seg_a_mn[s] = 0; g.seg_b_mn[s] = 0; }
+  g.seg_a_k[1] = a0 + a_lo;
+  if (weight_rows_are_k) g.seg_b_k[2] = b_lo; else g.seg_b_mn[2] = b_lo;
+}
+
 static sgg_gemm_desc_t gd_zero() { sgg_gemm_desc_t g; memset(&g, 0, sizeof(g)); g.alpha = 1.0f; return g; }
 int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream);
 
@@ -189,8 +208,8 @@ static int net_attn_proj(const Net& n) {
   sgg_gemm_desc_t g = gd_zero();
   const long long K = (long long)m.R * m.C;
   g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 0;
-  g.B = n.sh + n.L.sWa; g.b_rows = K; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
-  g.M = m.B; g.N = m.R; g.nseg = 1; g.seg_klen[0] = (int)K;
+  g.B = n.sh + n.L.sWa; g.b_rows = 2LL * n.L.rWa; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
+  g.M = m.B; g.N = m.R; g.nseg = 2; g.seg_klen[0] = g.seg_klen[1] = (int)K; g.seg_b_k[1] = n.L.rWa;  // a is bf16-exact
   g.C = n.w.P; g.ldc = m.RP; g.atomic = 1;
   const int tiles = ((m.B + 127) / 128);
   int splits = 148 / tiles; if (splits < 1) splits = 1;
@@ -212,9 +231,9 @@ static int net_scores(const Net& n, int t, int row0, int nrows, bool tangent) {
   const Dm& m = n.m;
   sgg_gemm_desc_t g = gd_zero();
   g.A = n.w.CH + t * n.sCH() + (long long)row0 * 2 * m.H; g.a_rows = nrows; g.a_cols = 2 * m.H; g.a_ld = 2 * m.H;
-  g.B = n.sh + n.L.sWh; g.b_rows = m.H; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
-  g.M = nrows; g.N = m.R; g.nseg = 2;
-  g.seg_klen[0] = g.seg_klen[1] = m.H; g.seg_a_k[1] = m.H;
+  g.B = n.sh + n.L.sWh; g.b_rows = 2LL * n.L.rWh; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
+  g.M = nrows; g.N = m.R;
+  segs_act_weight(g, 0, m.H, n.L.rWh, true, m.H);
   if (tangent) {
     g.C = n.w.ED + (long long)t * m.B * m.RP; g.ldc = m.RP;
   } else {
@@ -230,9 +249,9 @@ static int net_gates(const Net& n, int t, int row0, int nrows) {
   const Dm& m = n.m;
   sgg_gemm_desc_t g = gd_zero();
   g.A = n.w.X + t * n.sX() + (long long)row0 * 2 * n.KXP; g.a_rows = nrows; g.a_cols = 2 * n.KXP; g.a_ld = 2 * n.KXP;
-  g.B = n.sh + n.L.sK; g.b_rows = n.L.KX; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 1;
-  g.M = nrows; g.N = 4 * m.H; g.nseg = 2;
-  g.seg_klen[0] = g.seg_klen[1] = n.KXP; g.seg_a_k[1] = n.KXP;
+  g.B = n.sh + n.L.sK; g.b_rows = 2LL * n.L.rK; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 1;
+  g.M = nrows; g.N = 4 * m.H;
+  segs_act_weight(g, 0, n.KXP, n.L.rK, true, n.KXP);
   g.C = n.w.Q + t * n.sQ() + (long long)row0 * 4 * m.H; g.ldc = 4 * m.H;
   return gemm(g, n.st);
 }
@@ -300,7 +319,7 @@ static int net_tangent(const Net& n, int pblk, int tblk) {
 struct RevCfg {
   int blk0, nblk;        // primal stream blocks [blk0, blk0+nblk)
   int tan_pblk, tan_blk; // tangent pairing (or -1)
-  float ybar_blk[4];     // D head upstream per block
+  float ybar_blk[8];     // D head upstream per block
   float ydot_bar;        // D head tangent upstream (lambda)
   const float* HB;       // G: [T*B, H] h_bar contributions from the logits (row t*B+b), or null
   bool wgrad;            // accumulate parameter gradients
@@ -325,7 +344,7 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     lp.XBn = last ? nullptr : n.w.XB + (t + 1) * n.sXB(); lp.ldXB = n.KXP; lp.hoff = n.hoff;
     lp.HB = rc.HB ? rc.HB + (long long)t * m.B * m.H : nullptr; lp.ldHB = m.H;
     lp.CBn = last ? nullptr : n.w.CB + (t + 1) * n.sCf();
-    for (int i = 0; i < 4; ++i) lp.ybar_blk[i] = rc.ybar_blk[i];
+    for (int i = 0; i < 8; ++i) lp.ybar_blk[i] = rc.ybar_blk[i];
     lp.ydot_bar = rc.ydot_bar;
     lp.wdec = n.gen ? nullptr : n.theta + n.L.Wdec;
     lp.QB = n.w.QB + t * n.sQB(); lp.ldQB = 8 * m.H; lp.qb_lo = 4 * m.H;
@@ -334,23 +353,17 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
       for (int i = 0; i < 5; ++i) { lp.dgamma[i] = n.grad + n.L.lng[i]; lp.dbeta[i] = n.grad + n.L.lnb[i]; }
       if (!n.gen) { lp.dwdec = n.grad + n.L.Wdec; lp.dbdec = n.grad + n.L.bdec; }
     }
-    // rows without tangent
-    const int plain_blks = tan ? (rc.tan_pblk - rc.blk0) : rc.nblk;
-    if (plain_blks > 0) {
-      lp.nrows = plain_blks * m.B; lp.prow0 = row0; lp.trow0 = 0;
-      SGG_TRY(lstm_rev(lp, false, n.st));
-    }
-    if (tan) {
-      lp.nrows = m.B; lp.prow0 = rc.tan_pblk * m.B; lp.trow0 = rc.tan_blk * m.B;
-      SGG_TRY(lstm_rev(lp, true, n.st));
-    }
+    // first-order rows, then the (interp, tangent) pair, in one launch
+    lp.n_plain = (tan ? (rc.tan_pblk - rc.blk0) : rc.nblk) * m.B; lp.prow0 = row0;
+    lp.n_tan = tan ? m.B : 0; lp.tan_prow0 = tan ? rc.tan_pblk * m.B : 0; lp.trow0 = tan ? rc.tan_blk * m.B : 0;
+    SGG_TRY(lstm_rev(lp, n.st));
     // x_bar = q_bar K^T  (rows incl. tangent)
     {
       sgg_gemm_desc_t g = gd_zero();
       g.A = n.w.QB + t * n.sQB() + (long long)row0 * 8 * m.H; g.a_rows = nrows_all; g.a_cols = 8 * m.H; g.a_ld = 8 * m.H;
-      g.B = n.sh + n.L.sK; g.b_rows = n.L.KX; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 0;
-      g.M = nrows_all; g.N = n.L.KX; g.nseg = 2;
-      g.seg_klen[0] = g.seg_klen[1] = 4 * m.H; g.seg_a_k[1] = 4 * m.H;
+      g.B = n.sh + n.L.sK; g.b_rows = 2LL * n.L.rK; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 0;
+      g.M = nrows_all; g.N = n.L.KX;
+      segs_act_weight(g, 0, 4 * m.H, n.L.rK, false, 4 * m.H);
       g.C = n.w.XB + t * n.sXB() + (long long)row0 * n.KXP; g.ldc = n.KXP;
       SGG_TRY(gemm(g, n.st));
     }
@@ -370,9 +383,9 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     if (t > 0) {  // c_bar of step t (in place) += e_bar W_h^T
       sgg_gemm_desc_t g = gd_zero();
       g.A = n.w.EB + t * n.sEB() + (long long)row0 * 2 * m.RP; g.a_rows = nrows_all; g.a_cols = 2 * m.RP; g.a_ld = 2 * m.RP;
-      g.B = n.sh + n.L.sWh; g.b_rows = m.H; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 0;
-      g.M = nrows_all; g.N = m.H; g.nseg = 2;
-      g.seg_klen[0] = g.seg_klen[1] = m.RP; g.seg_a_k[1] = m.RP;
+      g.B = n.sh + n.L.sWh; g.b_rows = 2LL * n.L.rWh; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 0;
+      g.M = nrows_all; g.N = m.H;
+      segs_act_weight(g, 0, m.RP, n.L.rWh, false, m.RP);
       float* cb = n.w.CB + t * n.sCf() + (long long)row0 * m.H;
       g.C = cb; g.ldc = m.H; g.addm = cb; g.ld_addm = m.H; g.add_mod = nrows_all;
       SGG_TRY(gemm(g, n.st));
@@ -423,33 +436,45 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
 }
 
 // ============================================================================ generator forward
-static int gen_forward(const Net& g, const Ws& w, const float* noise, bool recompute_proj, float* logits_out) {
+static __nv_bfloat16* fake_slot(const Ws& w, const Dm& m, int slot) {
+  return w.FAKE + (long long)slot * m.T * m.B * 2 * m.VP;
+}
+
+// Generator forward (gen:74-91) for `ns` noise draws at once: rows s*B+b of every buffer belong to draw s, and
+// the ns streams of sample b share one read of its annotation tile.  g.NR must be ns*B.  Logits of draw s go
+// to FAKE slot slot0+s (hi/lo, rows t*B+b).  noise: [ns, B, C] fp32.
+static int gen_forward(const Net& g, const Ws& w, const float* noise, int ns, int slot0, bool recompute_proj,
+                       float* logits_out) {
   const Dm& m = g.m;
+  SGG_CHECK(ns >= 1 && ns <= m.GS && g.NR == ns * m.B && slot0 + ns <= m.FS, "gen_forward: bad stream count %d", ns);
   if (recompute_proj) {
     SGG_TRY(net_attn_proj(g));
-    SGG_TRY(net_init_state(g, 1));
+    SGG_TRY(net_init_state(g, m.GS));   // every stream block of step 0 (any later ns <= GS finds its state)
   }
-  // u_t = noise for every t (gen:81,86): hi/lo into the u columns of X[0..T-1]
-  for (int t = 0; t < m.T; ++t) {
+  {  // u_t = noise for every t (gen:81,86): hi/lo into the u columns of X[0..T-1]
     PackParams pk{};
-    pk.rows = m.B; pk.cols = m.C; pk.src = noise; pk.ld = m.C;
-    pk.dst = g.w.X + t * g.sX() + g.uoff; pk.ldd = 2 * g.KXP; pk.lo_off = g.KXP;
+    pk.rows = ns * m.B; pk.cols = m.C; pk.src = noise; pk.ld = m.C;
+    pk.dst = g.w.X + g.uoff; pk.ldd = 2 * g.KXP; pk.lo_off = g.KXP;
+    pk.reps = m.T; pk.rep_stride = g.sX();
     SGG_TRY(pack_hl(pk, g.st));
   }
-  SGG_TRY(net_forward(g, 1));
-  // logits for all timesteps in one GEMM: rows t*B+b, h_{t+1} lives in X[t+1] (gen:88)
+  SGG_TRY(net_forward(g, ns));
+  // logits for all timesteps and streams in one GEMM: A rows t*NR + s*B + b (h_{t+1} lives in X[t+1], gen:88),
+  // stored stream-major: slot (slot0+s), row t*B+b
   sgg_gemm_desc_t d = gd_zero();
-  d.A = g.w.X + g.sX(); d.a_rows = (long long)m.T * m.B; d.a_cols = 2 * g.KXP; d.a_ld = 2 * g.KXP;
-  d.B = g.sh + g.L.sWdec; d.b_rows = m.H; d.b_cols = m.V; d.b_ld = g.L.pWdec; d.b_mn_major = 1;
-  d.M = m.T * m.B; d.N = m.V; d.nseg = 2;
-  d.seg_klen[0] = d.seg_klen[1] = m.H; d.seg_a_k[0] = g.hoff; d.seg_a_k[1] = g.KXP + g.hoff;
+  d.A = g.w.X + g.sX(); d.a_rows = (long long)m.T * g.NR; d.a_cols = 2 * g.KXP; d.a_ld = 2 * g.KXP;
+  d.B = g.sh + g.L.sWdec; d.b_rows = 2LL * g.L.rWdec; d.b_cols = m.V; d.b_ld = g.L.pWdec; d.b_mn_major = 1;
+  d.M = m.T * g.NR; d.N = m.V;
+  segs_act_weight(d, g.hoff, g.KXP, g.L.rWdec, true, m.H);
   d.bias = g.theta + g.L.bdec;
-  d.Chl = w.FAKE; d.ld_hl = 2 * m.VP; d.lo_off = m.VP;
+  d.Chl = fake_slot(w, m, slot0); d.ld_hl = 2 * m.VP; d.lo_off = m.VP;
+  d.out_d0 = g.NR; d.out_d1 = m.B; d.out_s0 = m.B; d.out_s1 = (long long)m.T * m.B;
   SGG_TRY(gemm(d, g.st));
-  if (logits_out) {  // [B,T,V] fp32 for the caller: one strided store per timestep
+  if (logits_out) {  // [B,T,V] fp32 for the caller (stream 0 only): one strided store per timestep
     for (int t = 0; t < m.T; ++t) {
       sgg_gemm_desc_t e = d;
       e.A = g.w.X + (t + 1) * g.sX(); e.a_rows = m.B; e.M = m.B;
+      e.out_d0 = 0;
       e.Chl = nullptr; e.C = logits_out + (long long)t * m.V; e.ldc = (long long)m.T * m.V;
       SGG_TRY(gemm(e, g.st));
     }
@@ -462,9 +487,9 @@ static int embed_dense(const Net& d, const Ws& w, const __nv_bfloat16* xhl) {
   const Dm& m = d.m;
   sgg_gemm_desc_t g = gd_zero();
   g.A = xhl; g.a_rows = (long long)m.T * m.B; g.a_cols = 2 * m.VP; g.a_ld = 2 * m.VP;
-  g.B = d.sh + d.L.sWemb; g.b_rows = m.V; g.b_cols = m.E; g.b_ld = d.L.pWemb; g.b_mn_major = 1;
-  g.M = m.T * m.B; g.N = m.E; g.nseg = 2;
-  g.seg_klen[0] = g.seg_klen[1] = m.VP; g.seg_a_k[1] = m.VP;
+  g.B = d.sh + d.L.sWemb; g.b_rows = 2LL * d.L.rWemb; g.b_cols = m.E; g.b_ld = d.L.pWemb; g.b_mn_major = 1;
+  g.M = m.T * m.B; g.N = m.E;
+  segs_act_weight(g, 0, m.VP, d.L.rWemb, true, m.VP);
   g.C = w.UF; g.ldc = m.EP;
   return gemm(g, d.st);
 }
@@ -479,9 +504,9 @@ static int embed_input_grad(const Net& d, const Ws& w, int blk, bool want_hl) {
   SGG_TRY(pack_hl(pk, d.st));
   sgg_gemm_desc_t g = gd_zero();
   g.A = w.UBH; g.a_rows = (long long)m.T * m.B; g.a_cols = 2 * m.EP; g.a_ld = 2 * m.EP;
-  g.B = d.sh + d.L.sWemb; g.b_rows = m.V; g.b_cols = m.E; g.b_ld = d.L.pWemb; g.b_mn_major = 0;
-  g.M = m.T * m.B; g.N = m.V; g.nseg = 2;
-  g.seg_klen[0] = g.seg_klen[1] = m.EP; g.seg_a_k[1] = m.EP;
+  g.B = d.sh + d.L.sWemb; g.b_rows = 2LL * d.L.rWemb; g.b_cols = m.E; g.b_ld = d.L.pWemb; g.b_mn_major = 0;
+  g.M = m.T * m.B; g.N = m.V;
+  segs_act_weight(g, 0, m.EP, d.L.rWemb, false, m.EP);
   g.C = w.DFAKE; g.ldc = m.VP;
   if (want_hl) { g.Chl = w.DFAKEH; g.ld_hl = 2 * m.VP; g.lo_off = m.VP; }
   return gemm(g, d.st);
@@ -507,29 +532,31 @@ extern "C" int sgg_param_table(int net, const sgg_dims_t* d, sgg_param_entry_t* 
   const ParamLayout L = param_layout(gen, *d);
   const char* pre = gen ? "Generator/Generator" : "Discriminator/Discriminator";
   int n = 0;
-  auto add = [&](const char* suffix, long long off, int rows, int cols, long long soff, int pitch, bool full_name) {
+  auto add = [&](const char* suffix, long long off, int rows, int cols, long long soff, int pitch, bool full_name,
+                 int srows = 0) {
     if (out && n < max_entries) {
       sgg_param_entry_t& e = out[n];
       memset(&e, 0, sizeof(e));
       if (full_name) snprintf(e.name, sizeof(e.name), "%s", suffix);
       else snprintf(e.name, sizeof(e.name), "%s/%s", pre, suffix);
-      e.offset = off; e.rows = rows; e.cols = cols; e.shadow_offset = soff; e.shadow_pitch = pitch;
+      e.offset = off; e.rows = rows; e.cols = cols; e.shadow_offset = soff; e.shadow_pitch = pitch; e.shadow_rows = srows;
     }
     ++n;
   };
   char buf[96];
-  add("attention_perceptron/kernel", L.Watt, L.R * L.C + L.H, L.R, L.sWa, L.pAtt, false);
+  // (the attention kernel's shadow is split into its annotation rows W_a at sWa and its state rows W_h at sWh)
+  add("attention_perceptron/kernel", L.Watt, L.R * L.C + L.H, L.R, L.sWa, L.pAtt, false, L.rWa);
   add("attention_perceptron/bias", L.batt, 1, L.R, -1, 0, false);
-  add("layer_norm_basic_lstm_cell/kernel", L.K, L.KX, 4 * L.H, L.sK, L.pK, false);
+  add("layer_norm_basic_lstm_cell/kernel", L.K, L.KX, 4 * L.H, L.sK, L.pK, false, L.rK);
   for (int i = 0; i < 5; ++i) {
     snprintf(buf, sizeof(buf), "layer_norm_basic_lstm_cell/%s/gamma", LN_NAMES[i]);
     add(buf, L.lng[i], 1, L.H, -1, 0, false);
     snprintf(buf, sizeof(buf), "layer_norm_basic_lstm_cell/%s/beta", LN_NAMES[i]);
     add(buf, L.lnb[i], 1, L.H, -1, 0, false);
   }
-  add("decoder/kernel", L.Wdec, L.H, L.OUT, L.sWdec, L.pWdec, false);
+  add("decoder/kernel", L.Wdec, L.H, L.OUT, L.sWdec, L.pWdec, false, L.rWdec);
   add("decoder/bias", L.bdec, 1, L.OUT, -1, 0, false);
-  if (!gen) add("Discriminator/W", L.Wemb, L.V, L.E, L.sWemb, L.pWemb, true);
+  if (!gen) add("Discriminator/W", L.Wemb, L.V, L.E, L.sWemb, L.pWemb, true, L.rWemb);
   if (n_entries) *n_entries = n;
   if (n_floats) *n_floats = L.total;
   if (n_shadow) *n_shadow = L.stotal;
@@ -549,6 +576,22 @@ extern "C" int sgg_refresh_shadow(int net, const sgg_dims_t* d, const float* the
   const int n = fill_adam_segs(L, seg);
   for (int i = 0; i < n; ++i) SGG_TRY(refresh_shadow(theta, (__nv_bfloat16*)shadow, seg[i], (cudaStream_t)stream));
   return 0;
+}
+
+struct AdamHyper { float lr, b1, b2, eps; };
+namespace sgg { int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st); }  // comm.cu
+// Adam with the step number taken from the device counter: step = iter[0] * step_mul + step_add.
+static int adam_dev(int net, const sgg_dims_t& d, float* theta, const float* grad, float* mm, float* vv, void* shadow,
+                    const AdamHyper& h, const long long* iter, long long step_mul, long long step_add, cudaStream_t st) {
+  const ParamLayout L = param_layout(net == 0, d);
+  AdamParams p{};
+  p.theta = theta; p.grad = grad; p.m = mm; p.v = vv; p.shadow = (__nv_bfloat16*)shadow;
+  p.lr = h.lr; p.b1 = h.b1; p.b2 = h.b2; p.eps = h.eps; p.gscale = 1.0f;
+  p.iter = iter; p.step_mul = step_mul; p.step_add = step_add;
+  p.nseg = fill_adam_segs(L, p.seg);
+  long long mx = 0;
+  for (int i = 0; i < p.nseg; ++i) mx = p.seg[i].n > mx ? p.seg[i].n : mx;
+  return adam(p, mx, st);
 }
 
 extern "C" int sgg_adam_step(int net, const sgg_dims_t* d, float* theta, const float* grad, float* m, float* v,
@@ -577,15 +620,15 @@ extern "C" int sgg_rng_fill_uniform(float* out, int64_t n, uint64_t seed, uint64
   return rng_fill(out, n, seed, offset, 0, (cudaStream_t)stream);
 }
 
-static int check_step(const sgg_step_args_t* a, bool need_d, bool need_labels) {
+static int check_step(const sgg_step_args_t* a, bool need_d, bool need_labels, bool need_noise = true) {
   SGG_CHECK(a != nullptr, "step: null args");
   SGG_TRY(check_dims(a->dims));
   SGG_CHECK(a->workspace && a->workspace_bytes >= ws_layout(a->dims, nullptr).bytes,
             "step: workspace too small (%lld < %lld)", (long long)a->workspace_bytes,
             (long long)ws_layout(a->dims, nullptr).bytes);
-  SGG_CHECK(a->g_theta && a->g_shadow && a->ann_g && a->noise, "step: missing generator inputs");
+  SGG_CHECK(a->g_theta && a->g_shadow && a->ann_g && (a->noise || !need_noise), "step: missing generator inputs");
   if (need_d) SGG_CHECK(a->d_theta && a->d_shadow && a->ann_d, "step: missing discriminator inputs");
-  if (need_labels) SGG_CHECK(a->labels && a->gp_alpha, "step: missing labels / gp_alpha");
+  if (need_labels) SGG_CHECK(a->labels && (a->gp_alpha || !need_noise), "step: missing labels / gp_alpha");
   SGG_CHECK(a->world >= 1, "step: world must be >= 1");
   return 0;
 }
@@ -596,7 +639,7 @@ extern "C" int sgg_gen_forward(const sgg_step_args_t* a, sgg_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const Ws w = ws_layout(a->dims, a->workspace);
   const Net g = make_net(true, a->dims, a->g_theta, a->g_shadow, nullptr, a->ann_g, w.g, a->dims.B, st);
-  return gen_forward(g, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out);
+  return gen_forward(g, w, a->noise, 1, 0, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out);
 }
 
 // D forward on caller-supplied float triples [B,T,V] (disc:73-93): scores [B,T].
@@ -630,26 +673,21 @@ extern "C" int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, 
 
 // One discriminator step (train:365): grads of disc_cost = mean D(G(z)) - mean D(real) + lam * GP
 // w.r.t. every Discriminator* variable into d_grad; scalars[1] = w_disc, scalars[2] = gp.
-extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
-  SGG_TRY(check_step(a, true, true));
-  SGG_CHECK(a->d_grad && a->scalars, "sgg_disc_step: missing d_grad / scalars");
-  cudaStream_t st = (cudaStream_t)stream;
+// `fake` = the generator's logits for this step (hi/lo rows t*B+b, a constant here), already computed.
+static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bfloat16* fake, const float* gp_alpha,
+                          float* scalars, cudaStream_t st) {
   const sgg_dims_t& dd = a->dims;
-  const Ws w = ws_layout(dd, a->workspace);
-  const Net g = make_net(true, dd, a->g_theta, a->g_shadow, nullptr, a->ann_g, w.g, dd.B, st);
   const Net d = make_net(false, dd, a->d_theta, a->d_shadow, a->d_grad, a->ann_d, w.d, 4 * dd.B, st);
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
   const float invBT = 1.0f / ((float)B * a->world * T);
   SGG_CUDA(cudaMemsetAsync(a->d_grad, 0, (size_t)d.L.total * 4, st));
-  SGG_CUDA(cudaMemsetAsync(a->scalars, 0, 4 * sizeof(float), st));
-  // 1. fake = G(a_g, noise)  (constant for this step)
-  SGG_TRY(gen_forward(g, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out));
+  SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
   // 2. embeddings of the three streams
-  SGG_TRY(embed_dense(d, w, w.FAKE));
+  SGG_TRY(embed_dense(d, w, fake));
   EmbedMixParams em{};
   em.B = B; em.T = T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
-  em.labels = a->labels; em.Wemb = a->d_theta + d.L.Wemb; em.gp_alpha = a->gp_alpha;
+  em.labels = a->labels; em.Wemb = a->d_theta + d.L.Wemb; em.gp_alpha = gp_alpha;
   em.blk_fake = 0; em.blk_real = 1; em.blk_int = 2;
   em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
   SGG_TRY(embed_mix(em, st));
@@ -657,14 +695,14 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
   SGG_TRY(net_attn_proj(d));
   SGG_TRY(net_init_state(d, 3));
   SGG_TRY(net_forward(d, 3));
-  LossParams lp{B, T, d.w.Y, 0, 1, invBT, a->scalars};
+  LossParams lp{B, T, d.w.Y, 0, 1, invBT, scalars};
   SGG_TRY(losses(lp, st));
   // 4. g = d sum D(x_hat) / d x_hat : data-path reverse on the interp block
   RevCfg ig{};
   ig.blk0 = 2; ig.nblk = 1; ig.tan_pblk = -1; ig.tan_blk = -1; ig.ybar_blk[2] = 1.0f; ig.wgrad = false;
   SGG_TRY(net_reverse(d, ig));
   SGG_TRY(embed_input_grad(d, w, 2, false));
-  GpSlopesParams sp{B, T, m.V, w.DFAKE, m.VP, w.slopes, w.coef, a->scalars, 1.0f / ((float)B * a->world)};
+  GpSlopesParams sp{B, T, m.V, w.DFAKE, m.VP, w.slopes, w.coef, scalars, 1.0f / ((float)B * a->world)};
   SGG_TRY(gp_slopes(sp, st));
   // 5. tangent forward along v = coef * g
   {
@@ -699,7 +737,7 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
     pk.rows = T * B; pk.cols = m.E; pk.rpg = B;
     pk.src = d.w.XB + d.uoff; pk.ld = d.KXP; pk.gstride = d.sXB();
     pk.src2 = d.w.XB + 2LL * B * d.KXP + d.uoff; pk.ld2 = d.KXP; pk.gstride2 = d.sXB();
-    pk.mix = a->gp_alpha; pk.mmod = B;
+    pk.mix = gp_alpha; pk.mmod = B;
     pk.dst = w.UBH; pk.ldd = 2 * m.EP; pk.lo_off = m.EP;
     SGG_TRY(pack_hl(pk, st));
     PackParams pt{};
@@ -709,7 +747,7 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
     SGG_TRY(pack_hl(pt, st));
     for (int which = 0; which < 2; ++which) {
       sgg_gemm_desc_t q = gd_zero();
-      q.A = which == 0 ? w.FAKE : w.VHL; q.a_rows = (long long)T * B; q.a_cols = 2 * m.VP; q.a_ld = 2 * m.VP; q.a_mn_major = 1;
+      q.A = which == 0 ? fake : w.VHL; q.a_rows = (long long)T * B; q.a_cols = 2 * m.VP; q.a_ld = 2 * m.VP; q.a_mn_major = 1;
       q.B = which == 0 ? w.UBH : w.UDB; q.b_rows = (long long)T * B; q.b_cols = 2 * m.EP; q.b_ld = 2 * m.EP; q.b_mn_major = 1;
       q.M = m.V; q.N = m.E; q.nseg = 3;
       for (int s = 0; s < 3; ++s) q.seg_klen[s] = T * B;
@@ -718,7 +756,7 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
       SGG_TRY(gemm(q, st));
     }
     EmbedScatterParams es{};
-    es.B = B; es.T = T; es.E = m.E; es.labels = a->labels; es.gp_alpha = a->gp_alpha;
+    es.B = B; es.T = T; es.E = m.E; es.labels = a->labels; es.gp_alpha = gp_alpha;
     es.XB = d.w.XB; es.ldXB = d.KXP; es.strideT = d.sXB(); es.uoff = d.uoff;
     es.blk_real = 1; es.blk_int = 2; es.dWemb = a->d_grad + d.L.Wemb;
     SGG_TRY(embed_scatter(es, st));
@@ -726,24 +764,33 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
   return 0;
 }
 
-// One generator step (train:368): grads of gen_cost = -mean D(G(z)) w.r.t. every Generator*
-// variable into g_grad; scalars[3] = gen_cost.
-extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
-  SGG_TRY(check_step(a, true, false));
-  SGG_CHECK(a->g_grad && a->scalars, "sgg_gen_step: missing g_grad / scalars");
+extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
+  SGG_TRY(check_step(a, true, true));
+  SGG_CHECK(a->d_grad && a->scalars, "sgg_disc_step: missing d_grad / scalars");
   cudaStream_t st = (cudaStream_t)stream;
   const sgg_dims_t& dd = a->dims;
   const Ws w = ws_layout(dd, a->workspace);
+  const Net g = make_net(true, dd, a->g_theta, a->g_shadow, nullptr, a->ann_g, w.g, dd.B, st);
+  // 1. fake = G(a_g, noise)  (constant for this step)
+  SGG_TRY(gen_forward(g, w, a->noise, 1, 0, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out));
+  return disc_step_core(a, w, fake_slot(w, g.m, 0), a->gp_alpha, a->scalars, st);
+}
+
+// One generator step (train:368): grads of gen_cost = -mean D(G(z)) w.r.t. every Generator*
+// variable into g_grad; scalars[3] = gen_cost.
+static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noise, bool recompute_proj, float* scalars,
+                         cudaStream_t st) {
+  const sgg_dims_t& dd = a->dims;
   const Net g = make_net(true, dd, a->g_theta, a->g_shadow, a->g_grad, a->ann_g, w.g, dd.B, st);
   const Net d = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, dd.B, st);
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
   const float invBT = 1.0f / ((float)B * a->world * T);
   SGG_CUDA(cudaMemsetAsync(a->g_grad, 0, (size_t)g.L.total * 4, st));
-  SGG_CUDA(cudaMemsetAsync(a->scalars, 0, 4 * sizeof(float), st));
-  SGG_TRY(gen_forward(g, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->logits_out));
+  SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
+  SGG_TRY(gen_forward(g, w, noise, 1, 0, recompute_proj, a->logits_out));
   // D(fake), single stream
-  SGG_TRY(embed_dense(d, w, w.FAKE));
+  SGG_TRY(embed_dense(d, w, fake_slot(w, m, 0)));
   EmbedMixParams em{};
   em.B = B; em.T = T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
   em.blk_fake = 0; em.blk_real = -1; em.blk_int = -1;
@@ -752,7 +799,7 @@ extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
   SGG_TRY(net_attn_proj(d));
   SGG_TRY(net_init_state(d, 1));
   SGG_TRY(net_forward(d, 1));
-  LossParams lp{B, T, d.w.Y, 0, -1, invBT, a->scalars};
+  LossParams lp{B, T, d.w.Y, 0, -1, invBT, scalars};
   SGG_TRY(losses(lp, st));
   // d gen_cost / d fake through D's data path
   RevCfg rd{};
@@ -763,9 +810,9 @@ extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
   {
     sgg_gemm_desc_t q = gd_zero();
     q.A = w.DFAKEH; q.a_rows = (long long)T * B; q.a_cols = 2 * m.VP; q.a_ld = 2 * m.VP;
-    q.B = g.sh + g.L.sWdec; q.b_rows = m.H; q.b_cols = m.V; q.b_ld = g.L.pWdec; q.b_mn_major = 0;
-    q.M = T * B; q.N = m.H; q.nseg = 2;
-    q.seg_klen[0] = q.seg_klen[1] = m.VP; q.seg_a_k[1] = m.VP;
+    q.B = g.sh + g.L.sWdec; q.b_rows = 2LL * g.L.rWdec; q.b_cols = m.V; q.b_ld = g.L.pWdec; q.b_mn_major = 0;
+    q.M = T * B; q.N = m.H;
+    segs_act_weight(q, 0, m.VP, g.L.rWdec, false, m.VP);
     q.C = w.HB; q.ldc = m.H;
     SGG_TRY(gemm(q, st));
   }
@@ -784,6 +831,64 @@ extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
     SGG_TRY(colsum(w.DFAKE, m.VP, T * B, m.V, a->g_grad + g.L.bdec, st));
   }
   return 0;
+}
+
+extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
+  SGG_TRY(check_step(a, true, false));
+  SGG_CHECK(a->g_grad && a->scalars, "sgg_gen_step: missing g_grad / scalars");
+  const Ws w = ws_layout(a->dims, a->workspace);
+  return gen_step_core(a, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->scalars, (cudaStream_t)stream);
+}
+
+// ============================================================================ one training iteration
+// train:362-368 on one batch (train:185-187): critic_iters x {D step, Adam(D)} then {G step, Adam(G)}, with
+// fresh noise / interpolation coefficients per step drawn on the device.  The generator is constant during the
+// critic steps, so its forwards for ALL critic steps run first as one batched forward (their noise draws
+// share each annotation tile read).  Everything is enqueued on `stream` and depends on the host only through
+// the arguments, so one call can be captured into a CUDA graph and replayed: the iteration counter, RNG
+// position and Adam step numbers live in device memory (`counters`).
+extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t stream) {
+  SGG_CHECK(it != nullptr, "sgg_train_iteration: null args");
+  const sgg_step_args_t* a = &it->step;
+  SGG_TRY(check_step(a, true, true, false));
+  SGG_CHECK(a->g_grad && a->d_grad, "sgg_train_iteration: missing gradient buckets");
+  SGG_CHECK(it->g_m && it->g_v && it->d_m && it->d_v, "sgg_train_iteration: missing Adam moments");
+  SGG_CHECK(it->critic_iters >= 0 && it->critic_iters <= a->dims.S, "sgg_train_iteration: critic_iters=%d exceeds dims.S=%d",
+            it->critic_iters, a->dims.S);
+  SGG_CHECK(it->counters && it->noise_all && it->gp_alpha_all && it->scalars_all, "sgg_train_iteration: missing buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sgg_dims_t& dd = a->dims;
+  const Ws w = ws_layout(dd, a->workspace);
+  const Dm m = derive(dd);
+  const int nc = it->critic_iters;
+  const long long* iter = reinterpret_cast<const long long*>(it->counters);
+  // ---- fresh randomness for every step of this iteration (Philox position = f(iteration counter))
+  const long long n_noise = (long long)(nc + 1) * m.B * m.C, n_alpha = (long long)nc * m.B;
+  const uint64_t per_iter = (uint64_t)((n_noise + 3) / 4 + (n_alpha + 3) / 4);
+  SGG_TRY(rng_fill(it->noise_all, n_noise, it->seed, 0, 1, st, iter, per_iter));
+  SGG_TRY(rng_fill(it->gp_alpha_all, n_alpha, it->seed, (uint64_t)((n_noise + 3) / 4), 0, st, iter, per_iter));
+  // ---- generator forwards of all critic steps, MAX_GEN_STREAMS draws per pass
+  bool fresh = true;
+  for (int s0 = 0; s0 < nc; s0 += m.GS) {
+    const int ns = nc - s0 < m.GS ? nc - s0 : m.GS;
+    const Net g = make_net(true, dd, a->g_theta, a->g_shadow, nullptr, a->ann_g, w.g, ns * m.B, st);
+    SGG_TRY(gen_forward(g, w, it->noise_all + (long long)s0 * m.B * m.C, ns, s0, fresh, nullptr));
+    fresh = false;
+  }
+  // ---- critic steps
+  AdamHyper hp{it->lr, it->beta1, it->beta2, it->eps};
+  for (int i = 0; i < nc; ++i) {
+    SGG_TRY(disc_step_core(a, w, fake_slot(w, m, i), it->gp_alpha_all + (long long)i * m.B, it->scalars_all + 4 * i, st));
+    if (it->comm) SGG_TRY(comm_allreduce(it->comm, a->d_grad, param_layout(false, dd).total, st));
+    SGG_TRY(adam_dev(1, dd, const_cast<float*>(a->d_theta), a->d_grad, it->d_m, it->d_v, const_cast<void*>(a->d_shadow), hp,
+                     iter, nc, i + 1, st));
+  }
+  // ---- generator step (its own forward keeps the activations the reverse pass needs)
+  SGG_TRY(gen_step_core(a, w, it->noise_all + (long long)nc * m.B * m.C, fresh, it->scalars_all + 4 * nc, st));
+  if (it->comm) SGG_TRY(comm_allreduce(it->comm, a->g_grad, param_layout(true, dd).total, st));
+  SGG_TRY(adam_dev(0, dd, const_cast<float*>(a->g_theta), a->g_grad, it->g_m, it->g_v, const_cast<void*>(a->g_shadow), hp,
+                   iter, 1, 1, st));
+  return bump_counter(reinterpret_cast<long long*>(it->counters), st);
 }
 
 // Debug / test accessor: location of an intermediate buffer inside the workspace.

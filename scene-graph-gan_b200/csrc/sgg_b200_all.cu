@@ -5,3 +5,4 @@
 #include "lstm.cu"
 #include "misc.cu"
 #include "plan.cu"
+#include "comm.cu"

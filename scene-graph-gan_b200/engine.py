@@ -6,7 +6,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import FLAG_REFRESH_GEN_PROJ, Dims, StepArgs, check, lib, stream_ptr
+from ._lib import FLAG_REFRESH_GEN_PROJ, Dims, IterArgs, StepArgs, check, lib, stream_ptr
 from .params import DISC, GEN, ParamBucket, make_dims
 
 
@@ -18,10 +18,11 @@ class Engine:
     """One data-parallel rank of the WGAN-GP hot path (train.py:231-266, 362-368)."""
 
     def __init__(self, B: int, T: int = 3, V: int = 2000, R: int = 196, E: int = 300, lam: float = 10.0,
-                 world: int = 1, seed: int = 0, device="cuda"):
+                 world: int = 1, seed: int = 0, device="cuda", critic_iters: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("sgg_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.dims: Dims = make_dims(B, T, V, R, 512, 512, E)
+        self.critic_iters = int(critic_iters)
+        self.dims: Dims = make_dims(B, T, V, R, 512, 512, E, S=max(1, self.critic_iters))
         self.B, self.T, self.V, self.R, self.E = B, T, V, R, E
         self.lam, self.world, self.device = float(lam), int(world), device
         nbytes = lib().sgg_workspace_bytes
@@ -39,6 +40,12 @@ class Engine:
         self.ann_g = self.ann_d = self.labels = None
         self._refresh = True
         self.seed, self._rng_off = seed, 0
+        # sgg_train_iteration state: device-side iteration counter, per-step randomness and losses
+        nc = max(1, self.critic_iters)
+        self.counters = torch.zeros(1, dtype=torch.int64, device=device)
+        self.noise_all = torch.zeros(nc + 1, B, 512, dtype=torch.float32, device=device)
+        self.gp_alpha_all = torch.zeros(nc, B, dtype=torch.float32, device=device)
+        self.scalars_all = torch.zeros(nc + 1, 4, dtype=torch.float32, device=device)
 
     # ------------------------------------------------------------------ inputs
     def set_batch(self, ann_g: torch.Tensor, ann_d: torch.Tensor, labels: Optional[torch.Tensor]) -> None:
@@ -103,6 +110,26 @@ class Engine:
         a = self._args()
         check(lib().sgg_gen_step(C.byref(a), stream_ptr(stream)), "sgg_gen_step")
         self._refresh = False
+
+    def train_iteration(self, critic_iters: Optional[int] = None, comm=None, lr=1e-4, beta1=0.5, beta2=0.9,
+                        eps=1e-8, stream=None) -> None:
+        """One reference loop body (train.py:362-368): critic_iters D steps + 1 G step with their Adam
+        updates, randomness drawn on the device.  Per-step losses land in self.scalars_all.  Safe to
+        capture into a CUDA graph (no host-dependent state)."""
+        nc = self.critic_iters if critic_iters is None else int(critic_iters)
+        it = IterArgs()
+        it.step = self._args()
+        it.critic_iters = nc
+        it.g_m, it.g_v, it.d_m, it.d_v = (self.g.m.data_ptr(), self.g.v.data_ptr(), self.d.m.data_ptr(),
+                                          self.d.v.data_ptr())
+        it.lr, it.beta1, it.beta2, it.eps = lr, beta1, beta2, eps
+        it.seed = self.seed
+        it.counters = self.counters.data_ptr()
+        it.noise_all, it.gp_alpha_all = self.noise_all.data_ptr(), self.gp_alpha_all.data_ptr()
+        it.scalars_all = self.scalars_all.data_ptr()
+        it.comm = comm
+        check(lib().sgg_train_iteration(C.byref(it), stream_ptr(stream)), "sgg_train_iteration")
+        self._refresh = True   # the generator was updated
 
     def ws_view(self, name: str, shape, dtype) -> torch.Tensor:
         """Test accessor: a view of a named workspace buffer."""

@@ -19,8 +19,8 @@ from ._lib import Dims, ParamEntry, check, lib, stream_ptr
 GEN, DISC = 0, 1
 
 
-def make_dims(B, T, V, R=196, C_=512, H=512, E=300) -> Dims:
-    return Dims(B=B, T=T, V=V, R=R, C=C_, H=H, E=E)
+def make_dims(B, T, V, R=196, C_=512, H=512, E=300, S=1) -> Dims:
+    return Dims(B=B, T=T, V=V, R=R, C=C_, H=H, E=E, S=S)
 
 
 class ParamBucket:
@@ -31,6 +31,7 @@ class ParamBucket:
         ents = (ParamEntry * n.value)()
         check(lib().sgg_param_table(net, C.byref(dims), ents, n.value, C.byref(n), C.byref(nf), C.byref(ns)), "sgg_param_table")
         self.entries = [(e.name.decode(), e.offset, e.rows, e.cols, e.shadow_offset, e.shadow_pitch) for e in ents]
+        self.shadow_rows = {e.name.decode(): e.shadow_rows for e in ents}
         self.n_floats, self.n_shadow = nf.value, ns.value
         self.theta = torch.zeros(self.n_floats, dtype=torch.float32, device=device)
         self.grad = torch.zeros_like(self.theta)

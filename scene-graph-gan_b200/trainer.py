@@ -3,25 +3,33 @@
 One iteration = ``critic_iters`` discriminator steps followed by one generator step, all on the
 same data batch (train.py:185-187 repeats each batch CRITIC_ITERS+1 times), fresh noise
 (gen:81) and fresh interpolation coefficients (tfgan gradient penalty) per step, two
-tf.train.AdamOptimizer(1e-4, beta1=0.5, beta2=0.9) updates (train.py:258-266).
+tf.train.AdamOptimizer(1e-4, beta1=0.5, beta2=0.9) updates (train.py:258-266).  The whole
+iteration is ONE C-ABI call (sgg_train_iteration) that is captured once per input-buffer set
+into a CUDA graph and replayed.
 
 Data parallelism (the reference has none): one process per GPU, the batch is sharded
 over ranks, the kernels normalise every loss by the GLOBAL batch, so the only exchange is one
-sum-allreduce of the flat gradient bucket per optimiser step (NCCL over NVLink/NVSwitch).
+sum of the flat gradient bucket per optimiser step (NCCL over NVLink/NVSwitch, enqueued by the
+library on the compute stream, inside the graph).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, Iterable, Optional, Tuple
 
 import torch
 
+from ._lib import check, lib
 from .engine import Engine
+
+COMM_ID_BYTES = 128
 
 
 class HotPathTrainer:
     def __init__(self, batch_size: int, n_steps: int = 3, vocab_size: int = 2000, critic_iters: int = 5,
                  lam: float = 10.0, regions: int = 196, embed_dim: int = 300, seed: int = 0,
-                 embedding: Optional[torch.Tensor] = None, process_group=None, device=None):
+                 embedding: Optional[torch.Tensor] = None, process_group=None, device=None,
+                 use_graph: bool = True, lr: float = 1e-4, beta1: float = 0.5, beta2: float = 0.9):
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.pg = process_group
@@ -29,62 +37,104 @@ class HotPathTrainer:
         self.rank = self.dist.get_rank(process_group) if self.dist else 0
         self.B, self.T, self.V, self.R = batch_size, n_steps, vocab_size, regions
         self.critic_iters, self.lam = int(critic_iters), float(lam)
+        self.lr, self.beta1, self.beta2 = lr, beta1, beta2
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         # identical initial weights on every rank (same seed); decorrelated noise / alpha streams per rank
         self.eng = Engine(batch_size, n_steps, vocab_size, regions, embed_dim, lam=lam, world=self.world,
-                          seed=(seed * 1000003 + 7919 * self.rank) & 0x7FFFFFFF, device=self.device)
+                          seed=(seed * 1000003 + 7919 * self.rank) & 0x7FFFFFFF, device=self.device,
+                          critic_iters=self.critic_iters)
         self.eng.g.init_reference(seed * 2 + 1)
         self.eng.d.init_reference(seed * 2 + 2, embedding=embedding)
+        self.comm = self._init_comm() if self.world > 1 else None
         self.iterations = 0
+        self.use_graph = use_graph
+        self._graphs: Dict[Tuple[int, int, int], Tuple[torch.cuda.CUDAGraph, int]] = {}
+        self.kernel_launches = 0          # kernels of this library executed so far (graph replays included)
         # double-buffered device staging for host batches
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._slots = [None, None]
         self._slot_ready = [None, None]
         self._cur = 0
-        self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._loss_host = torch.zeros(self.critic_iters + 1, 4, dtype=torch.float32).pin_memory()
         self.h2d_bytes_per_batch = 2 * batch_size * regions * 512 * 2 + batch_size * n_steps * 8
-        self.d2h_bytes_per_iteration = 16
+        self.d2h_bytes_per_iteration = self._loss_host.numel() * 4
+
+    # ------------------------------------------------------------------ communicator
+    def _init_comm(self):
+        ident = (C.c_ubyte * COMM_ID_BYTES)()
+        if self.rank == 0:
+            check(lib().sgg_comm_unique_id(ident), "sgg_comm_unique_id")
+        box = [bytes(ident)]
+        self.dist.broadcast_object_list(box, src=0, group=self.pg)
+        handle = C.c_void_p(0)
+        check(lib().sgg_comm_init(box[0], C.c_int32(self.rank), C.c_int32(self.world), C.byref(handle)), "sgg_comm_init")
+        return handle
+
+    def close(self) -> None:
+        if self.comm is not None:
+            torch.cuda.synchronize()
+            self._graphs.clear()
+            lib().sgg_comm_destroy(self.comm)
+            self.comm = None
 
     # ------------------------------------------------------------------ device-resident path
     def set_batch(self, ann_g: torch.Tensor, ann_d: torch.Tensor, labels: torch.Tensor) -> None:
         self.eng.set_batch(ann_g, ann_d, labels)
 
-    def _allreduce(self, bucket) -> None:
-        if self.world > 1:
-            self.dist.all_reduce(bucket.grad, op=self.dist.ReduceOp.SUM, group=self.pg)
+    def _launch_count(self) -> int:
+        fn = lib().sgg_launch_count
+        fn.restype = C.c_int64
+        return int(fn())
 
-    def disc_step(self) -> None:
-        """train.py:365 sess.run(disc_train_op)."""
-        e = self.eng
-        e.sample_noise()
-        e.sample_gp_alpha()
-        e.disc_step()
-        self._allreduce(e.d)
-        e.d.adam_step()
-
-    def gen_step(self) -> None:
-        """train.py:368 sess.run(gen_train_op)."""
-        e = self.eng
-        e.sample_noise()
-        e.gen_step()
-        self._allreduce(e.g)
-        e.g.adam_step()
-        e._refresh = True          # generator weights changed: its hoisted projection is stale
+    def _run_iteration_eager(self) -> None:
+        self.eng.train_iteration(self.critic_iters, comm=self.comm, lr=self.lr, beta1=self.beta1, beta2=self.beta2)
 
     def iteration(self) -> None:
         """train.py:362-368 loop body on the batch given to set_batch()."""
-        for _ in range(self.critic_iters):
-            self.disc_step()
-        self.gen_step()
+        e = self.eng
+        if not self.use_graph:
+            n0 = self._launch_count()
+            self._run_iteration_eager()
+            self.kernel_launches += self._launch_count() - n0
+        else:
+            key = (e.ann_g.data_ptr(), e.ann_d.data_ptr(), e.labels.data_ptr())
+            entry = self._graphs.get(key)
+            if entry is None:
+                if len(self._graphs) >= 8:
+                    self._graphs.clear()
+                # warm-up outside capture (lazy kernel attribute setup), on a side stream as capture requires
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    n0 = self._launch_count()
+                    self._run_iteration_eager()
+                    self.kernel_launches += self._launch_count() - n0
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                n0 = self._launch_count()
+                with torch.cuda.graph(graph, stream=side):
+                    self._run_iteration_eager()
+                entry = (graph, self._launch_count() - n0)
+                self._graphs[key] = entry
+                # the eager warm-up above already performed this call's iteration
+            else:
+                entry[0].replay()
+                self.kernel_launches += entry[1]
+        e.d.step += self.critic_iters
+        e.g.step += 1
         self.iterations += 1
 
     def losses(self) -> Dict[str, float]:
-        """Host copy of the last step's scalars (forces a stream sync, 16 bytes D2H).  With world > 1
+        """Host copy of the last iteration's per-step scalars (one small D2H + stream sync).  With world > 1
         these are this rank's shard of the global means (sum over ranks = the global value)."""
-        self._loss_host.copy_(self.eng.scalars, non_blocking=True)
+        self._loss_host.copy_(self.eng.scalars_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        w, gp, gc = (float(x) for x in self._loss_host[1:4])
-        return {"w_disc": w, "gp": gp, "disc_cost": w + self.lam * gp, "gen_cost": gc}
+        nc = self.critic_iters
+        out = {"gen_cost": float(self._loss_host[nc, 3])}
+        if nc > 0:
+            w, gp = float(self._loss_host[nc - 1, 1]), float(self._loss_host[nc - 1, 2])
+            out.update({"w_disc": w, "gp": gp, "disc_cost": w + self.lam * gp})
+        return out
 
     # ------------------------------------------------------------------ host-buffer path (end to end)
     def _alloc_slot(self):
@@ -116,7 +166,7 @@ class HotPathTrainer:
 
     def fit(self, host_batches: Iterable[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]):
         """Trains one iteration per host batch; the upload of batch i+1 overlaps the compute of batch i.
-        Yields the losses of every iteration (a 16-byte D2H read per iteration)."""
+        Yields the losses of every iteration (a small D2H read per iteration)."""
         it = iter(host_batches)
         try:
             nxt = self.upload(*next(it))
