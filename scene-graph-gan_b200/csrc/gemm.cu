@@ -3,6 +3,8 @@
 //
 // Replaces every tf MatMul of the reference hot path (gen:15,79/87,88; disc:87,90) and the
 // MatMul gradients TF registers for them.  See include/sgg_b200.h (sgg_gemm_desc_t).
+#include <cmath>
+
 #include "common.cuh"
 #include "../../include/sgg_b200.h"
 
@@ -175,12 +177,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
       const bool full = (col0 + 32 <= p.N);
-      if (p.bias) {
+      if (p.bias && blockIdx.z == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
       }
-      if (addrow) {
+      if (addrow && blockIdx.z == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (full || col0 + j < p.N) v[j] += __ldg(addrow + col0 + j);
@@ -188,9 +190,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (p.C) {
         float* crow = p.C + orow * p.ldc + col0;
         if (p.atomic) {
+          if (full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || col0 + j < p.N) atomicAdd(crow + j, v[j]);
+            for (int j = 0; j < 32; j += 4)   // 16-byte vector reduction (sm_90+): 4x fewer L2 atomic operations
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j), "f"(v[j]), "f"(v[j + 1]),
+                           "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || col0 + j < p.N) atomicAdd(crow + j, v[j]);
+          }
         } else if (full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -290,18 +300,47 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
   kp.addm = d.addm; kp.ld_addm = d.ld_addm; kp.add_mod = d.add_mod > 0 ? d.add_mod : 1;
   kp.alpha = d.alpha;
   kp.rm_d0 = d.out_d0; kp.rm_d1 = d.out_d1 > 0 ? d.out_d1 : 1; kp.rm_s0 = d.out_s0; kp.rm_s1 = d.out_s1;
-  int splits = d.splits > 1 ? d.splits : 1;
-  if (splits > kp.total_kb) splits = kp.total_kb;
-  SGG_CHECK(splits == 1 || (d.atomic && d.C && !d.Chl && !d.bias && !d.addm),
-            "sgg_gemm: split-K needs the atomic fp32 epilogue only");
-  int bn = d.block_n;
-  if (bn == 0) {
-    const int tm = (d.M + BM - 1) / BM;
-    if (d.N <= 64) bn = 64;
-    else if (d.N <= 128) bn = 128;
-    else bn = (tm * ((d.N + 255) / 256) * splits >= 120) ? 256 : 128;
+  // ---- tile width and split-K.  These GEMMs are small (M = a few hundred rows) and long in K (three bf16
+  // products per contraction), so a plain tile grid leaves most of the 148 SMs idle.  Unless the caller fixed
+  // them, pick (block_n, splits) minimising a simple cost: waves x (k-blocks per CTA x tile bytes / L2 feed rate).
+  // A split-K launch accumulates with fp32 vector reductions into an output that is zeroed first (or, when the
+  // caller asked for `atomic`, into whatever the output already holds).
+  const int tm = (d.M + BM - 1) / BM;
+  const bool can_split = d.C && !d.Chl;
+  int bn = d.block_n, splits = d.splits > 1 ? d.splits : 1;
+  if (d.splits <= 0 || d.block_n == 0) {
+    double best = 1e30;
+    int best_bn = 128, best_sp = 1;
+    const int bn_lo = d.block_n ? d.block_n : 64, bn_hi = d.block_n ? d.block_n : 256;
+    for (int b = bn_lo; b <= bn_hi; b *= 2) {
+      if (b > 64 && d.N <= b / 2 && !d.block_n) continue;         // do not pad N by more than 2x
+      const int tiles = tm * ((d.N + b - 1) / b);
+      const int sp_hi = (d.splits > 0) ? splits : (can_split && tiles < 148 ? 148 / tiles : 1);
+      for (int sp = (d.splits > 0 ? splits : 1); sp <= sp_hi; ++sp) {
+        if (sp > kp.total_kb) break;
+        const int kb_per = (kp.total_kb + sp - 1) / sp;
+        if (sp > 1 && kb_per < 4) break;
+        const int ctas = tiles * sp;
+        const int waves = (ctas + 147) / 148;
+        const int conc = ctas < 148 ? ctas : 148;                  // CTAs competing for the L2 -> SM feed
+        const double feed = 6300.0 / conc < 100.0 ? 6300.0 / conc : 100.0;   // bytes / cycle / SM
+        const double kb_cyc = fmax((double)(BM + b) * BK * 2 / feed, 2.0 * b);   // TMA-bound vs MMA-bound k-block
+        const double epi = 600.0 + 6.0 * b * (sp > 1 ? 2.0 : 1.0);
+        const double cost = waves * (1500.0 + kb_per * kb_cyc + epi) + (sp > 1 ? 1500.0 : 0.0);
+        if (cost < best) { best = cost; best_bn = b; best_sp = sp; }
+      }
+    }
+    bn = best_bn;
+    splits = best_sp;
   }
+  if (splits > kp.total_kb) splits = kp.total_kb;
+  SGG_CHECK(splits == 1 || can_split, "sgg_gemm: split-K needs the fp32 output only");
   SGG_CHECK(bn == 64 || bn == 128 || bn == 256, "sgg_gemm: block_n=%d unsupported", bn);
+  if (splits > 1 && !d.atomic) {   // overwrite semantics: clear the output, then accumulate
+    SGG_CHECK(d.out_d0 == 0, "sgg_gemm: split-K with an output row permutation is not supported");
+    SGG_CUDA(cudaMemset2DAsync(d.C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, stream));
+    kp.atomic = 1;
+  }
   CUtensorMap tmA, tmB;
   // K-major: tensor [MN rows, K cols], box {64 k, tile rows}.  MN-major: tensor [K rows, MN cols], box {64 mn, 64 k}.
   SGG_TRY(make_tmap_bf16_2d(&tmA, d.A, d.a_rows, d.a_cols, d.a_ld, 64, d.a_mn_major ? BK : BM));

@@ -1,4 +1,4 @@
-// LayerNormBasicLSTMCell(512) pointwise stages (gen:79,87 / disc:81,89), one warp per row:
+// LayerNormBasicLSTMCell(512) pointwise stages (gen:79,87 / disc:81,89):
 //   lstm_fwd : i,j,f,o = LN(split(q)); c' = c*sigmoid(f+1) + sigmoid(i)*tanh(j); c_new = LN(c');
 //              h = tanh(c_new)*sigmoid(o); optional D head y = h.w_dec + b (disc:90)
 //   lstm_tan : forward tangent (JVP) of the same, for the WGAN-GP interpolate stream
@@ -6,32 +6,32 @@
 //              gradients and the D head's w_dec / b_dec gradients.
 // The gate pre-activations q = [z,u,h] K come from the tcgen05 GEMM; all statistics stay fp32
 // (LN eps = 1e-12).  Everything is recomputed from (q, c_in) in the reverse pass.
+//
+// Work decomposition: one CTA of 4 warps per row.  The rows are few (a few hundred) and each row is a long
+// dependent chain of 512-wide reductions, so the row is split two ways:
+//   gate phases  (A: LN + nonlinearity of one gate, C: its reverse)  -> warp G owns gate G, lane owns 16 columns
+//   state phase  (B: cell update, LN(state), h and their reverse)    -> thread owns 4 columns, block reductions
+// with the gate activations / their adjoints exchanged through shared memory.
 #include "common.cuh"
 #include "../../include/sgg_b200.h"
 
 namespace sgg {
 
 constexpr int LH = 512;             // LSTM units
-constexpr int LS_WARPS = 4;
-constexpr int LS_THREADS = LS_WARPS * 32;
+constexpr int LS_THREADS = 128;     // 4 warps: one per gate
 constexpr float LN_EPS_F = 1e-12f;
 constexpr float FORGET_BIAS_F = 1.0f;
+constexpr float INV_LH = 1.0f / LH;
 
 typedef float V16[16];
 
+// ---- warp-per-gate helpers: lane owns columns lane*4 + 128*i + e
 __device__ __forceinline__ void ld16(const float* base, V16& v) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 t = *reinterpret_cast<const float4*>(base + lane * 4 + 128 * i);
     v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void ld16_or_zero(const float* base, V16& v) {
-  if (base) ld16(base, v);
-  else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.f;
   }
 }
 __device__ __forceinline__ void st16(float* base, const V16& v) {
@@ -53,43 +53,124 @@ __device__ __forceinline__ void st16_hl(__nv_bfloat16* base, long long lo_off, c
         make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
   }
 }
+__device__ __forceinline__ void acc16(float* base, const V16& v) {   // base[col] += v (lane-owned columns)
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4* p = reinterpret_cast<float4*>(base + lane * 4 + 128 * i);
+    float4 t = *p;
+    t.x += v[4 * i]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
+    *p = t;
+  }
+}
 __device__ __forceinline__ float sum16(const V16& a) {
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) s += a[j];
   return warp_sum(s);
 }
-__device__ __forceinline__ float dot16(const V16& a, const V16& b) {
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) s = fmaf(a[j], b[j], s);
-  return warp_sum(s);
-}
 // n = (x - mean) * r, r = rsqrt(var + eps)   (tf.contrib.layers.layer_norm, biased variance)
 __device__ __forceinline__ void ln_norm(const V16& x, V16& n, float& r) {
-  const float mean = sum16(x) * (1.0f / LH);
+  const float mean = sum16(x) * INV_LH;
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     n[j] = x[j] - mean;
     s = fmaf(n[j], n[j], s);
   }
-  const float var = warp_sum(s) * (1.0f / LH);
+  const float var = warp_sum(s) * INV_LH;
   r = 1.0f / sqrtf(var + LN_EPS_F);
 #pragma unroll
   for (int j = 0; j < 16; ++j) n[j] *= r;
 }
 // out = r * (w - mean(w) - n * mean(n*w)) : LN JVP and VJP (the Jacobian is symmetric)
 __device__ __forceinline__ void ln_proj(const V16& n, float r, const V16& w, V16& out) {
-  const float mw = sum16(w) * (1.0f / LH);
-  const float mnw = dot16(n, w) * (1.0f / LH);
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) out[j] = r * (w[j] - mw - n[j] * mnw);
+  for (int j = 0; j < 16; ++j) { s0 += w[j]; s1 = fmaf(n[j], w[j], s1); }
+  s0 = warp_sum(s0) * INV_LH;
+  s1 = warp_sum(s1) * INV_LH;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = r * (w[j] - s0 - n[j] * s1);
+}
+
+// ---- state-phase helpers: thread owns columns tid*4 .. tid*4+3
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* base) {
+  const float4 t = *reinterpret_cast<const float4*>(base + threadIdx.x * 4);
+  return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ F4 ld4_or_zero(const float* base) {
+  if (base) return ld4(base);
+  return F4{{0.f, 0.f, 0.f, 0.f}};
+}
+__device__ __forceinline__ void st4(float* base, const F4& a) {
+  *reinterpret_cast<float4*>(base + threadIdx.x * 4) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ void st4_hl(__nv_bfloat16* base, long long lo_off, const F4& a) {
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_bf16(a.v[e], h[e], l[e]);
+  *reinterpret_cast<uint2*>(base + threadIdx.x * 4) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+  *reinterpret_cast<uint2*>(base + lo_off + threadIdx.x * 4) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+}
+// Sum of NV per-thread values over the 128 threads of the CTA.  `red` holds 2 x 4 x 8 floats; consecutive calls
+// alternate between its halves (tracked by `tog`), so one barrier per call suffices.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red, int& tog) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* buf = red + tog * 32;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) buf[warp * 8 + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = buf[k] + buf[8 + k] + buf[16 + k] + buf[24 + k];
+  tog ^= 1;
 }
 
 struct LstmLN {
   const float* gamma[5];  // input, transform, forget, output, state
   const float* beta[5];
+};
+
+// Gate phase A for gate G (= this warp): LN + nonlinearity, optionally with the tangent.
+//   n, r      : normalised pre-activation and 1/std (kept for the reverse gate phase)
+//   xd, nd    : tangent pre-activation and its LN tangent (TAN only)
+//   act, actd : gate activation and its tangent
+template <bool TAN>
+__device__ __forceinline__ void gate_fwd(int G, const float* q, const float* qd, const LstmLN& ln, V16& n, float& r,
+                                         V16& xd, V16& nd, V16& act, V16& actd) {
+  V16 x, g, bt;
+  ld16(q + G * LH, x);
+  if (TAN) ld16(qd + G * LH, xd);
+  ld16(ln.gamma[G], g);
+  ld16(ln.beta[G], bt);
+  ln_norm(x, n, r);
+  if (TAN) ln_proj(n, r, xd, nd);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float a = fmaf(n[j], g[j], bt[j]);
+    if (G == 1) {
+      const float t = tanhf_(a);
+      act[j] = t;
+      if (TAN) actd[j] = (1.f - t * t) * nd[j] * g[j];
+    } else {
+      const float s = sigmoidf_(G == 2 ? a + FORGET_BIAS_F : a);
+      act[j] = s;
+      if (TAN) actd[j] = s * (1.f - s) * nd[j] * g[j];
+    }
+  }
+}
+
+// shared memory: gate activations [4][512] (+ tangents [4][512]) + reduction scratch
+struct LstmSmemFwd {
+  float xa[4][LH];
+  float xad[4][LH];
+  float red[64];
 };
 
 // ------------------------------------------------------------------------------------ fwd
@@ -106,42 +187,54 @@ struct LstmFwdParams {
 };
 
 __global__ void __launch_bounds__(LS_THREADS) lstm_fwd_kernel(const LstmFwdParams p) {
-  const int row = blockIdx.x * LS_WARPS + (threadIdx.x >> 5);
-  if (row >= p.nrows) return;
-  const float* q = p.Q + (long long)row * p.ldQ;
-  V16 x, n, g, act[4];
-  float r;
-#pragma unroll
-  for (int G = 0; G < 4; ++G) {
-    ld16(q + G * LH, x);
-    ln_norm(x, n, r);
-    ld16(p.ln.gamma[G], g);
-    ld16(p.ln.beta[G], x);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float a = fmaf(n[j], g[j], x[j]);
-      act[G][j] = (G == 1) ? tanhf_(a) : sigmoidf_(G == 2 ? a + FORGET_BIAS_F : a);
+  __shared__ __align__(16) LstmSmemFwd sm;
+  const int G = threadIdx.x >> 5;
+  int tog = 0;
+  for (int row = blockIdx.x; row < p.nrows; row += gridDim.x) {
+    {
+      V16 n, xd, nd, act, actd;
+      float r;
+      const float* q = p.Q + (long long)row * p.ldQ;
+      switch (G) {   // G is warp-uniform; the switch makes it a compile-time constant inside
+        case 0: gate_fwd<false>(0, q, q, p.ln, n, r, xd, nd, act, actd); break;
+        case 1: gate_fwd<false>(1, q, q, p.ln, n, r, xd, nd, act, actd); break;
+        case 2: gate_fwd<false>(2, q, q, p.ln, n, r, xd, nd, act, actd); break;
+        default: gate_fwd<false>(3, q, q, p.ln, n, r, xd, nd, act, actd); break;
+      }
+      st16(sm.xa[G], act);
     }
-  }
-  ld16(p.Cin + (long long)row * LH, x);
+    __syncthreads();
+    const F4 si = ld4(sm.xa[0]), tj = ld4(sm.xa[1]), sf = ld4(sm.xa[2]), so = ld4(sm.xa[3]);
+    const F4 c = ld4(p.Cin + (long long)row * LH);
+    const F4 g4 = ld4(p.ln.gamma[4]), b4 = ld4(p.ln.beta[4]);
+    F4 cp;
+    float s1[1] = {0.f};
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = fmaf(x[j], act[2][j], act[0][j] * act[1][j]);
-  ln_norm(x, n, r);
-  ld16(p.ln.gamma[4], g);
-  ld16(p.ln.beta[4], x);
-  V16 cn, h;
+    for (int e = 0; e < 4; ++e) { cp.v[e] = fmaf(c.v[e], sf.v[e], si.v[e] * tj.v[e]); s1[0] += cp.v[e]; }
+    block_sum(s1, sm.red, tog);
+    const float mean = s1[0] * INV_LH;
+    float s2[1] = {0.f};
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    cn[j] = fmaf(n[j], g[j], x[j]);
-    h[j] = tanhf_(cn[j]) * act[3][j];
-  }
-  st16(p.Cout + (long long)row * LH, cn);
-  if (p.CH) st16_hl(p.CH + (long long)row * p.ldCH, p.ch_lo, cn);
-  if (p.Xn) st16_hl(p.Xn + (long long)row * p.ldX + p.hoff, p.x_lo, h);
-  if (p.Y) {
-    ld16(p.wdec, g);
-    const float y = dot16(h, g) + p.bdec[0];
-    if ((threadIdx.x & 31) == 0) p.Y[(long long)row * p.ldY] = y;
+    for (int e = 0; e < 4; ++e) { cp.v[e] -= mean; s2[0] = fmaf(cp.v[e], cp.v[e], s2[0]); }
+    block_sum(s2, sm.red, tog);
+    const float rc = 1.0f / sqrtf(s2[0] * INV_LH + LN_EPS_F);
+    F4 cn, h;
+    float sy[1] = {0.f};
+    const F4 wd = p.Y ? ld4(p.wdec) : F4{{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      cn.v[e] = fmaf(cp.v[e] * rc, g4.v[e], b4.v[e]);
+      h.v[e] = tanhf_(cn.v[e]) * so.v[e];
+      sy[0] = fmaf(h.v[e], wd.v[e], sy[0]);
+    }
+    st4(p.Cout + (long long)row * LH, cn);
+    if (p.CH) st4_hl(p.CH + (long long)row * p.ldCH, p.ch_lo, cn);
+    if (p.Xn) st4_hl(p.Xn + (long long)row * p.ldX + p.hoff, p.x_lo, h);
+    if (p.Y) {
+      block_sum(sy, sm.red, tog);
+      if (threadIdx.x == 0) p.Y[(long long)row * p.ldY] = sy[0] + p.bdec[0];
+    }
+    __syncthreads();   // xa is rewritten by the next row
   }
 }
 
@@ -157,70 +250,101 @@ struct LstmTanParams {
   __nv_bfloat16* Xn; long long ldX; long long x_lo; int hoff;
 };
 
-__global__ void __launch_bounds__(LS_THREADS) lstm_tan_kernel(const LstmTanParams p) {
-  const int i = blockIdx.x * LS_WARPS + (threadIdx.x >> 5);
-  if (i >= p.nrows) return;
-  const long long prow = p.prow0 + i, trow = p.trow0 + i;
-  const float* q = p.Q + prow * p.ldQ;
-  const float* qd = p.Q + trow * p.ldQ;
-  V16 x, n, g, act[4], actd[4];
-  float r;
+// State phase shared by the tangent and reverse kernels: from the gate activations in shared memory and c_in,
+// recompute c', LN(state) and (TAN) their tangents.
+struct StateFwd {
+  F4 si, tj, sf, so, sid, tjd, sfd, sod;   // gate activations and tangents
+  F4 c, cd;                                // c_in and its tangent
+  F4 nc, ncd, cpd;                         // normalised state, its tangent, tangent of c'
+  float rc;
+  float qq;                                // sum(nc * cpd)
+};
+template <bool TAN>
+__device__ __forceinline__ void state_fwd(const LstmSmemFwd& sm, const float* c_in, const float* cd_in, StateFwd& s,
+                                          float* red, int& tog) {
+  s.si = ld4(sm.xa[0]); s.tj = ld4(sm.xa[1]); s.sf = ld4(sm.xa[2]); s.so = ld4(sm.xa[3]);
+  s.c = ld4(c_in);
+  if (TAN) {
+    s.sid = ld4(sm.xad[0]); s.tjd = ld4(sm.xad[1]); s.sfd = ld4(sm.xad[2]); s.sod = ld4(sm.xad[3]);
+    s.cd = ld4(cd_in);
+  }
+  F4 cp;
+  float s1[2] = {0.f, 0.f};
 #pragma unroll
-  for (int G = 0; G < 4; ++G) {
-    ld16(q + G * LH, x);
-    ln_norm(x, n, r);
-    ld16(p.ln.gamma[G], g);
-    V16 bt, xd, nd;
-    ld16(p.ln.beta[G], bt);
-    ld16(qd + G * LH, xd);
-    ln_proj(n, r, xd, nd);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float a = fmaf(n[j], g[j], bt[j]);
-      const float ad = nd[j] * g[j];
-      if (G == 1) {
-        const float t = tanhf_(a);
-        act[G][j] = t;
-        actd[G][j] = (1.f - t * t) * ad;
-      } else {
-        const float s = sigmoidf_(G == 2 ? a + FORGET_BIAS_F : a);
-        act[G][j] = s;
-        actd[G][j] = s * (1.f - s) * ad;
-      }
+  for (int e = 0; e < 4; ++e) {
+    cp.v[e] = fmaf(s.c.v[e], s.sf.v[e], s.si.v[e] * s.tj.v[e]);
+    s1[0] += cp.v[e];
+    if (TAN) {
+      s.cpd.v[e] = s.cd.v[e] * s.sf.v[e] + s.c.v[e] * s.sfd.v[e] + s.sid.v[e] * s.tj.v[e] + s.si.v[e] * s.tjd.v[e];
+      s1[1] += s.cpd.v[e];
     }
   }
-  V16 c, cd, cp, cpd;
-  ld16(p.C + prow * LH, c);
-  ld16(p.C + trow * LH, cd);
+  block_sum(s1, red, tog);
+  const float mean = s1[0] * INV_LH;
+  float s2[1] = {0.f};
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    cp[j] = fmaf(c[j], act[2][j], act[0][j] * act[1][j]);
-    cpd[j] = cd[j] * act[2][j] + c[j] * actd[2][j] + actd[0][j] * act[1][j] + act[0][j] * actd[1][j];
-  }
-  ln_norm(cp, n, r);
-  V16 ncd;
-  ln_proj(n, r, cpd, ncd);
-  ld16(p.ln.gamma[4], g);
-  ld16(p.ln.beta[4], x);
-  V16 cnd, hd;
+  for (int e = 0; e < 4; ++e) { cp.v[e] -= mean; s2[0] = fmaf(cp.v[e], cp.v[e], s2[0]); }
+  block_sum(s2, red, tog);
+  s.rc = 1.0f / sqrtf(s2[0] * INV_LH + LN_EPS_F);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float cn = fmaf(n[j], g[j], x[j]);
-    const float tc = tanhf_(cn);
-    cnd[j] = ncd[j] * g[j];
-    hd[j] = (1.f - tc * tc) * cnd[j] * act[3][j] + tc * actd[3][j];
+  for (int e = 0; e < 4; ++e) s.nc.v[e] = cp.v[e] * s.rc;
+  if (TAN) {
+    float s3[1] = {0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s3[0] = fmaf(s.nc.v[e], s.cpd.v[e], s3[0]);
+    block_sum(s3, red, tog);
+    s.qq = s3[0];
+    const float m0 = s1[1] * INV_LH, m1 = s3[0] * INV_LH;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s.ncd.v[e] = s.rc * (s.cpd.v[e] - m0 - s.nc.v[e] * m1);
   }
-  st16(p.Cout + trow * LH, cnd);
-  if (p.CH) st16_hl(p.CH + trow * p.ldCH, p.ch_lo, cnd);
-  if (p.Xn) st16_hl(p.Xn + trow * p.ldX + p.hoff, p.x_lo, hd);
+}
+
+__global__ void __launch_bounds__(LS_THREADS) lstm_tan_kernel(const LstmTanParams p) {
+  __shared__ __align__(16) LstmSmemFwd sm;
+  const int G = threadIdx.x >> 5;
+  int tog = 0;
+  for (int i = blockIdx.x; i < p.nrows; i += gridDim.x) {
+    const long long prow = p.prow0 + i, trow = p.trow0 + i;
+    {
+      V16 n, xd, nd, act, actd;
+      float r;
+      const float* q = p.Q + prow * p.ldQ;
+      const float* qd = p.Q + trow * p.ldQ;
+      switch (G) {
+        case 0: gate_fwd<true>(0, q, qd, p.ln, n, r, xd, nd, act, actd); break;
+        case 1: gate_fwd<true>(1, q, qd, p.ln, n, r, xd, nd, act, actd); break;
+        case 2: gate_fwd<true>(2, q, qd, p.ln, n, r, xd, nd, act, actd); break;
+        default: gate_fwd<true>(3, q, qd, p.ln, n, r, xd, nd, act, actd); break;
+      }
+      st16(sm.xa[G], act);
+      st16(sm.xad[G], actd);
+    }
+    __syncthreads();
+    StateFwd s;
+    state_fwd<true>(sm, p.C + prow * LH, p.C + trow * LH, s, sm.red, tog);
+    const F4 g4 = ld4(p.ln.gamma[4]), b4 = ld4(p.ln.beta[4]);
+    F4 cnd, hd;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float cn = fmaf(s.nc.v[e], g4.v[e], b4.v[e]);
+      const float tc = tanhf_(cn);
+      cnd.v[e] = s.ncd.v[e] * g4.v[e];
+      hd.v[e] = (1.f - tc * tc) * cnd.v[e] * s.so.v[e] + tc * s.sod.v[e];
+    }
+    st4(p.Cout + trow * LH, cnd);
+    if (p.CH) st4_hl(p.CH + trow * p.ldCH, p.ch_lo, cnd);
+    if (p.Xn) st4_hl(p.Xn + trow * p.ldX + p.hoff, p.x_lo, hd);
+    __syncthreads();   // xa / xad are rewritten by the next row
+  }
 }
 
 // ------------------------------------------------------------------------------------ reverse
-// One launch handles `n_plain` first-order rows (row = prow0 + i) and `n_tan` rows that carry a tangent
-// (primal row tan_prow0 + j, tangent row trow0 + j).  One warp per row, rows strided over the grid.
-// Parameter gradients (5 LN gammas/betas, D head) are reduced without shared-memory atomics: every warp
-// owns a [11][512] fp32 slab in shared memory, the CTA sums its slabs, and only the CTA totals go to
-// global memory as fp32 reductions.
+// One launch handles `n_tan` rows that carry a tangent (primal row tan_prow0 + j, tangent row trow0 + j) and
+// `n_plain` first-order rows (row = prow0 + i).  Parameter gradients (5 LN gammas/betas, D head) accumulate in
+// shared memory per CTA and are flushed to a per-CTA slice of `partials` ([grid][LR_NPART] fp32, overwritten when
+// init_partials, else accumulated: the launches of one reverse pass use the same grid); lngrad_reduce() sums
+// the slices into the gradient bucket once per pass.  No atomics anywhere.
 struct LstmRevParams {
   int n_plain, prow0;
   int n_tan, tan_prow0, trow0;
@@ -238,288 +362,306 @@ struct LstmRevParams {
   // outputs
   __nv_bfloat16* QB; long long ldQB; long long qb_lo;   // q_bar hi/lo [rows, 2*4H]
   float* CB;                                    // c_bar [rows,H]
-  // parameter gradients (nullable => data path only)
-  float* dgamma[5]; float* dbeta[5];
-  float* dwdec; float* dbdec;
+  // parameter gradients (partials == nullptr => data path only)
+  float* partials; int init_partials;
 };
 
-constexpr int LR_WARPS = 8;
-constexpr int LR_THREADS = LR_WARPS * 32;
-constexpr int LR_SLAB = 11 * LH;   // dgamma[5], dbeta[5], dwdec
+constexpr int LR_NVEC = 11;                 // dgamma[5], dbeta[5], dwdec
+constexpr int LR_NPART = LR_NVEC * LH + 4;  // + dbdec (padded)
+constexpr int LR_MAX_GRID = 296;            // 2 CTAs per SM
 
-// slab accumulate: lane owns columns lane*4 + 128*i (conflict-free float4 accesses)
-__device__ __forceinline__ void slab_acc(float* slab_vec, const V16& v, bool first) {
-  const int lane = threadIdx.x & 31;
+struct LstmSmemRev {
+  LstmSmemFwd f;
+  float yb[4][LH];     // adjoints of the gate activations
+  float ydb[4][LH];    // ... and of their tangents
+  float acc[LR_NVEC][LH];
+  float dbd;
+};
+
+// Gate phase C for gate G (= this warp): reverse through the nonlinearity and its LayerNorm.
+template <bool TAN>
+__device__ __forceinline__ void gate_rev(int G, const LstmRevParams& p, LstmSmemRev& sm, long long prow, long long trow,
+                                         const V16& n, float r, const V16& xd, const V16& nd, bool wgrad) {
+  V16 g, act, ybv, ydbv, nb, ndb, dgs;
+  ld16(p.ln.gamma[G], g);
+  ld16(sm.f.xa[G], act);
+  ld16(sm.yb[G], ybv);
+  if (TAN) ld16(sm.ydb[G], ydbv);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4* p = reinterpret_cast<float4*>(slab_vec + lane * 4 + 128 * i);
-    float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    if (!first) {
-      const float4 o = *p;
-      t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+  for (int j = 0; j < 16; ++j) {
+    const float y = act[j];
+    const float d1 = (G == 1) ? (1.f - y * y) : y * (1.f - y);
+    float abar = ybv[j] * d1;
+    if (TAN) {
+      const float d2 = (G == 1) ? (-2.f * y * d1) : d1 * (1.f - 2.f * y);
+      abar += ydbv[j] * d2 * (nd[j] * g[j]);
+      const float adb = ydbv[j] * d1;
+      ndb[j] = adb * g[j];
+      dgs[j] = abar * n[j] + adb * nd[j];
+    } else {
+      dgs[j] = abar * n[j];
     }
-    *p = t;
+    ybv[j] = abar;           // = d beta contribution
+    nb[j] = abar * g[j];
   }
+  if (wgrad) {
+    acc16(sm.acc[G], dgs);
+    acc16(sm.acc[5 + G], ybv);
+  }
+  V16 xb;
+  if (!TAN) {
+    ln_proj(n, r, nb, xb);
+  } else {
+    // six row sums at once: sum(nb), sum(n nb), sum(ndb), pp = sum(n ndb), ss = sum(ndb nd), qq = sum(n xd)
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      s[0] += nb[j]; s[1] = fmaf(n[j], nb[j], s[1]);
+      s[2] += ndb[j]; s[3] = fmaf(n[j], ndb[j], s[3]);
+      s[4] = fmaf(ndb[j], nd[j], s[4]); s[5] = fmaf(n[j], xd[j], s[5]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] = warp_sum(s[k]);
+    const float kk = r * INV_LH;
+    V16 xdb;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      xdb[j] = r * (ndb[j] - s[2] * INV_LH - n[j] * s[3] * INV_LH);
+      xb[j] = r * (nb[j] - s[0] * INV_LH - n[j] * s[1] * INV_LH) - kk * (n[j] * s[4] + s[5] * xdb[j] + s[3] * nd[j]);
+    }
+    st16_hl(p.QB + trow * p.ldQB + G * LH, p.qb_lo, xdb);
+  }
+  st16_hl(p.QB + prow * p.ldQB + G * LH, p.qb_lo, xb);
 }
 
 template <bool TAN>
-__device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, long long prow, long long trow, float* slab,
-                                             bool first, float& dbd_acc) {
-  const bool wgrad = slab != nullptr;
+__device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev& sm, long long prow, long long trow,
+                                             bool wgrad, int& tog) {
+  const int G = threadIdx.x >> 5;
   const float* q = p.Q + prow * p.ldQ;
   const float* qd = p.Q + trow * p.ldQ;
-  V16 x, n, g, bt, act[4], actd[4], ad[4];
+  // ---- phase A (warp = gate): recompute the gate activations (and tangents); n, r, xd, nd stay in registers
+  V16 n, xd, nd;
   float r;
-  // ---- phase A: recompute forward (and tangent) gate activations
-#pragma unroll
-  for (int G = 0; G < 4; ++G) {
-    ld16(q + G * LH, x);
-    ln_norm(x, n, r);
-    ld16(p.ln.gamma[G], g);
-    ld16(p.ln.beta[G], bt);
-    V16 nd;
-    if (TAN) {
-      V16 xd;
-      ld16(qd + G * LH, xd);
-      ln_proj(n, r, xd, nd);
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float a = fmaf(n[j], g[j], bt[j]);
-      if (TAN) ad[G][j] = nd[j] * g[j];
-      if (G == 1) {
-        const float t = tanhf_(a);
-        act[G][j] = t;
-        if (TAN) actd[G][j] = (1.f - t * t) * ad[G][j];
-      } else {
-        const float s = sigmoidf_(G == 2 ? a + FORGET_BIAS_F : a);
-        act[G][j] = s;
-        if (TAN) actd[G][j] = s * (1.f - s) * ad[G][j];
-      }
-    }
-  }
-  V16 c, cd, cp, cpd, nc, ncd;
-  float rc;
-  ld16(p.C + prow * LH, c);
-  if (TAN) ld16(p.C + trow * LH, cd);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    cp[j] = fmaf(c[j], act[2][j], act[0][j] * act[1][j]);
-    if (TAN) cpd[j] = cd[j] * act[2][j] + c[j] * actd[2][j] + actd[0][j] * act[1][j] + act[0][j] * actd[1][j];
-  }
-  ln_norm(cp, nc, rc);
-  if (TAN) ln_proj(nc, rc, cpd, ncd);
-  ld16(p.ln.gamma[4], g);
-  ld16(p.ln.beta[4], bt);
-  // ---- phase B: cell-level reverse
-  V16 hb, cnb, hdb, cndb;
-  ld16_or_zero(p.XBn ? p.XBn + prow * p.ldXB + p.hoff : nullptr, hb);
-  if (p.HB) {
-    ld16(p.HB + prow * p.ldHB, x);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) hb[j] += x[j];
-  }
-  const float yb = p.ybar_blk[(int)(prow / p.B) & 7];
-  V16 wd;
-  if (p.wdec) {
-    ld16(p.wdec, wd);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) hb[j] = fmaf(yb, wd[j], hb[j]);
-  }
-  ld16_or_zero(p.CBn ? p.CBn + prow * LH : nullptr, cnb);
-  if (TAN) {
-    ld16_or_zero(p.XBn ? p.XBn + trow * p.ldXB + p.hoff : nullptr, hdb);
-    if (p.wdec) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) hdb[j] = fmaf(p.ydot_bar, wd[j], hdb[j]);
-    }
-    ld16_or_zero(p.CBn ? p.CBn + trow * LH : nullptr, cndb);
-  }
-  V16 ncb, ncdb;        // adjoints of nc (normalised state) and its tangent
-  V16 yb_[4], ydb_[4];  // adjoints of the gate activations (and of their tangents)
   {
-    V16 dgs, dbs, dwv;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float cn = fmaf(nc[j], g[j], bt[j]);
-      const float tc = tanhf_(cn);
-      const float dt = 1.f - tc * tc;
-      const float so = act[3][j];
-      float tcb = hb[j] * so;
-      float sob = hb[j] * tc;
-      float cnbar = cnb[j];
-      float tcdb = 0.f, cndbar = 0.f;
-      float h = tc * so;
-      float hd = 0.f;
-      if (TAN) {
-        const float cnd = ncd[j] * g[j];
-        const float tcd = dt * cnd;
-        hd = tcd * so + tc * actd[3][j];
-        tcb += hdb[j] * actd[3][j];
-        sob += hdb[j] * tcd;
-        tcdb = hdb[j] * so;
-        ydb_[3][j] = hdb[j] * tc;
-        cnbar += tcdb * (-2.f * tc * dt) * cnd;
-        cndbar = cndb[j] + tcdb * dt;
-      }
-      cnbar += tcb * dt;
-      yb_[3][j] = sob;
-      ncb[j] = cnbar * g[j];
-      dgs[j] = cnbar * nc[j];
-      dbs[j] = cnbar;
-      dwv[j] = h * yb;
-      if (TAN) {
-        ncdb[j] = cndbar * g[j];
-        dgs[j] += cndbar * ncd[j];
-        dwv[j] += hd * p.ydot_bar;
-      }
+    V16 act, actd;
+    switch (G) {
+      case 0: gate_fwd<TAN>(0, q, qd, p.ln, n, r, xd, nd, act, actd); break;
+      case 1: gate_fwd<TAN>(1, q, qd, p.ln, n, r, xd, nd, act, actd); break;
+      case 2: gate_fwd<TAN>(2, q, qd, p.ln, n, r, xd, nd, act, actd); break;
+      default: gate_fwd<TAN>(3, q, qd, p.ln, n, r, xd, nd, act, actd); break;
     }
-    if (wgrad) {
-      slab_acc(slab + 4 * LH, dgs, first);
-      slab_acc(slab + 9 * LH, dbs, first);
-      slab_acc(slab + 10 * LH, dwv, first);
-      dbd_acc += yb;
+    st16(sm.f.xa[G], act);
+    if (TAN) st16(sm.f.xad[G], actd);
+  }
+  __syncthreads();
+  // ---- phase B (thread = 4 columns): cell-level reverse
+  {
+    StateFwd s;
+    state_fwd<TAN>(sm.f, p.C + prow * LH, p.C + trow * LH, s, sm.f.red, tog);
+    const F4 g4 = ld4(p.ln.gamma[4]), b4 = ld4(p.ln.beta[4]);
+    F4 hb = ld4_or_zero(p.XBn ? p.XBn + prow * p.ldXB + p.hoff : nullptr);
+    if (p.HB) {
+      const F4 x = ld4(p.HB + prow * p.ldHB);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hb.v[e] += x.v[e];
     }
-  }
-  // LN(state) reverse -> adjoint of c' (and of its tangent)
-  V16 cpb, cpdb;
-  ln_proj(nc, rc, ncb, cpb);
-  if (TAN) {
-    ln_proj(nc, rc, ncdb, cpdb);
-    const float pp = dot16(nc, ncdb), qq = dot16(nc, cpd), ss = dot16(ncdb, ncd);
-    const float k = rc * (1.0f / LH);
+    const float yb = p.ybar_blk[(int)(prow / p.B) & 7];
+    const F4 wd = p.wdec ? ld4(p.wdec) : F4{{0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) cpb[j] -= k * (nc[j] * ss + qq * cpdb[j] + pp * ncd[j]);
-  }
-  // c' = c*sf + si*tj
-  V16 cbar, cdbar;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    cbar[j] = cpb[j] * act[2][j];
-    yb_[2][j] = cpb[j] * c[j];
-    yb_[0][j] = cpb[j] * act[1][j];
-    yb_[1][j] = cpb[j] * act[0][j];
+    for (int e = 0; e < 4; ++e) hb.v[e] = fmaf(yb, wd.v[e], hb.v[e]);
+    const F4 cnb = ld4_or_zero(p.CBn ? p.CBn + prow * LH : nullptr);
+    F4 hdb = F4{{0.f, 0.f, 0.f, 0.f}}, cndb = F4{{0.f, 0.f, 0.f, 0.f}};
     if (TAN) {
-      cbar[j] += cpdb[j] * actd[2][j];
-      yb_[2][j] += cpdb[j] * cd[j];
-      yb_[0][j] += cpdb[j] * actd[1][j];
-      yb_[1][j] += cpdb[j] * actd[0][j];
-      cdbar[j] = cpdb[j] * act[2][j];
-      ydb_[2][j] = cpdb[j] * c[j];
-      ydb_[0][j] = cpdb[j] * act[1][j];
-      ydb_[1][j] = cpdb[j] * act[0][j];
-    }
-  }
-  st16(p.CB + prow * LH, cbar);
-  if (TAN) st16(p.CB + trow * LH, cdbar);
-  // ---- phase C: per-gate reverse through the nonlinearity and its LayerNorm
+      hdb = ld4_or_zero(p.XBn ? p.XBn + trow * p.ldXB + p.hoff : nullptr);
 #pragma unroll
-  for (int G = 0; G < 4; ++G) {
-    ld16(q + G * LH, x);
-    ln_norm(x, n, r);
-    ld16(p.ln.gamma[G], g);
-    V16 nb, xb, xd, nd, ndb, xdb;
-    if (TAN) {
-      ld16(qd + G * LH, xd);
-      ln_proj(n, r, xd, nd);
+      for (int e = 0; e < 4; ++e) hdb.v[e] = fmaf(p.ydot_bar, wd.v[e], hdb.v[e]);
+      cndb = ld4_or_zero(p.CBn ? p.CBn + trow * LH : nullptr);
     }
-    V16 dgs, dbs;
+    F4 ncb, ncdb, ybo, ydbo;
+    float rs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // sum(ncb), sum(nc ncb), sum(ncdb), pp = sum(nc ncdb), ss = sum(ncdb ncd)
+    {
+      F4 dgs, dbs, dwv;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float y = act[G][j];
-      const float d1 = (G == 1) ? (1.f - y * y) : y * (1.f - y);
-      float abar = yb_[G][j] * d1;
-      if (TAN) {
-        const float d2 = (G == 1) ? (-2.f * y * d1) : d1 * (1.f - 2.f * y);
-        abar += ydb_[G][j] * d2 * ad[G][j];
-        const float adb = ydb_[G][j] * d1;
-        ndb[j] = adb * g[j];
-        dgs[j] = abar * n[j] + adb * nd[j];
-      } else {
-        dgs[j] = abar * n[j];
+      for (int e = 0; e < 4; ++e) {
+        const float cn = fmaf(s.nc.v[e], g4.v[e], b4.v[e]);
+        const float tc = tanhf_(cn);
+        const float dt = 1.f - tc * tc;
+        const float so = s.so.v[e];
+        float tcb = hb.v[e] * so;
+        float sob = hb.v[e] * tc;
+        float cnbar = cnb.v[e];
+        float cndbar = 0.f;
+        const float h = tc * so;
+        float hd = 0.f;
+        ydbo.v[e] = 0.f;
+        ncdb.v[e] = 0.f;
+        if (TAN) {
+          const float cnd = s.ncd.v[e] * g4.v[e];
+          const float tcd = dt * cnd;
+          hd = tcd * so + tc * s.sod.v[e];
+          tcb += hdb.v[e] * s.sod.v[e];
+          sob += hdb.v[e] * tcd;
+          const float tcdb = hdb.v[e] * so;
+          ydbo.v[e] = hdb.v[e] * tc;
+          cnbar += tcdb * (-2.f * tc * dt) * cnd;
+          cndbar = cndb.v[e] + tcdb * dt;
+        }
+        cnbar += tcb * dt;
+        ybo.v[e] = sob;
+        ncb.v[e] = cnbar * g4.v[e];
+        dgs.v[e] = cnbar * s.nc.v[e];
+        dbs.v[e] = cnbar;
+        dwv.v[e] = h * yb;
+        rs[0] += ncb.v[e];
+        rs[1] = fmaf(s.nc.v[e], ncb.v[e], rs[1]);
+        if (TAN) {
+          ncdb.v[e] = cndbar * g4.v[e];
+          dgs.v[e] += cndbar * s.ncd.v[e];
+          dwv.v[e] += hd * p.ydot_bar;
+          rs[2] += ncdb.v[e];
+          rs[3] = fmaf(s.nc.v[e], ncdb.v[e], rs[3]);
+          rs[4] = fmaf(ncdb.v[e], s.ncd.v[e], rs[4]);
+        }
       }
-      dbs[j] = abar;
-      nb[j] = abar * g[j];
-    }
-    if (wgrad) {
-      slab_acc(slab + G * LH, dgs, first);
-      slab_acc(slab + (5 + G) * LH, dbs, first);
-    }
-    ln_proj(n, r, nb, xb);
-    if (TAN) {
-      ln_proj(n, r, ndb, xdb);
-      const float pp = dot16(n, ndb), qq = dot16(n, xd), ss = dot16(ndb, nd);
-      const float k = r * (1.0f / LH);
+      if (wgrad) {
+        const int c0 = threadIdx.x * 4;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) xb[j] -= k * (n[j] * ss + qq * xdb[j] + pp * nd[j]);
-      st16_hl(p.QB + trow * p.ldQB + G * LH, p.qb_lo, xdb);
+        for (int e = 0; e < 4; ++e) {
+          sm.acc[4][c0 + e] += dgs.v[e];
+          sm.acc[9][c0 + e] += dbs.v[e];
+          sm.acc[10][c0 + e] += dwv.v[e];
+        }
+        if (threadIdx.x == 0) sm.dbd += yb;
+      }
     }
-    st16_hl(p.QB + prow * p.ldQB + G * LH, p.qb_lo, xb);
+    block_sum(rs, sm.f.red, tog);
+    // LN(state) reverse -> adjoint of c' (and of its tangent); then c' = c*sf + si*tj
+    F4 cbar, cdbar, ybi, ybj, ybf, ydbi, ydbj, ydbf;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float cpb = s.rc * (ncb.v[e] - rs[0] * INV_LH - s.nc.v[e] * rs[1] * INV_LH);
+      float cpdb = 0.f;
+      if (TAN) {
+        cpdb = s.rc * (ncdb.v[e] - rs[2] * INV_LH - s.nc.v[e] * rs[3] * INV_LH);
+        cpb -= s.rc * INV_LH * (s.nc.v[e] * rs[4] + s.qq * cpdb + rs[3] * s.ncd.v[e]);
+      }
+      cbar.v[e] = cpb * s.sf.v[e];
+      ybf.v[e] = cpb * s.c.v[e];
+      ybi.v[e] = cpb * s.tj.v[e];
+      ybj.v[e] = cpb * s.si.v[e];
+      if (TAN) {
+        cbar.v[e] += cpdb * s.sfd.v[e];
+        ybf.v[e] += cpdb * s.cd.v[e];
+        ybi.v[e] += cpdb * s.tjd.v[e];
+        ybj.v[e] += cpdb * s.sid.v[e];
+        cdbar.v[e] = cpdb * s.sf.v[e];
+        ydbf.v[e] = cpdb * s.c.v[e];
+        ydbi.v[e] = cpdb * s.tj.v[e];
+        ydbj.v[e] = cpdb * s.si.v[e];
+      }
+    }
+    st4(p.CB + prow * LH, cbar);
+    st4(sm.yb[0], ybi); st4(sm.yb[1], ybj); st4(sm.yb[2], ybf); st4(sm.yb[3], ybo);
+    if (TAN) {
+      st4(p.CB + trow * LH, cdbar);
+      st4(sm.ydb[0], ydbi); st4(sm.ydb[1], ydbj); st4(sm.ydb[2], ydbf); st4(sm.ydb[3], ydbo);
+    }
   }
+  __syncthreads();
+  // ---- phase C (warp = gate): reverse through the nonlinearity and its LayerNorm
+  switch (G) {
+    case 0: gate_rev<TAN>(0, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
+    case 1: gate_rev<TAN>(1, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
+    case 2: gate_rev<TAN>(2, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
+    default: gate_rev<TAN>(3, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
+  }
+  // No barrier needed here: the next row's phase A writes xa[G] / xad[G], which only warp G reads in phase C,
+  // and every other buffer is rewritten only after the next row's post-phase-A barrier.
 }
 
-__global__ void __launch_bounds__(LR_THREADS, 1) lstm_rev_kernel(const LstmRevParams p) {
-  extern __shared__ __align__(16) float lr_smem[];   // [LR_WARPS][11][512] + [LR_WARPS] (only with parameter gradients)
-  const bool wgrad = p.dgamma[0] != nullptr;
-  const int warp = threadIdx.x >> 5;
-  float* slab = wgrad ? lr_smem + warp * LR_SLAB : nullptr;
+__global__ void __launch_bounds__(LS_THREADS) lstm_rev_kernel(const LstmRevParams p) {
+  extern __shared__ __align__(16) uint8_t lr_smem_raw[];
+  LstmSmemRev& sm = *reinterpret_cast<LstmSmemRev*>(lr_smem_raw);
+  const bool wgrad = p.partials != nullptr;
+  if (wgrad) {
+    float* a = &sm.acc[0][0];
+    for (int k = threadIdx.x; k < LR_NVEC * LH; k += LS_THREADS) a[k] = 0.f;
+    if (threadIdx.x == 0) sm.dbd = 0.f;
+    __syncthreads();
+  }
   const int nrows = p.n_plain + p.n_tan;
-  const int gw = blockIdx.x * LR_WARPS + warp;
-  const int stride = gridDim.x * LR_WARPS;
-  bool first = true;
-  float dbd = 0.f;
-  // tangent rows first: they are the longest, so they start earliest
-  for (int i = gw; i < nrows; i += stride) {
-    if (i < p.n_tan) lstm_rev_row<true>(p, p.tan_prow0 + i, p.trow0 + i, slab, first, dbd);
-    else lstm_rev_row<false>(p, p.prow0 + (i - p.n_tan), 0, slab, first, dbd);
-    first = false;
+  int tog = 0;
+  // tangent rows first: they are the longest
+  for (int i = blockIdx.x; i < nrows; i += gridDim.x) {
+    if (i < p.n_tan) lstm_rev_row<true>(p, sm, p.tan_prow0 + i, p.trow0 + i, wgrad, tog);
+    else lstm_rev_row<false>(p, sm, p.prow0 + (i - p.n_tan), 0, wgrad, tog);
   }
   if (!wgrad) return;
-  float* dbds = lr_smem + LR_WARPS * LR_SLAB;
-  if ((threadIdx.x & 31) == 0) dbds[warp] = dbd;
   __syncthreads();
-  int nact = min(LR_WARPS, nrows - blockIdx.x * LR_WARPS);   // warps of this CTA that processed >= 1 row
-  if (nact <= 0) return;
-  for (int k = threadIdx.x; k < LR_SLAB; k += LR_THREADS) {
-    float s = 0.f;
-    for (int w = 0; w < nact; ++w) s += lr_smem[w * LR_SLAB + k];
-    const int vec = k / LH, col = k % LH;
-    float* dst = vec < 5 ? p.dgamma[vec] : (vec < 10 ? p.dbeta[vec - 5] : p.dwdec);
-    if (dst) atomicAdd(dst + col, s);
+  float* dst = p.partials + (long long)blockIdx.x * LR_NPART;
+  const float* a = &sm.acc[0][0];
+  for (int k = threadIdx.x; k < LR_NVEC * LH; k += LS_THREADS) dst[k] = p.init_partials ? a[k] : dst[k] + a[k];
+  if (threadIdx.x == 0) dst[LR_NVEC * LH] = p.init_partials ? sm.dbd : dst[LR_NVEC * LH] + sm.dbd;
+}
+
+// Sums the per-CTA partial parameter gradients of one reverse pass into the gradient bucket.
+struct LnGradParams {
+  const float* partials; int nslices;
+  float* dgamma[5]; float* dbeta[5]; float* dwdec; float* dbdec;
+};
+__global__ void __launch_bounds__(256) lngrad_reduce_kernel(const LnGradParams p) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k > LR_NVEC * LH) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 4 <= p.nslices; b += 4) {
+    s0 += p.partials[(long long)b * LR_NPART + k];
+    s1 += p.partials[(long long)(b + 1) * LR_NPART + k];
+    s2 += p.partials[(long long)(b + 2) * LR_NPART + k];
+    s3 += p.partials[(long long)(b + 3) * LR_NPART + k];
   }
-  if (p.dbdec && threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < nact; ++w) s += dbds[w];
-    atomicAdd(p.dbdec, s);
+  for (; b < p.nslices; ++b) s0 += p.partials[(long long)b * LR_NPART + k];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (k == LR_NVEC * LH) {
+    if (p.dbdec) p.dbdec[0] += s;
+    return;
   }
+  const int vec = k / LH, col = k % LH;
+  float* dst = vec < 5 ? p.dgamma[vec] : (vec < 10 ? p.dbeta[vec - 5] : p.dwdec);
+  if (dst) dst[col] += s;
 }
 
 int lstm_fwd(const LstmFwdParams& p, cudaStream_t stream) {
   if (p.nrows <= 0) return 0;
-  lstm_fwd_kernel<<<(p.nrows + LS_WARPS - 1) / LS_WARPS, LS_THREADS, 0, stream>>>(p);
+  const int grid = p.nrows < 148 * 8 ? p.nrows : 148 * 8;
+  lstm_fwd_kernel<<<grid, LS_THREADS, 0, stream>>>(p);
   SGG_LAUNCHED();
   return 0;
 }
 int lstm_tan(const LstmTanParams& p, cudaStream_t stream) {
   if (p.nrows <= 0) return 0;
-  lstm_tan_kernel<<<(p.nrows + LS_WARPS - 1) / LS_WARPS, LS_THREADS, 0, stream>>>(p);
+  const int grid = p.nrows < 148 * 8 ? p.nrows : 148 * 8;
+  lstm_tan_kernel<<<grid, LS_THREADS, 0, stream>>>(p);
   SGG_LAUNCHED();
   return 0;
 }
+int lstm_rev_grid(int nrows) { return nrows < LR_MAX_GRID ? nrows : LR_MAX_GRID; }
+long long lstm_rev_partials_floats() { return (long long)LR_MAX_GRID * LR_NPART; }
 int lstm_rev(const LstmRevParams& p, cudaStream_t stream) {
   const int nrows = p.n_plain + p.n_tan;
   if (nrows <= 0) return 0;
-  const bool wgrad = p.dgamma[0] != nullptr;
-  const size_t smem = wgrad ? (size_t)(LR_WARPS * LR_SLAB + LR_WARPS) * sizeof(float) : 0;
   static bool configured = false;
   if (!configured) {
-    SGG_CUDA(cudaFuncSetAttribute(lstm_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)((LR_WARPS * LR_SLAB + LR_WARPS) * sizeof(float))));
+    SGG_CUDA(cudaFuncSetAttribute(lstm_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmSmemRev)));
     configured = true;
   }
-  int grid = (nrows + LR_WARPS - 1) / LR_WARPS;
-  if (grid > 148) grid = 148;
-  lstm_rev_kernel<<<grid, LR_THREADS, smem, stream>>>(p);
+  lstm_rev_kernel<<<lstm_rev_grid(nrows), LS_THREADS, sizeof(LstmSmemRev), stream>>>(p);
+  SGG_LAUNCHED();
+  return 0;
+}
+int lngrad_reduce(const LnGradParams& p, cudaStream_t stream) {
+  lngrad_reduce_kernel<<<(LR_NVEC * LH + 1 + 255) / 256, 256, 0, stream>>>(p);
   SGG_LAUNCHED();
   return 0;
 }

@@ -312,19 +312,29 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
         if (i + e < sg.n) { p.theta[gi + e] = th[e]; p.m[gi + e] = m[e]; p.v[gi + e] = v[e]; }
     }
     if (p.shadow && sg.sh_off >= 0) {
-      for (int e = 0; e < 4; ++e)
-        if (i + e < sg.n) {
-          const long long r = (i + e) / sg.cols, c = (i + e) % sg.cols;
-          __nv_bfloat16 h, l;
-          split_bf16(th[e], h, l);
-          p.shadow[sg.sh_off + r * sg.pitch + c] = h;
-          p.shadow[sg.sh_off + sg.lo_off + r * sg.pitch + c] = l;
-        }
+      // bf16 hi/lo shadow of the updated weights (row pitch may exceed the column count)
+      unsigned r = (unsigned)i / (unsigned)sg.cols, c = (unsigned)i - r * (unsigned)sg.cols;
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_bf16(th[e], h[e], l[e]);
+      if (vec && ((sg.cols | sg.pitch) & 3) == 0) {   // the 4 elements share a row and are 8-byte aligned
+        __nv_bfloat16* dst = p.shadow + sg.sh_off + (long long)r * sg.pitch + c;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        *reinterpret_cast<uint2*>(dst + sg.lo_off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (i + e < sg.n) {
+            __nv_bfloat16* dst = p.shadow + sg.sh_off + (long long)r * sg.pitch + c;
+            dst[0] = h[e];
+            dst[sg.lo_off] = l[e];
+            if (++c == (unsigned)sg.cols) { c = 0; ++r; }
+          }
+      }
     }
   }
 }
 int adam(const AdamParams& p, long long max_n, cudaStream_t stream) {
-  const int gx = (int)llmin((max_n / 4 + 255) / 256, 148 * 4);
+  const int gx = (int)llmin((max_n / 4 + 255) / 256, 148 * 8);
   dim3 grid(gx > 0 ? gx : 1, p.nseg);
   adam_kernel<<<grid, 256, 0, stream>>>(p);
   SGG_LAUNCHED();

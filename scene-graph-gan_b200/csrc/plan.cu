@@ -91,6 +91,7 @@ struct Ws {
   __nv_bfloat16* UDB;    // [T*B, 2*EP]
   __nv_bfloat16* TRIH;   // [T*B, 2*VP] arbitrary float triples hi/lo (sgg_disc_forward)
   float* slopes; float* coef;
+  float* LNP;            // [lstm_rev grid][LR_NPART] partial LN / head gradients
   long long bytes;
 };
 
@@ -145,6 +146,7 @@ static Ws ws_layout(const sgg_dims_t& d, void* base) {
   w.TRIH = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
   w.slopes = (float*)take(m.B * 4);
   w.coef = (float*)take(m.B * 4);
+  w.LNP = (float*)take(lstm_rev_partials_floats() * 4);
   w.bytes = o;
   return w;
 }
@@ -157,6 +159,7 @@ struct Net {
   const float* theta; const __nv_bfloat16* sh; float* grad;  // grad may be null (data path only)
   const __nv_bfloat16* a;
   NetWs w;
+  float* lnp;    // per-CTA partial LN / head gradients of the reverse pass
   int NR;        // active rows per timestep (streams * B)
   int KXP, U, uoff, hoff;
   cudaStream_t st;
@@ -177,8 +180,9 @@ struct Net {
 };
 
 static Net make_net(bool gen, const sgg_dims_t& d, const float* theta, const void* sh, float* grad, const void* a,
-                    const NetWs& w, int NR, cudaStream_t st) {
+                    const NetWs& w, int NR, cudaStream_t st, float* lnp = nullptr) {
   Net n{};
+  n.lnp = lnp;
   n.gen = gen; n.m = derive(d); n.L = param_layout(gen, d);
   n.theta = theta; n.sh = (const __nv_bfloat16*)sh; n.grad = grad; n.a = (const __nv_bfloat16*)a;
   n.w = w; n.NR = NR; n.st = st;
@@ -204,16 +208,12 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream);
 // K1: P = flat(a) W_a  (bias is added where P is consumed); hoisted out of the time loop (gen:14-15).
 static int net_attn_proj(const Net& n) {
   const Dm& m = n.m;
-  SGG_CUDA(cudaMemsetAsync(n.w.P, 0, (size_t)m.B * m.RP * 4, n.st));
   sgg_gemm_desc_t g = gd_zero();
   const long long K = (long long)m.R * m.C;
   g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 0;
   g.B = n.sh + n.L.sWa; g.b_rows = 2LL * n.L.rWa; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
   g.M = m.B; g.N = m.R; g.nseg = 2; g.seg_klen[0] = g.seg_klen[1] = (int)K; g.seg_b_k[1] = n.L.rWa;  // a is bf16-exact
-  g.C = n.w.P; g.ldc = m.RP; g.atomic = 1;
-  const int tiles = ((m.B + 127) / 128);
-  int splits = 148 / tiles; if (splits < 1) splits = 1;
-  g.splits = splits; g.block_n = 256;
+  g.C = n.w.P; g.ldc = m.RP;
   return gemm(g, n.st);
 }
 
@@ -349,10 +349,7 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     lp.wdec = n.gen ? nullptr : n.theta + n.L.Wdec;
     lp.QB = n.w.QB + t * n.sQB(); lp.ldQB = 8 * m.H; lp.qb_lo = 4 * m.H;
     lp.CB = n.w.CB + t * n.sCf();
-    if (rc.wgrad) {
-      for (int i = 0; i < 5; ++i) { lp.dgamma[i] = n.grad + n.L.lng[i]; lp.dbeta[i] = n.grad + n.L.lnb[i]; }
-      if (!n.gen) { lp.dwdec = n.grad + n.L.Wdec; lp.dbdec = n.grad + n.L.bdec; }
-    }
+    if (rc.wgrad) { lp.partials = n.lnp; lp.init_partials = last ? 1 : 0; }
     // first-order rows, then the (interp, tangent) pair, in one launch
     lp.n_plain = (tan ? (rc.tan_pblk - rc.blk0) : rc.nblk) * m.B; lp.prow0 = row0;
     lp.n_tan = tan ? m.B : 0; lp.tan_prow0 = tan ? rc.tan_pblk * m.B : 0; lp.trow0 = tan ? rc.tan_blk * m.B : 0;
@@ -387,11 +384,18 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
       g.M = nrows_all; g.N = m.H;
       segs_act_weight(g, 0, m.RP, n.L.rWh, false, m.RP);
       float* cb = n.w.CB + t * n.sCf() + (long long)row0 * m.H;
-      g.C = cb; g.ldc = m.H; g.addm = cb; g.ld_addm = m.H; g.add_mod = nrows_all;
+      g.C = cb; g.ldc = m.H; g.atomic = 1;   // c_bar += e_bar W_h^T
       SGG_TRY(gemm(g, n.st));
     }
   }
   if (!rc.wgrad) return 0;
+  {  // LN gamma/beta (and D head) gradients: sum the per-CTA partials of the T launches above
+    LnGradParams lg{};
+    lg.partials = n.lnp; lg.nslices = lstm_rev_grid(nrows_all - (tan ? m.B : 0));
+    for (int i = 0; i < 5; ++i) { lg.dgamma[i] = n.grad + n.L.lng[i]; lg.dbeta[i] = n.grad + n.L.lnb[i]; }
+    if (!n.gen) { lg.dwdec = n.grad + n.L.Wdec; lg.dbdec = n.grad + n.L.bdec; }
+    SGG_TRY(lngrad_reduce(lg, n.st));
+  }
   // ---------------- weight gradients: one GEMM per kernel over all timesteps / streams
   const long long rowsT = (long long)m.T * n.NR;   // requires blk0 == 0 and nrows_all == NR
   SGG_CHECK(rc.blk0 == 0 && nrows_all == n.NR, "net_reverse: weight gradients need all active rows");
@@ -402,7 +406,7 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     g.M = n.L.KX; g.N = 4 * m.H; g.nseg = 3;
     for (int s = 0; s < 3; ++s) g.seg_klen[s] = (int)rowsT;
     g.seg_b_mn[1] = 4 * m.H; g.seg_a_mn[2] = n.KXP;
-    g.C = n.grad + n.L.K; g.ldc = 4 * m.H; g.atomic = 1; g.splits = 2; g.block_n = 256;
+    g.C = n.grad + n.L.K; g.ldc = 4 * m.H; g.atomic = 1;
     SGG_TRY(gemm(g, n.st));
   }
   {  // dW_h = C^T EB   [H, R]
@@ -412,9 +416,7 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     g.M = m.H; g.N = m.R; g.nseg = 3;
     for (int s = 0; s < 3; ++s) g.seg_klen[s] = (int)rowsT;
     g.seg_b_mn[1] = m.RP; g.seg_a_mn[2] = m.H;
-    g.C = n.grad + n.L.Watt + (long long)m.R * m.C * m.R; g.ldc = m.R; g.atomic = 1; g.block_n = 256;
-    int kb = (int)((rowsT + 63) / 64) * 3;
-    g.splits = kb >= 32 ? 32 : kb;
+    g.C = n.grad + n.L.Watt + (long long)m.R * m.C * m.R; g.ldc = m.R; g.atomic = 1;
     SGG_TRY(gemm(g, n.st));
   }
   {  // dW_a = flat(a)^T P_bar  [R*C, R] ; db_att = column sums of P_bar
@@ -428,7 +430,7 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
     g.M = (int)K; g.N = m.R; g.nseg = 2;
     g.seg_klen[0] = g.seg_klen[1] = m.B; g.seg_b_mn[1] = m.RP;
-    g.C = n.grad + n.L.Watt; g.ldc = m.R; g.atomic = 0; g.block_n = 256;
+    g.C = n.grad + n.L.Watt; g.ldc = m.R; g.atomic = 0; g.splits = 1;
     SGG_TRY(gemm(g, n.st));
     SGG_TRY(colsum(n.w.PB, m.RP, m.B, m.R, n.grad + n.L.batt, n.st));
   }
@@ -677,7 +679,7 @@ extern "C" int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, 
 static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bfloat16* fake, const float* gp_alpha,
                           float* scalars, cudaStream_t st) {
   const sgg_dims_t& dd = a->dims;
-  const Net d = make_net(false, dd, a->d_theta, a->d_shadow, a->d_grad, a->ann_d, w.d, 4 * dd.B, st);
+  const Net d = make_net(false, dd, a->d_theta, a->d_shadow, a->d_grad, a->ann_d, w.d, 4 * dd.B, st, w.LNP);
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
   const float invBT = 1.0f / ((float)B * a->world * T);
@@ -781,7 +783,7 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
 static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noise, bool recompute_proj, float* scalars,
                          cudaStream_t st) {
   const sgg_dims_t& dd = a->dims;
-  const Net g = make_net(true, dd, a->g_theta, a->g_shadow, a->g_grad, a->ann_g, w.g, dd.B, st);
+  const Net g = make_net(true, dd, a->g_theta, a->g_shadow, a->g_grad, a->ann_g, w.g, dd.B, st, w.LNP);
   const Net d = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, dd.B, st);
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
@@ -826,7 +828,7 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
     q.M = m.H; q.N = m.V; q.nseg = 3;
     for (int s = 0; s < 3; ++s) { q.seg_klen[s] = T * B; q.seg_a_mn[s] = g.hoff; }
     q.seg_b_mn[1] = m.VP; q.seg_a_mn[2] = g.KXP + g.hoff;
-    q.C = a->g_grad + g.L.Wdec; q.ldc = m.V; q.atomic = 1; q.splits = 2;
+    q.C = a->g_grad + g.L.Wdec; q.ldc = m.V; q.atomic = 1;
     SGG_TRY(gemm(q, st));
     SGG_TRY(colsum(w.DFAKE, m.VP, T * B, m.V, a->g_grad + g.L.bdec, st));
   }
