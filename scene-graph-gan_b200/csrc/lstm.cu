@@ -368,20 +368,25 @@ struct LstmRevParams {
 
 constexpr int LR_NVEC = 11;                 // dgamma[5], dbeta[5], dwdec
 constexpr int LR_NPART = LR_NVEC * LH + 4;  // + dbdec (padded)
-constexpr int LR_MAX_GRID = 296;            // 2 CTAs per SM
+constexpr int LR_MAX_GRID = 444;            // 3 CTAs per SM
 
 struct LstmSmemRev {
   LstmSmemFwd f;
   float yb[4][LH];     // adjoints of the gate activations
   float ydb[4][LH];    // ... and of their tangents
-  float acc[LR_NVEC][LH];
-  float dbd;
+};
+// Per-thread accumulators of the parameter gradients over the rows of a CTA: the gate phases always give a
+// lane the same 16 columns of gate G, the state phase always gives a thread the same 4 columns.
+struct RevAcc {
+  V16 dg, db;          // d gamma[G], d beta[G] (lane-owned columns)
+  F4 sg, sb, dw;       // d gamma[state], d beta[state], d w_dec (thread-owned columns)
+  float dbd;           // d b_dec (thread 0)
 };
 
 // Gate phase C for gate G (= this warp): reverse through the nonlinearity and its LayerNorm.
 template <bool TAN>
 __device__ __forceinline__ void gate_rev(int G, const LstmRevParams& p, LstmSmemRev& sm, long long prow, long long trow,
-                                         const V16& n, float r, const V16& xd, const V16& nd, bool wgrad) {
+                                         const V16& n, float r, const V16& xd, const V16& nd, RevAcc& acc) {
   V16 g, act, ybv, ydbv, nb, ndb, dgs;
   ld16(p.ln.gamma[G], g);
   ld16(sm.f.xa[G], act);
@@ -404,10 +409,8 @@ __device__ __forceinline__ void gate_rev(int G, const LstmRevParams& p, LstmSmem
     ybv[j] = abar;           // = d beta contribution
     nb[j] = abar * g[j];
   }
-  if (wgrad) {
-    acc16(sm.acc[G], dgs);
-    acc16(sm.acc[5 + G], ybv);
-  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { acc.dg[j] += dgs[j]; acc.db[j] += ybv[j]; }
   V16 xb;
   if (!TAN) {
     ln_proj(n, r, nb, xb);
@@ -436,7 +439,7 @@ __device__ __forceinline__ void gate_rev(int G, const LstmRevParams& p, LstmSmem
 
 template <bool TAN>
 __device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev& sm, long long prow, long long trow,
-                                             bool wgrad, int& tog) {
+                                             RevAcc& acc, int& tog) {
   const int G = threadIdx.x >> 5;
   const float* q = p.Q + prow * p.ldQ;
   const float* qd = p.Q + trow * p.ldQ;
@@ -524,16 +527,9 @@ __device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev
           rs[4] = fmaf(ncdb.v[e], s.ncd.v[e], rs[4]);
         }
       }
-      if (wgrad) {
-        const int c0 = threadIdx.x * 4;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          sm.acc[4][c0 + e] += dgs.v[e];
-          sm.acc[9][c0 + e] += dbs.v[e];
-          sm.acc[10][c0 + e] += dwv.v[e];
-        }
-        if (threadIdx.x == 0) sm.dbd += yb;
-      }
+      for (int e = 0; e < 4; ++e) { acc.sg.v[e] += dgs.v[e]; acc.sb.v[e] += dbs.v[e]; acc.dw.v[e] += dwv.v[e]; }
+      acc.dbd += yb;
     }
     block_sum(rs, sm.f.red, tog);
     // LN(state) reverse -> adjoint of c' (and of its tangent); then c' = c*sf + si*tj
@@ -571,38 +567,54 @@ __device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev
   __syncthreads();
   // ---- phase C (warp = gate): reverse through the nonlinearity and its LayerNorm
   switch (G) {
-    case 0: gate_rev<TAN>(0, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
-    case 1: gate_rev<TAN>(1, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
-    case 2: gate_rev<TAN>(2, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
-    default: gate_rev<TAN>(3, p, sm, prow, trow, n, r, xd, nd, wgrad); break;
+    case 0: gate_rev<TAN>(0, p, sm, prow, trow, n, r, xd, nd, acc); break;
+    case 1: gate_rev<TAN>(1, p, sm, prow, trow, n, r, xd, nd, acc); break;
+    case 2: gate_rev<TAN>(2, p, sm, prow, trow, n, r, xd, nd, acc); break;
+    default: gate_rev<TAN>(3, p, sm, prow, trow, n, r, xd, nd, acc); break;
   }
   // No barrier needed here: the next row's phase A writes xa[G] / xad[G], which only warp G reads in phase C,
   // and every other buffer is rewritten only after the next row's post-phase-A barrier.
 }
 
-__global__ void __launch_bounds__(LS_THREADS) lstm_rev_kernel(const LstmRevParams p) {
+__global__ void __launch_bounds__(LS_THREADS, 3) lstm_rev_kernel(const LstmRevParams p) {
   extern __shared__ __align__(16) uint8_t lr_smem_raw[];
   LstmSmemRev& sm = *reinterpret_cast<LstmSmemRev*>(lr_smem_raw);
-  const bool wgrad = p.partials != nullptr;
-  if (wgrad) {
-    float* a = &sm.acc[0][0];
-    for (int k = threadIdx.x; k < LR_NVEC * LH; k += LS_THREADS) a[k] = 0.f;
-    if (threadIdx.x == 0) sm.dbd = 0.f;
-    __syncthreads();
-  }
+  RevAcc acc;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc.dg[j] = acc.db[j] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc.sg.v[e] = acc.sb.v[e] = acc.dw.v[e] = 0.f;
+  acc.dbd = 0.f;
   const int nrows = p.n_plain + p.n_tan;
   int tog = 0;
   // tangent rows first: they are the longest
   for (int i = blockIdx.x; i < nrows; i += gridDim.x) {
-    if (i < p.n_tan) lstm_rev_row<true>(p, sm, p.tan_prow0 + i, p.trow0 + i, wgrad, tog);
-    else lstm_rev_row<false>(p, sm, p.prow0 + (i - p.n_tan), 0, wgrad, tog);
+    if (i < p.n_tan) lstm_rev_row<true>(p, sm, p.tan_prow0 + i, p.trow0 + i, acc, tog);
+    else lstm_rev_row<false>(p, sm, p.prow0 + (i - p.n_tan), 0, acc, tog);
   }
-  if (!wgrad) return;
-  __syncthreads();
+  if (p.partials == nullptr) return;
+  // flush this CTA's totals to its slice: vectors 0-3 / 5-8 by gate warps, 4 / 9 / 10 by column threads
   float* dst = p.partials + (long long)blockIdx.x * LR_NPART;
-  const float* a = &sm.acc[0][0];
-  for (int k = threadIdx.x; k < LR_NVEC * LH; k += LS_THREADS) dst[k] = p.init_partials ? a[k] : dst[k] + a[k];
-  if (threadIdx.x == 0) dst[LR_NVEC * LH] = p.init_partials ? sm.dbd : dst[LR_NVEC * LH] + sm.dbd;
+  const int G = threadIdx.x >> 5;
+  if (!p.init_partials) {
+    V16 o;
+    ld16(dst + G * LH, o);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc.dg[j] += o[j];
+    ld16(dst + (5 + G) * LH, o);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc.db[j] += o[j];
+    const F4 a = ld4(dst + 4 * LH), b = ld4(dst + 9 * LH), c = ld4(dst + 10 * LH);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc.sg.v[e] += a.v[e]; acc.sb.v[e] += b.v[e]; acc.dw.v[e] += c.v[e]; }
+    if (threadIdx.x == 0) acc.dbd += dst[LR_NVEC * LH];
+  }
+  st16(dst + G * LH, acc.dg);
+  st16(dst + (5 + G) * LH, acc.db);
+  st4(dst + 4 * LH, acc.sg);
+  st4(dst + 9 * LH, acc.sb);
+  st4(dst + 10 * LH, acc.dw);
+  if (threadIdx.x == 0) dst[LR_NVEC * LH] = acc.dbd;
 }
 
 // Sums the per-CTA partial parameter gradients of one reverse pass into the gradient bucket.
@@ -610,26 +622,30 @@ struct LnGradParams {
   const float* partials; int nslices;
   float* dgamma[5]; float* dbeta[5]; float* dwdec; float* dbdec;
 };
+constexpr int LNG_SPLIT = 16;
 __global__ void __launch_bounds__(256) lngrad_reduce_kernel(const LnGradParams p) {
   const int k = blockIdx.x * 256 + threadIdx.x;
   if (k > LR_NVEC * LH) return;
+  const int per = (p.nslices + LNG_SPLIT - 1) / LNG_SPLIT;
+  const int b0 = blockIdx.y * per, b1 = min(p.nslices, b0 + per);
+  if (b0 >= b1) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 4 <= p.nslices; b += 4) {
+  int b = b0;
+  for (; b + 4 <= b1; b += 4) {
     s0 += p.partials[(long long)b * LR_NPART + k];
     s1 += p.partials[(long long)(b + 1) * LR_NPART + k];
     s2 += p.partials[(long long)(b + 2) * LR_NPART + k];
     s3 += p.partials[(long long)(b + 3) * LR_NPART + k];
   }
-  for (; b < p.nslices; ++b) s0 += p.partials[(long long)b * LR_NPART + k];
+  for (; b < b1; ++b) s0 += p.partials[(long long)b * LR_NPART + k];
   const float s = (s0 + s1) + (s2 + s3);
   if (k == LR_NVEC * LH) {
-    if (p.dbdec) p.dbdec[0] += s;
+    if (p.dbdec) atomicAdd(p.dbdec, s);
     return;
   }
   const int vec = k / LH, col = k % LH;
   float* dst = vec < 5 ? p.dgamma[vec] : (vec < 10 ? p.dbeta[vec - 5] : p.dwdec);
-  if (dst) dst[col] += s;
+  if (dst) atomicAdd(dst + col, s);
 }
 
 int lstm_fwd(const LstmFwdParams& p, cudaStream_t stream) {
@@ -661,7 +677,7 @@ int lstm_rev(const LstmRevParams& p, cudaStream_t stream) {
   return 0;
 }
 int lngrad_reduce(const LnGradParams& p, cudaStream_t stream) {
-  lngrad_reduce_kernel<<<(LR_NVEC * LH + 1 + 255) / 256, 256, 0, stream>>>(p);
+  lngrad_reduce_kernel<<<dim3((LR_NVEC * LH + 1 + 255) / 256, LNG_SPLIT), 256, 0, stream>>>(p);
   SGG_LAUNCHED();
   return 0;
 }

@@ -391,7 +391,7 @@ def test_cuda_graph_replay_equals_eager_iterations():
         torch.cuda.synchronize()
         outs.append((tr.eng.g.theta.clone(), tr.eng.d.theta.clone(), tr.losses(), tr.kernel_launches))
     for a, b in zip(outs[0][:2], outs[1][:2]):
-        assert ((a - b).norm() / b.norm()).item() < 1e-5
+        assert ((a - b).norm() / b.norm()).item() < 1e-4   # fp32 reductions (split-K, scatter) are unordered
     assert abs(outs[0][2]["gen_cost"] - outs[1][2]["gen_cost"]) < 1e-3
     assert outs[0][3] == outs[1][3] > 0
 
