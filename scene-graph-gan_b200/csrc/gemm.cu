@@ -17,11 +17,12 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 struct GemmKParams {
   int M, N;
-  int nseg;
-  int seg_a_k[SGG_GEMM_MAX_SEG], seg_a_mn[SGG_GEMM_MAX_SEG];
-  int seg_b_k[SGG_GEMM_MAX_SEG], seg_b_mn[SGG_GEMM_MAX_SEG];
-  int seg_kb[SGG_GEMM_MAX_SEG];  // k-blocks per segment
-  int total_kb;
+  // Operand parts.  x ~= hi + lo operands are given as two parts of the same tensor (different k / mn offsets);
+  // a k-block loads every part ONCE and issues the products (A0,B0), (A1,B0), (A0,B1) into one accumulator.
+  int nA, nB;
+  int a_k[2], a_mn[2], b_k[2], b_mn[2];
+  int total_kb;                  // k-blocks of 64
+  int stages, stage_bytes;
   float* C; long long ldc; int atomic;
   __nv_bfloat16* Chl; long long ld_hl; long long lo_off;
   const float* bias;
@@ -30,24 +31,19 @@ struct GemmKParams {
   int rm_d0, rm_d1; long long rm_s0, rm_s1;   // output row permutation (rm_d0 == 0: identity)
 };
 
-template <int BN>
-struct GemmSmem {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
-  static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_SMEM_BUDGET = 200 * 1024;   // operand ring; + 1 KB alignment slack + barriers
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmKParams p) {
-  using S = GemmSmem<BN>;
+  constexpr int B_PART_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + S::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + S::STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_MAX_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -59,6 +55,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kb_begin = blockIdx.z * kb_per;
   const int kb_end = min(p.total_kb, kb_begin + kb_per);
   const int nkb = max(0, kb_end - kb_begin);
+  const int b_off = p.nA * A_STAGE_BYTES;   // B parts follow the A parts inside a stage
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -66,7 +63,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1) {
     if (elect_one()) {
-      for (int s = 0; s < S::STAGES; ++s) {
+      for (int s = 0; s < p.stages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
@@ -85,40 +82,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      // locate (segment, local k-block) of kb_begin
-      int seg = 0, kbl = kb_begin;
-      while (seg < p.nseg - 1 && kbl >= p.seg_kb[seg]) {
-        kbl -= p.seg_kb[seg];
-        ++seg;
-      }
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sA = smem + stage * S::STAGE_BYTES;
-        uint8_t* sB = sA + A_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-        const int ka = p.seg_a_k[seg] + kbl * BK;
-        const int kb = p.seg_b_k[seg] + kbl * BK;
-        if (!A_MN) {
-          tma_load_2d(sA, &tmA, &full_bar[stage], ka, m0 + p.seg_a_mn[seg]);
-        } else {
+        uint8_t* st = smem + stage * p.stage_bytes;
+        mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+        const int kc = (kb_begin + i) * BK;
+        for (int pa = 0; pa < p.nA; ++pa) {
+          uint8_t* sA = st + pa * A_STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], p.a_k[pa] + kc, m0 + p.a_mn[pa]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j)
-            tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + p.seg_a_mn[seg] + 64 * j, ka);
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + p.a_mn[pa] + 64 * j, p.a_k[pa] + kc);
+          }
         }
-        if (!B_MN) {
-          tma_load_2d(sB, &tmB, &full_bar[stage], kb, n0 + p.seg_b_mn[seg]);
-        } else {
+        for (int pb = 0; pb < p.nB; ++pb) {
+          uint8_t* sB = st + b_off + pb * B_PART_BYTES;
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], p.b_k[pb] + kc, n0 + p.b_mn[pb]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + p.seg_b_mn[seg] + 64 * j, kb);
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + p.b_mn[pb] + 64 * j, p.b_k[pb] + kc);
+          }
         }
-        if (++kbl == p.seg_kb[seg] && seg < p.nseg - 1) {
-          kbl = 0;
-          ++seg;
-        }
-        if (++stage == S::STAGES) {
+        if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
         }
@@ -133,21 +124,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sA = smem_u32(smem + stage * S::STAGE_BYTES);
-        const uint32_t sB = sA + A_STAGE_BYTES;
+        const uint32_t sA0 = smem_u32(smem + stage * p.stage_bytes);
+        const uint32_t sB0 = sA0 + b_off;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = A_MN ? make_smem_desc(sA + k * 2048, BK * 128, 1024)
-                                   : make_smem_desc(sA + k * 32, 0, 1024);
-          const uint64_t db = B_MN ? make_smem_desc(sB + k * 2048, BK * 128, 1024)
-                                   : make_smem_desc(sB + k * 32, 0, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (i | k) ? 1u : 0u);
+          const uint32_t ao = A_MN ? k * 2048 : k * 32, bo = B_MN ? k * 2048 : k * 32;
+          const uint64_t da0 = A_MN ? make_smem_desc(sA0 + ao, BK * 128, 1024) : make_smem_desc(sA0 + ao, 0, 1024);
+          const uint64_t db0 = B_MN ? make_smem_desc(sB0 + bo, BK * 128, 1024) : make_smem_desc(sB0 + bo, 0, 1024);
+          umma_bf16(tmem_base, da0, db0, idesc, (i | k) ? 1u : 0u);
+          if (p.nA == 2) {
+            const uint32_t sA1 = sA0 + A_STAGE_BYTES;
+            const uint64_t da1 = A_MN ? make_smem_desc(sA1 + ao, BK * 128, 1024) : make_smem_desc(sA1 + ao, 0, 1024);
+            umma_bf16(tmem_base, da1, db0, idesc, 1u);
+          }
+          if (p.nB == 2) {
+            const uint32_t sB1 = sB0 + B_PART_BYTES;
+            const uint64_t db1 = B_MN ? make_smem_desc(sB1 + bo, BK * 128, 1024) : make_smem_desc(sB1 + bo, 0, 1024);
+            umma_bf16(tmem_base, da0, db1, idesc, 1u);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         if (i == nkb - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
-      if (++stage == S::STAGES) {
+      if (++stage == p.stages) {
         stage = 0;
         phase ^= 1;
       }
@@ -248,18 +248,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
+static int gemm_smem_bytes() { return GEMM_SMEM_BUDGET + 1024 + 256; }
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, int splits,
                        cudaStream_t stream) {
-  using S = GemmSmem<BN>;
   auto kern = gemm_kernel<BN, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
-    SGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+    SGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes()));
     configured = true;
   }
   dim3 grid((kp.M + BM - 1) / BM, (kp.N + BN - 1) / BN, splits);
-  kern<<<grid, GEMM_THREADS, S::BYTES, stream>>>(tmA, tmB, kp);
+  const int smem = kp.stages * kp.stage_bytes + 1024 + 256;
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, kp);
   SGG_LAUNCHED();
   return 0;
 }
@@ -273,39 +275,15 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
   return launch_gemm<BN, true, false>(tmA, tmB, kp, splits, stream);
 }
 
-int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
-  SGG_CHECK(d.A && d.B, "sgg_gemm: null operand");
-  SGG_CHECK(d.M > 0 && d.N > 0, "sgg_gemm: bad M/N (%d, %d)", d.M, d.N);
-  SGG_CHECK(d.nseg >= 1 && d.nseg <= SGG_GEMM_MAX_SEG, "sgg_gemm: nseg=%d out of range", d.nseg);
-  SGG_CHECK(d.C || d.Chl, "sgg_gemm: no output");
-  GemmKParams kp{};
-  kp.M = d.M;
-  kp.N = d.N;
-  kp.nseg = d.nseg;
-  kp.total_kb = 0;
-  for (int s = 0; s < d.nseg; ++s) {
-    // A length that is not a multiple of 64 is only valid when the tail of the last k-block lies outside the
-    // tensors (TMA zero-fills out-of-bounds elements), e.g. a contraction over all rows of both operands.
-    SGG_CHECK(d.seg_klen[s] > 0, "sgg_gemm: segment %d has length %d", s, d.seg_klen[s]);
-    kp.seg_a_k[s] = d.seg_a_k[s];
-    kp.seg_a_mn[s] = d.seg_a_mn[s];
-    kp.seg_b_k[s] = d.seg_b_k[s];
-    kp.seg_b_mn[s] = d.seg_b_mn[s];
-    kp.seg_kb[s] = (d.seg_klen[s] + BK - 1) / BK;
-    kp.total_kb += kp.seg_kb[s];
-  }
-  kp.C = d.C; kp.ldc = d.ldc; kp.atomic = d.atomic;
-  kp.Chl = reinterpret_cast<__nv_bfloat16*>(d.Chl); kp.ld_hl = d.ld_hl; kp.lo_off = d.lo_off;
-  kp.bias = d.bias;
-  kp.addm = d.addm; kp.ld_addm = d.ld_addm; kp.add_mod = d.add_mod > 0 ? d.add_mod : 1;
-  kp.alpha = d.alpha;
-  kp.rm_d0 = d.out_d0; kp.rm_d1 = d.out_d1 > 0 ? d.out_d1 : 1; kp.rm_s0 = d.out_s0; kp.rm_s1 = d.out_s1;
-  // ---- tile width and split-K.  These GEMMs are small (M = a few hundred rows) and long in K (three bf16
-  // products per contraction), so a plain tile grid leaves most of the 148 SMs idle.  Unless the caller fixed
-  // them, pick (block_n, splits) minimising a simple cost: waves x (k-blocks per CTA x tile bytes / L2 feed rate).
-  // A split-K launch accumulates with fp32 vector reductions into an output that is zeroed first (or, when the
-  // caller asked for `atomic`, into whatever the output already holds).
+// One fused launch: parts (nA, nB) as described at GemmKParams.
+static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t stream) {
+  // ---- tile width and split-K.  These GEMMs are small (M = a few hundred rows) and long in K, so a plain tile grid
+  // leaves most of the 148 SMs idle.  Unless the caller fixed them, pick (block_n, splits) minimising a simple
+  // cost: waves x (k-blocks per CTA x max(stage bytes / L2 feed rate, MMA cycles)).  A split-K launch accumulates
+  // with fp32 vector reductions into an output that is zeroed first (or, when the caller asked for `atomic`, into
+  // whatever the output already holds).
   const int tm = (d.M + BM - 1) / BM;
+  const int nprod = kp.nA + kp.nB - 1;
   const bool can_split = d.C && !d.Chl;
   int bn = d.block_n, splits = d.splits > 1 ? d.splits : 1;
   if (d.splits <= 0 || d.block_n == 0) {
@@ -315,18 +293,20 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
     for (int b = bn_lo; b <= bn_hi; b *= 2) {
       if (b > 64 && d.N <= b / 2 && !d.block_n) continue;         // do not pad N by more than 2x
       const int tiles = tm * ((d.N + b - 1) / b);
-      const int sp_hi = (d.splits > 0) ? splits : (can_split && tiles < 148 ? 148 / tiles : 1);
-      for (int sp = (d.splits > 0 ? splits : 1); sp <= sp_hi; ++sp) {
+      const int sp_lo = d.splits > 0 ? splits : 1;
+      const int sp_hi = d.splits > 0 ? splits : (can_split && tiles < 148 ? 148 / tiles : 1);
+      for (int sp = sp_lo; sp <= sp_hi; ++sp) {
         if (sp > kp.total_kb) break;
         const int kb_per = (kp.total_kb + sp - 1) / sp;
-        if (sp > 1 && kb_per < 4) break;
+        if (sp > 1 && kb_per < 2) break;
         const int ctas = tiles * sp;
         const int waves = (ctas + 147) / 148;
         const int conc = ctas < 148 ? ctas : 148;                  // CTAs competing for the L2 -> SM feed
         const double feed = 6300.0 / conc < 100.0 ? 6300.0 / conc : 100.0;   // bytes / cycle / SM
-        const double kb_cyc = fmax((double)(BM + b) * BK * 2 / feed, 2.0 * b);   // TMA-bound vs MMA-bound k-block
+        const double stage_b = (double)kp.nA * A_STAGE_BYTES + (double)kp.nB * b * BK * 2;
+        const double kb_cyc = fmax(stage_b / feed, nprod * 2.0 * b);   // TMA-bound vs MMA-bound k-block
         const double epi = 600.0 + 6.0 * b * (sp > 1 ? 2.0 : 1.0);
-        const double cost = waves * (1500.0 + kb_per * kb_cyc + epi) + (sp > 1 ? 1500.0 : 0.0);
+        const double cost = waves * (2500.0 + kb_per * kb_cyc + epi) + (sp > 1 ? 1500.0 : 0.0);
         if (cost < best) { best = cost; best_bn = b; best_sp = sp; }
       }
     }
@@ -341,6 +321,11 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
     SGG_CUDA(cudaMemset2DAsync(d.C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, stream));
     kp.atomic = 1;
   }
+  kp.stage_bytes = kp.nA * A_STAGE_BYTES + kp.nB * bn * BK * 2;
+  kp.stages = GEMM_SMEM_BUDGET / kp.stage_bytes;
+  if (kp.stages > GEMM_MAX_STAGES) kp.stages = GEMM_MAX_STAGES;
+  const int kb_per = (kp.total_kb + splits - 1) / splits;
+  if (kp.stages > kb_per) kp.stages = kb_per < 1 ? 1 : kb_per;
   CUtensorMap tmA, tmB;
   // K-major: tensor [MN rows, K cols], box {64 k, tile rows}.  MN-major: tensor [K rows, MN cols], box {64 mn, 64 k}.
   SGG_TRY(make_tmap_bf16_2d(&tmA, d.A, d.a_rows, d.a_cols, d.a_ld, 64, d.a_mn_major ? BK : BM));
@@ -351,6 +336,62 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
     case 128: return dispatch_major<128>(amn, bmn, tmA, tmB, kp, splits, stream);
     default: return dispatch_major<256>(amn, bmn, tmA, tmB, kp, splits, stream);
   }
+}
+
+int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
+  SGG_CHECK(d.A && d.B, "sgg_gemm: null operand");
+  SGG_CHECK(d.M > 0 && d.N > 0, "sgg_gemm: bad M/N (%d, %d)", d.M, d.N);
+  SGG_CHECK(d.nseg >= 1 && d.nseg <= SGG_GEMM_MAX_SEG, "sgg_gemm: nseg=%d out of range", d.nseg);
+  SGG_CHECK(d.C || d.Chl, "sgg_gemm: no output");
+  GemmKParams kp{};
+  kp.M = d.M;
+  kp.N = d.N;
+  kp.C = d.C; kp.ldc = d.ldc; kp.atomic = d.atomic;
+  kp.Chl = reinterpret_cast<__nv_bfloat16*>(d.Chl); kp.ld_hl = d.ld_hl; kp.lo_off = d.lo_off;
+  kp.bias = d.bias;
+  kp.addm = d.addm; kp.ld_addm = d.ld_addm; kp.add_mod = d.add_mod > 0 ? d.add_mod : 1;
+  kp.alpha = d.alpha;
+  kp.rm_d0 = d.out_d0; kp.rm_d1 = d.out_d1 > 0 ? d.out_d1 : 1; kp.rm_s0 = d.out_s0; kp.rm_s1 = d.out_s1;
+  for (int s = 0; s < d.nseg; ++s)
+    SGG_CHECK(d.seg_klen[s] > 0, "sgg_gemm: segment %d has length %d", s, d.seg_klen[s]);
+  // ---- recognise the hi/lo product pattern: every segment pairs A0 or B0 of segment 0 with at most one other part
+  // and all segments have the same length.  (A length that is not a multiple of 64 is only valid when the tail of
+  // the last k-block lies outside the tensors or in zero padding: TMA zero-fills out-of-bounds elements.)
+  bool fusable = true;
+  kp.nA = kp.nB = 1;
+  kp.a_k[0] = d.seg_a_k[0]; kp.a_mn[0] = d.seg_a_mn[0]; kp.b_k[0] = d.seg_b_k[0]; kp.b_mn[0] = d.seg_b_mn[0];
+  for (int s = 1; s < d.nseg && fusable; ++s) {
+    const bool a_same = d.seg_a_k[s] == kp.a_k[0] && d.seg_a_mn[s] == kp.a_mn[0];
+    const bool b_same = d.seg_b_k[s] == kp.b_k[0] && d.seg_b_mn[s] == kp.b_mn[0];
+    if (d.seg_klen[s] != d.seg_klen[0] || a_same == b_same) { fusable = false; break; }
+    if (b_same) {
+      if (kp.nA == 2) { fusable = false; break; }
+      kp.nA = 2; kp.a_k[1] = d.seg_a_k[s]; kp.a_mn[1] = d.seg_a_mn[s];
+    } else {
+      if (kp.nB == 2) { fusable = false; break; }
+      kp.nB = 2; kp.b_k[1] = d.seg_b_k[s]; kp.b_mn[1] = d.seg_b_mn[s];
+    }
+  }
+  if (fusable) {
+    kp.total_kb = (d.seg_klen[0] + BK - 1) / BK;
+    return gemm_fused(d, kp, stream);
+  }
+  // ---- general segment lists: one accumulate-launch per segment
+  SGG_CHECK(d.C && !d.Chl && d.out_d0 == 0, "sgg_gemm: this segment pattern needs the plain fp32 output");
+  if (!d.atomic) SGG_CUDA(cudaMemset2DAsync(d.C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, stream));
+  for (int s = 0; s < d.nseg; ++s) {
+    sgg_gemm_desc_t e = d;
+    e.atomic = 1;
+    if (s > 0) { e.bias = nullptr; e.addm = nullptr; }
+    GemmKParams ks = kp;
+    ks.atomic = 1;
+    if (s > 0) { ks.bias = nullptr; ks.addm = nullptr; }
+    ks.nA = ks.nB = 1;
+    ks.a_k[0] = d.seg_a_k[s]; ks.a_mn[0] = d.seg_a_mn[s]; ks.b_k[0] = d.seg_b_k[s]; ks.b_mn[0] = d.seg_b_mn[s];
+    ks.total_kb = (d.seg_klen[s] + BK - 1) / BK;
+    SGG_TRY(gemm_fused(e, ks, stream));
+  }
+  return 0;
 }
 
 }  // namespace sgg
