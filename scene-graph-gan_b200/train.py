@@ -1,0 +1,167 @@
+"""``SceneGraphGAN`` trainer with the reference's interface (train.py:17-422) over the B200 hot path.
+
+Kept from the reference: the constructor signature (train.py:23-24), ``_Generator`` / ``_Discriminator`` /
+``train`` method names, the CLI flag names (train.py:399-412), the step schedule (CRITIC_ITERS D steps then one G
+step on the same batch, train.py:185-187,362-368), the losses (train.py:245-253) and the two Adam optimisers
+(train.py:258-259).  Not reproduced (outside the hot path): the conv front-end, the tf.data JPEG
+pipeline, summaries, R@k evaluation.  Documented deviations: the reference passes batch_size / critic_iters to
+the constructor in swapped order (train.py:420-421 vs 23-24) -- here each flag reaches its own parameter; the
+constructor does not delete the contents of the checkpoint / summary directories (train.py:50-53).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import time
+from typing import Iterable, Optional
+
+import torch
+
+from .architectures import Discriminator, Generator
+from .trainer import HotPathTrainer
+
+
+class SceneGraphGAN(object):
+    def __init__(self, checkpoints_dir, summaries_dir, path_to_ims_to_triples, path_to_vocab, path_to_word_embeddings,
+                 path_to_image_means, path_to_image_stds, critic_iters, batch_size, lambda_, resume,
+                 vocab_size: Optional[int] = None, n_triples: int = 1, seed: int = 0):
+        # Hyperparameters (train.py:27-32)
+        self.CRITIC_ITERS = int(critic_iters)
+        self.BATCH_SIZE = int(batch_size)
+        self.LAMBDA = float(lambda_)
+        self.resume = bool(resume)
+        self.checkpoints_dir, self.summaries_dir = checkpoints_dir, summaries_dir
+        for d in (checkpoints_dir, summaries_dir):
+            if d and not os.path.exists(d):
+                os.makedirs(d)
+        # vocabulary and embeddings (train.py:55-63); both optional for synthetic runs
+        self.vocab = None
+        if path_to_vocab and os.path.exists(path_to_vocab):
+            with open(path_to_vocab) as f:
+                self.vocab = json.load(f)
+            vocab_size = len(self.vocab)
+            self.reverse_vocab = {y: x for x, y in self.vocab.items()}      # train.py:77
+        if vocab_size is None:
+            raise ValueError("need path_to_vocab or vocab_size")
+        self.embeddings = None
+        if path_to_word_embeddings and os.path.exists(path_to_word_embeddings):
+            import numpy as np
+            self.embeddings = torch.from_numpy(np.load(path_to_word_embeddings)).float()
+            if self.embeddings.shape[0] != vocab_size:
+                raise ValueError("word_embeddings rows != vocabulary size")
+        self.ims_to_triples = None
+        if path_to_ims_to_triples and os.path.exists(path_to_ims_to_triples):
+            with open(path_to_ims_to_triples) as f:
+                self.ims_to_triples = json.load(f)
+        self.n_steps = 3 * int(n_triples)                                    # gen:85 hard-codes 3 = one triple
+        E = self.embeddings.shape[1] if self.embeddings is not None else 300
+        self.trainer = HotPathTrainer(self.BATCH_SIZE, self.n_steps, vocab_size, critic_iters=self.CRITIC_ITERS,
+                                      lam=self.LAMBDA, embed_dim=E, seed=seed, embedding=self.embeddings)
+        # train.py:65-72: Generator(len(vocab)); Discriminator(len(vocab), W) with W initialised from the embeddings
+        self.g = Generator(vocab_size, self.n_steps)
+        self.d = Discriminator(vocab_size, self.trainer.eng.d.views()["Discriminator/W"], self.n_steps)
+        self.g._attach(self.trainer.eng)
+        self.d._attach(self.trainer.eng)
+        if self.resume:
+            self._loadModel()
+
+    # ------------------------------------------------------------------ train.py:85-93
+    def _Generator(self, images, is_training=True):
+        return self.g.build_generator(images, is_training)
+
+    def _Discriminator(self, triple_input, images, is_training=True):
+        return self.d.build_discriminator(triple_input, images, is_training)
+
+    # ------------------------------------------------------------------ train.py:288-292 (never called there)
+    def _ckpt(self):
+        return os.path.join(self.checkpoints_dir, "model.ckpt.pt")
+
+    def _saveModel(self, itr=None):
+        e = self.trainer.eng
+        torch.save({"generator": e.g.state_dict(), "discriminator": e.d.state_dict(),
+                    "adam": {"g": (e.g.m.cpu(), e.g.v.cpu(), e.g.step), "d": (e.d.m.cpu(), e.d.v.cpu(), e.d.step)},
+                    "iterations": int(e.counters.item())}, self._ckpt())
+
+    def _loadModel(self):
+        ck = torch.load(self._ckpt(), map_location="cpu")
+        e = self.trainer.eng
+        e.g.load_state_dict(ck["generator"])
+        e.d.load_state_dict(ck["discriminator"])
+        for b, key in ((e.g, "g"), (e.d, "d")):
+            m, v, step = ck["adam"][key]
+            b.m.copy_(m); b.v.copy_(v); b.step = step
+        e.counters.fill_(ck["iterations"])
+
+    # ------------------------------------------------------------------ train.py:341-388
+    def train(self, batches: Optional[Iterable] = None, max_iterations: Optional[int] = None, log_every: int = 10):
+        """``batches`` yields (annotations_for_G, annotations_for_D, labels) host tensors: bf16/float [B,14,14,512]
+        twice and int64 [B, n_steps] class ids (the one-hot of train.py:173).  Without it, synthetic batches of
+        the configured shape are generated."""
+        tr = self.trainer
+        if batches is None:
+            batches = synthetic_batches(tr.B, tr.T, tr.V, tr.R, max_iterations or 100)
+        log_path = os.path.join(self.summaries_dir, "train_log.jsonl") if self.summaries_dir else None
+        t0, n = time.time(), 0
+        out = open(log_path, "a") if log_path else None
+        try:
+            for losses in tr.fit(_to_host_batches(batches, tr)):
+                n += 1
+                if out and (n % log_every == 0 or n == 1):
+                    out.write(json.dumps({"iteration": n, "images_per_s": n * tr.B * tr.world / (time.time() - t0), **losses}) + "\n")
+                if max_iterations and n >= max_iterations:
+                    break
+        finally:
+            if out:
+                out.close()
+        return n
+
+    def test(self, *args, **kwargs):
+        raise NotImplementedError("R@k evaluation (train.py:294-335) is outside the B200 hot path (SURVEY 8f-3)")
+
+
+def synthetic_batches(B, T, V, R, n, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    for _ in range(n):
+        yield (torch.randn(B, R, 512, generator=g).to(torch.bfloat16), torch.randn(B, R, 512, generator=g).to(torch.bfloat16),
+               torch.randint(0, V, (B, T), generator=g))
+
+
+def _to_host_batches(batches, tr):
+    for ag, ad, lb in batches:
+        yield (ag.to(torch.bfloat16).contiguous().pin_memory(), ad.to(torch.bfloat16).contiguous().pin_memory(),
+               lb.to(torch.int64).contiguous().pin_memory())
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser()   # flag names of train.py:399-412
+    p.add_argument("--checkpoints_dir", default="./checkpoints")
+    p.add_argument("--summaries_dir", default="./logs")
+    p.add_argument("--path_to_ims_to_triples", default="./dataset_creation/ims_to_triples.json")
+    p.add_argument("--path_to_vocab", default="./dataset_creation/vocab.json")
+    p.add_argument("--path_to_word_embeddings", default="./dataset_creation/word_embeddings.npy")
+    p.add_argument("--path_to_image_means", default="./dataset_creation/image_means.txt")
+    p.add_argument("--path_to_image_stds", default="./dataset_creation/image_stds.txt")
+    p.add_argument("--batch_size", default=64, type=int)
+    p.add_argument("--critic_iters", default=10, type=int)
+    p.add_argument("--lambda", dest="lambda_", default=10, type=int)
+    p.add_argument("--resume", default=False, type=bool)
+    p.add_argument("--GPU", default="0")
+    # additions for the hot-path build
+    p.add_argument("--vocab_size", type=int, default=None, help="synthetic vocabulary size when no vocab.json exists")
+    p.add_argument("--n_triples", type=int, default=1)
+    p.add_argument("--iterations", type=int, default=100)
+    a = p.parse_args(argv)
+    if "LOCAL_RANK" not in os.environ:
+        os.environ.setdefault("CUDA_VISIBLE_DEVICES", a.GPU)          # train.py:417-418
+    gan = SceneGraphGAN(a.checkpoints_dir, a.summaries_dir, a.path_to_ims_to_triples, a.path_to_vocab,
+                        a.path_to_word_embeddings, a.path_to_image_means, a.path_to_image_stds,
+                        critic_iters=a.critic_iters, batch_size=a.batch_size, lambda_=a.lambda_, resume=a.resume,
+                        vocab_size=a.vocab_size, n_triples=a.n_triples)
+    n = gan.train(max_iterations=a.iterations)
+    gan._saveModel()
+    print(json.dumps({"iterations": n, **gan.trainer.losses()}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""The reference's Python surface on top of the CUDA path: Generator / Discriminator classes with
+their constructors, build methods, attentionMechanism and tensor attributes; SceneGraphGAN with its constructor
+signature, _Generator / _Discriminator, train() and checkpoint helpers."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(B=5, T=3, V=60, R=196):
+    from tests.util import make_problem
+    return make_problem(B, T, V, R=R, dtype=torch.float64)
+
+
+def test_generator_class_matches_reference_semantics():
+    from oracle import sgg_oracle as O
+    from sgg_b200.architectures.generator_with_attention import Generator
+    from tests.util import rel
+    B, T, V = 5, 3, 60
+    prob = _problem(B, T, V)
+    g = Generator(V)                                       # gen:10-11
+    assert g.vocab_size == V
+    ann = prob["ann_g"].reshape(B, 14, 14, 512)
+    g.build_generator(ann.bfloat16(), True)               # creates the variables (reference initialisers)
+    assert set(g.variables) == set(prob["gp"])            # TF variable names
+    g._engine.g.load_state_dict({k: v.float() for k, v in prob["gp"].items()})
+    logits = g.build_generator(ann.bfloat16(), is_training=True, noise=prob["noise"].float())
+    ref, aux = O.generator_forward(prob["gp"], ann, prob["noise"], T, return_aux=True)
+    assert logits.shape == (B, 3, V) and rel(logits, ref) < 1e-3                 # gen:90-91
+    assert g.downsampled.shape == (B, 14, 14, 512)                               # gen:68
+    assert g.flattened_context.shape == (B, 100352)                              # gen:74
+    assert g.partially_flattened_context.shape == (B, 196, 512)                  # gen:75
+    assert g.alpha.shape == (B, 196) and rel(g.alpha, aux["alpha"][:, -1]) < 1e-3   # gen:16, last evaluated step
+    # attentionMechanism(cell_state) uses cell_state[0] = c (gen:14)
+    c = torch.randn(B, 512, generator=torch.Generator().manual_seed(4), dtype=torch.float64)
+    z = g.attentionMechanism((c.float().cuda(), None))
+    z_ref, al_ref = O.attention_mechanism(prob["gp"], "Generator/Generator", ann.reshape(B, -1), ann.reshape(B, 196, 512), (c, None))
+    assert rel(z, z_ref) < 1e-3 and rel(g.alpha, al_ref) < 1e-3
+    # fresh noise per call when none is injected (gen:81)
+    a1 = g.build_generator(ann.bfloat16())
+    a2 = g.build_generator(ann.bfloat16())
+    assert not torch.equal(a1, a2)
+
+
+def test_discriminator_class_matches_reference_semantics():
+    from oracle import sgg_oracle as O
+    from sgg_b200.architectures.discriminator_with_attention import Discriminator
+    from tests.util import rel
+    B, T, V = 5, 3, 60
+    prob = _problem(B, T, V)
+    W = prob["dp"]["Discriminator/W"].float()
+    d = Discriminator(V, W)                                # disc:9-11
+    ann = prob["ann_d"].reshape(B, 14, 14, 512)
+    fake = torch.randn(B, 3, V, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    d.build_discriminator(fake.float(), ann.bfloat16())
+    assert set(d.variables) == set(prob["dp"])
+    assert torch.equal(d.variables["Discriminator/W"].cpu(), W)     # embedding_matrix initialises Discriminator/W (train:70-72)
+    d._engine.d.load_state_dict({k: v.float() for k, v in prob["dp"].items()})
+    for tri in (fake, prob["real"]):                       # soft inputs and one-hot reals (disc:86-87)
+        out = d.build_discriminator(tri.float(), ann.bfloat16(), is_training=False)
+        ref = O.discriminator_forward(prob["dp"], tri, ann, T)
+        assert out.shape == (B, 3, 1) and rel(out, ref) < 1e-3      # disc:92-93
+    assert d.alpha.shape == (B, 196)
+    with pytest.raises(ValueError):
+        d.build_discriminator(fake.float()[:, :2], ann.bfloat16())
+    with pytest.raises(ValueError):
+        d.build_discriminator(fake.float(), torch.zeros(B, 221, 221, 3))   # pixels: the conv front-end is out of scope
+
+
+def test_scene_graph_gan_trainer(tmp_path):
+    from sgg_b200.train import SceneGraphGAN
+    V, B = 50, 4
+    vocab = {f"w{i}": i for i in range(V)}
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    import numpy as np
+    emb = (np.random.RandomState(0).rand(V, 300).astype("float32") - 0.5) * 0.2
+    np.save(tmp_path / "emb.npy", emb)
+    ck, logs = str(tmp_path / "ck"), str(tmp_path / "logs")
+    gan = SceneGraphGAN(ck, logs, None, str(tmp_path / "vocab.json"), str(tmp_path / "emb.npy"), None, None,
+                        critic_iters=2, batch_size=B, lambda_=10, resume=False)      # train.py:23-24 argument order
+    assert gan.CRITIC_ITERS == 2 and gan.BATCH_SIZE == B and gan.LAMBDA == 10
+    assert gan.g.vocab_size == V and gan.d.vocab_size == V
+    assert torch.allclose(gan.d.variables["Discriminator/W"].cpu(), torch.from_numpy(emb))
+    n = gan.train(max_iterations=3)
+    assert n == 3 and gan.trainer.iterations == 3
+    lines = open(os.path.join(logs, "train_log.jsonl")).read().strip().splitlines()
+    assert json.loads(lines[0])["iteration"] == 1
+    ann = torch.randn(B, 14, 14, 512).bfloat16()
+    fake = gan._Generator(ann)                              # train.py:85-88
+    score = gan._Discriminator(fake, ann)                   # train.py:90-93
+    assert fake.shape == (B, 3, V) and score.shape == (B, 3, 1)
+    gan._saveModel()
+    gan2 = SceneGraphGAN(ck, logs, None, str(tmp_path / "vocab.json"), str(tmp_path / "emb.npy"), None, None,
+                         critic_iters=2, batch_size=B, lambda_=10, resume=True)
+    for k, v in gan.g.variables.items():
+        assert torch.equal(v, gan2.g.variables[k]), k
+    assert int(gan2.trainer.eng.counters.item()) == 3
