@@ -19,6 +19,7 @@ from typing import Dict, Iterable, Optional, Tuple
 
 import torch
 
+from . import dp
 from ._lib import check, lib
 from .engine import Engine
 
@@ -41,7 +42,7 @@ class HotPathTrainer:
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         # identical initial weights on every rank (same seed); decorrelated noise / alpha streams per rank
         self.eng = Engine(batch_size, n_steps, vocab_size, regions, embed_dim, lam=lam, world=self.world,
-                          seed=(seed * 1000003 + 7919 * self.rank) & 0x7FFFFFFF, device=self.device,
+                          seed=dp.rank_seed(seed, self.rank), device=self.device,
                           critic_iters=self.critic_iters)
         self.eng.g.init_reference(seed * 2 + 1)
         self.eng.d.init_reference(seed * 2 + 2, embedding=embedding)
@@ -61,13 +62,13 @@ class HotPathTrainer:
 
     # ------------------------------------------------------------------ communicator
     def _init_comm(self):
-        ident = (C.c_ubyte * COMM_ID_BYTES)()
-        if self.rank == 0:
+        def make_id() -> bytes:
+            ident = (C.c_ubyte * COMM_ID_BYTES)()
             check(lib().sgg_comm_unique_id(ident), "sgg_comm_unique_id")
-        box = [bytes(ident)]
-        self.dist.broadcast_object_list(box, src=0, group=self.pg)
+            return bytes(ident)
+        ident = dp.broadcast_comm_id(self.dist, self.pg, self.rank, make_id)
         handle = C.c_void_p(0)
-        check(lib().sgg_comm_init(box[0], C.c_int32(self.rank), C.c_int32(self.world), C.byref(handle)), "sgg_comm_init")
+        check(lib().sgg_comm_init(ident, C.c_int32(self.rank), C.c_int32(self.world), C.byref(handle)), "sgg_comm_init")
         return handle
 
     def close(self) -> None:
