@@ -29,7 +29,7 @@ UNIT = "images/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (config 2: 256)")
@@ -163,45 +163,95 @@ def synthetic_host_batches(n, B, T, V, R, seed):
     return out
 
 
-def attention_roofline(trainer, args, pk):
-    """Times the dominant HBM-bound kernel family of the step, the attention step forward (K2: softmax over R and
-    context reduction over one read of the annotation tile), alone, with CUDA events on the launching stream, between
-    L2 flushes.  Algorithmic bytes per launch: B * (R*C*2 [bf16 tile] + 4*(R [e] + R [alpha]) * nv + 4*C*nv)."""
+def _time_launches(fn, n, warm=3):
+    """Average device time of n back-to-back launches (CUDA events on the launching stream)."""
+    import torch
+    st = torch.cuda.current_stream()
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(n):
+        fn(warm + i)
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / n
+
+
+def kernel_rooflines(trainer, args, pk, dev_batches):
+    """Times the HBM-bound kernels of the step alone, each as a train of back-to-back launches whose inputs
+    rotate over buffers larger than L2 (6 annotation tensors = 308 MB at B=256; the Adam buckets are 370 MB per
+    launch), with CUDA events on the launching stream.  Algorithmic bytes per launch follow SURVEY 8d / DESIGN 5.
+    The first entry (attention step forward, the kernel family north_star names) is the `roofline` object."""
     import ctypes as C
     import torch
-    from sgg_b200._lib import lib
-    fn = getattr(lib(), "sgg_attn_forward", None)
-    if fn is None:
-        return None
-    B, R = args.batch, 196
-    nv = 3
+    from sgg_b200 import ops
+    from sgg_b200._lib import check, lib, stream_ptr
+    L = lib()
+    B, R, T, V = args.batch, 196, args.timesteps, args.vocab
     dev = trainer.device
-    a = trainer.eng.ann_d
+    anns = [t for hb in dev_batches for t in hb[:2]]
+    out = []
+
+    def entry(name, secs, nbytes, note):
+        ach = nbytes / secs / 1e9
+        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": None, "us_per_launch": secs * 1e6, "algorithmic_bytes": nbytes, "peak_source": pk["source"],
+                "l2": note}
+
+    # ---- attention step forward, 3 streams (fake / real / interpolate) sharing one tile read
+    nv = 3
     E = torch.randn(nv * B, 256, device=dev)
     alpha = torch.empty_like(E)
     X = torch.empty(nv * B, 2 * 1344, dtype=torch.bfloat16, device=dev)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    st = torch.cuda.current_stream()
-    times = []
-    for i in range(13):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(st)
-        rc = fn(C.c_void_p(a.data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv), C.c_void_p(E.data_ptr()),
-                C.c_void_p(alpha.data_ptr()), C.c_int64(256), C.c_void_p(X.data_ptr()), C.c_int64(2 * 1344), C.c_int64(1344),
-                C.c_void_p(st.cuda_stream))
-        e1.record(st)
-        torch.cuda.synchronize()
-        if rc != 0:
-            return None
-        if i >= 3:
-            times.append(e0.elapsed_time(e1) * 1e-3)
-    t = statistics.median(times)
-    bytes_alg = B * (R * 512 * 2 + nv * (4 * R + 4 * R + 2 * 2 * 512))
-    ach = bytes_alg / t / 1e9
-    return {"bound": "hbm", "kernel": "attn_fwd_kernel<0> (3 streams share one annotation read)", "achieved": ach, "peak": pk["hbm"],
-            "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None, "us_per_launch": t * 1e6, "algorithmic_bytes": bytes_alg,
-            "peak_source": pk["source"], "l2": "flushed between launches"}
+
+    def attn(i):
+        a = anns[i % len(anns)]
+        check(L.sgg_attn_forward(C.c_void_p(a.data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv), C.c_void_p(E.data_ptr()),
+                                 C.c_void_p(alpha.data_ptr()), C.c_int64(256), C.c_void_p(X.data_ptr()), C.c_int64(2 * 1344),
+                                 C.c_int64(1344), stream_ptr()), "sgg_attn_forward")
+    t = _time_launches(attn, 24)
+    nbytes = B * (R * 512 * 2 + nv * (4 * R + 4 * R + 2 * 2 * 512))
+    out.append(entry("attn_fwd_kernel<0> (3 streams share one annotation read)", t, nbytes,
+                     f"24 back-to-back launches over {len(anns)} annotation tensors ({len(anns) * B * R * 1024 >> 20} MB > L2)"))
+
+    # ---- K1: P = flat(a) W_a (hi/lo weight: 2 products), split-K tcgen05 GEMM, HBM-bound at this B
+    bucket = trainer.eng.d
+    name, off, rows, cols, soff, pitch = next(e for e in bucket.entries if e[0].endswith("attention_perceptron/kernel"))
+    srows = bucket.shadow_rows[name]
+    Wa = bucket.shadow[soff:soff + 2 * srows * pitch].view(2 * srows, pitch)[:, :R]
+    P = torch.empty(B, 256, dtype=torch.float32, device=dev)
+
+    def k1(i):
+        a = anns[i % len(anns)]
+        ops.gemm(a.view(B, R * 512), Wa, B, R, b_mn=True, segs=[(0, 0, 0, 0, R * 512), (0, 0, srows, 0, R * 512)],
+                 out=P[:, :R], splits=0)
+    t = _time_launches(k1, 12)
+    nbytes = B * R * 512 * 2 + 2 * R * 512 * R * 2 + 4 * B * R
+    out.append(entry("gemm_kernel K1: P = flat(a) W_a (M=B, N=196, K=100352, hi/lo weight)", t, nbytes,
+                     "12 back-to-back launches, rotating annotation tensors; W_a hi/lo (79 MB) + annotations (51 MB) per launch"))
+
+    # ---- Adam over the discriminator bucket (+ hi/lo shadow rewrite)
+    n = bucket.theta.numel()
+    th, gr, mm, vv = (torch.zeros(n, device=dev) for _ in range(4))
+    th.copy_(bucket.theta)
+    gr.normal_(std=1e-3)
+    sh = torch.empty_like(bucket.shadow)
+    dims = trainer.eng.dims
+
+    def adam(i):
+        check(L.sgg_adam_step(C.c_int(1), C.byref(dims), C.c_void_p(th.data_ptr()), C.c_void_p(gr.data_ptr()),
+                              C.c_void_p(mm.data_ptr()), C.c_void_p(vv.data_ptr()), C.c_void_p(sh.data_ptr()),
+                              C.c_int64(i + 1), C.c_float(1e-4), C.c_float(0.5), C.c_float(0.9), C.c_float(1e-8), C.c_float(1.0),
+                              stream_ptr()), "sgg_adam_step")
+    t = _time_launches(adam, 10)
+    n_par = sum(r * c for (_, _, r, c, _, _) in bucket.entries)
+    n_sh = sum(r * c for (_, _, r, c, so, _) in bucket.entries if so >= 0)
+    nbytes = 28 * n_par + 4 * n_sh
+    out.append(entry("adam_kernel (discriminator bucket, TF-form Adam + bf16 hi/lo shadow rewrite)", t, nbytes,
+                     "10 back-to-back launches; 28 B/param + 4 B/param shadow = one launch streams 739 MB (>> L2)"))
+    return out
 
 
 def run_gpu_arm(args):
@@ -283,7 +333,7 @@ def run_gpu_arm(args):
         secs, e2e_max = t[0].item(), t[1].item()
         e2e_secs = e2e_max if e2e_secs is not None else None
 
-    roof = attention_roofline(tr, args, pk) if rank == 0 else None
+    roofs = kernel_rooflines(tr, args, pk, dev_batches) if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, times, cores = cpu_reference_iterations(args, 4, 1)
@@ -307,7 +357,7 @@ def run_gpu_arm(args):
                 "api": "HotPathTrainer.fit(pinned host batches): double-buffered H2D on a copy stream + 16 B loss read per iteration"},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "cuda_graph": tr.use_graph,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roofs[0] if roofs else None, "roofline_more": roofs[1:] if roofs else None, "cpu_baseline": cpu,
             "losses_last": losses,
         }
         print(json.dumps(line), flush=True)

@@ -34,6 +34,10 @@ int sgg_version(void);
 /* Number of CUDA kernels this library has launched (or recorded into a stream capture) in this
  * process so far.  Lets a caller report how much of a timed region ran in these kernels. */
 int64_t sgg_launch_count(void);
+/* Profiling aid: with SGG_TIMING=1 in the environment every eager (non-captured) kernel launch is bracketed by CUDA
+ * events.  This call synchronises the device, writes one "kernel;grid;block;launches;total_us" line per distinct
+ * launch shape timed since the previous call into buf (NUL-terminated, truncated to cap) and returns the size needed. */
+int64_t sgg_timing_report(char* buf, int64_t cap);
 
 /* ----------------------------------------------------------------------------------------
  * Problem dimensions.  Reference values: R=196 (14x14, gen:74-75), C=512 (gen:68), H=512

@@ -8,6 +8,8 @@
 //   attn_rev : alpha_bar_r = <z_bar, a_r>, softmax reverse (first order, or reverse over
 //              primal+tangent for the interp stream), P_bar accumulation.
 // e = P + c W_h itself (gen:14-15 in split form) is produced by the tcgen05 GEMM.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/sgg_b200.h"
 
@@ -50,6 +52,7 @@ struct AttnFwdParams {
   const float* alpha_in;              // mode 1: saved alpha (same row indexing / ld as alpha_out)
   float* alpha_out; long long ldA;    // alpha (mode 0) or adot (mode 1)
   __nv_bfloat16* X; long long ldX; long long lo_off;  // z written at X[row, 0:C] (hi) and +lo_off (lo)
+  int early_a;             // the annotations are not written by any kernel of this stream's PDL chain
 };
 
 template <int MODE, int NV>
@@ -61,11 +64,16 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParam
   const int R = p.R;
   const int nchunks = (R + AT_CHUNK_ROWS - 1) / AT_CHUNK_ROWS;
   const __nv_bfloat16* a_b = p.a + (size_t)b * R * AT_C;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < AT_STAGES; ++s) mbar_init(&sm.full[s], 1);
     mbar_fence_init();
+    // annotations that no kernel of the current stream writes (a training-iteration input) may be fetched before
+    // the preceding kernel has finished; everything else waits for it
+    if (!p.early_a) pdl_wait();
     for (int c = 0; c < min(AT_STAGES, nchunks); ++c) attn_issue_chunk(sm, a_b, c, R);
   }
+  pdl_wait();
   // ---- per-stream weights (softmax or its tangent), one warp per stream (8 warps >= AT_MAXV streams)
   if (warp >= p.nv && warp < NV) {
     for (int r = lane; r < R; r += 32) sm.w[r][warp] = 0.f;   // unused stream slots of the float4 reads
@@ -160,6 +168,195 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnFwdParam
   }
 }
 
+// ------------------------------------------------------------------------------------ fwd on tensor cores
+// The context reduction z_v = sum_r w_v[r] a[r,:] is a small contraction per sample: D[channel, stream] =
+// sum_r a[r, channel] * w[stream, r] with M = 512 channels (4 UMMA tiles of 128), N = streams padded to 16,
+// K = R regions.  Done with CUDA-core FMAs it is issue-bound (2*NV FMAs per tile element); on tcgen05 the tile
+// streams HBM -> shared memory (TMA, 128B-swizzled MN-major A operand) -> tensor core and no thread ever
+// touches it.  The softmax weights are the B operand, written to shared memory as a bf16 hi/lo pair (two MMAs per
+// k-step) so that alpha keeps 2^-17 relative precision; accumulation is fp32 in TMEM.
+//   warp 0: TMA producer (ring of A2_STAGES stages of 16 regions x 512 channels = 16 KB)
+//   warp 1: TMEM allocation + MMA issue
+//   warps 2-5: softmax (or its tangent) -> weights, then epilogue TMEM -> z hi/lo
+constexpr int A2_ROWS = 16;
+constexpr int A2_STAGES = 5;
+constexpr int A2_STAGE_BYTES = A2_ROWS * AT_C * 2;   // 16 KB = 8 boxes of {64 channels x 16 regions}
+constexpr int A2_THREADS = 192;
+constexpr int A2_NPAD = 16;
+constexpr int A2_W_BYTES = A2_NPAD * AT_RMAX * 2;    // 8 KB per part: 4 k-blocks of {16 rows x 128 B}
+constexpr int A2_TMEM_COLS = 64;                     // 4 channel tiles x 16 streams
+
+struct Attn2Smem {
+  uint8_t stage[A2_STAGES][A2_STAGE_BYTES];
+  uint8_t whi[A2_W_BYTES];
+  uint8_t wlo[A2_W_BYTES];
+  uint64_t full[A2_STAGES];
+  uint64_t empty[A2_STAGES];
+  uint64_t wready, tmem_full;
+  uint32_t tmem_ptr;
+};
+
+// byte offset of weight element (stream n, region k) inside a K-major, 128B-swizzled [16 x 256] bf16 operand
+__device__ __forceinline__ uint32_t a2_w_off(int n, int k) {
+  return (uint32_t)((k >> 6) * 2048 + (n >> 3) * 1024 + (n & 7) * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(A2_THREADS) attn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  Attn2Smem& sm = *reinterpret_cast<Attn2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.R;
+  const int nch = (R + A2_ROWS - 1) / A2_ROWS;
+  pdl_trigger();
+  if (warp == 0 && elect_one()) tma_prefetch_desc(&tmA);
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < A2_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+      mbar_init(&sm.wready, 128);
+      mbar_init(&sm.tmem_full, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm.tmem_ptr, A2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      if (!p.early_a) pdl_wait();   // annotations that a preceding kernel may have written
+      for (int c = 0; c < nch; ++c) {
+        const int st = c % A2_STAGES;
+        mbar_wait(&sm.empty[st], ((c / A2_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&sm.full[st], A2_STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < AT_C / 64; ++j)
+          tma_load_3d(sm.stage[st] + j * (A2_ROWS * 128), &tmA, &sm.full[st], 64 * j, c * A2_ROWS, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, A2_NPAD, true, false);
+    mbar_wait(&sm.wready, 0);
+    tc_fence_after();
+    const uint32_t whi = smem_u32(sm.whi), wlo = smem_u32(sm.wlo);
+    for (int c = 0; c < nch; ++c) {
+      const int st = c % A2_STAGES;
+      mbar_wait(&sm.full[st], (c / A2_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sA = smem_u32(sm.stage[st]);
+        const uint32_t boff = (uint32_t)((c >> 2) * 2048 + (c & 3) * 32);   // k-step c = regions [16c, 16c+16)
+        const uint64_t dbh = make_smem_desc(whi + boff, 0, 1024);
+        const uint64_t dbl = make_smem_desc(wlo + boff, 0, 1024);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const uint64_t da = make_smem_desc(sA + mt * (2 * A2_ROWS * 128), A2_ROWS * 128, 1024);
+          umma_bf16(tmem_base + mt * A2_NPAD, da, dbh, idesc, c ? 1u : 0u);
+          umma_bf16(tmem_base + mt * A2_NPAD, da, dbl, idesc, 1u);
+        }
+        umma_commit(&sm.empty[st]);
+        if (c == nch - 1) umma_commit(&sm.tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax / tangent weights, then epilogue =====================
+    pdl_wait();
+    const int wi = warp - 2;
+#pragma unroll 1
+    for (int n = wi; n < A2_NPAD; n += 4) {
+      float v[AT_RMAX / 32];
+      if (n < p.nv) {
+        const long long row = (long long)p.row_blk[n] * p.B + b;
+        const float* e = p.E + ((long long)p.e_blk[n] * p.B + b) * p.ldE;
+        if (MODE == 0) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < AT_RMAX / 32; ++i) {
+            const int r = lane + 32 * i;
+            v[i] = (r < R) ? e[r] : -INFINITY;
+            mx = fmaxf(mx, v[i]);
+          }
+          mx = warp_max(mx);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < AT_RMAX / 32; ++i) {
+            v[i] = (lane + 32 * i < R) ? __expf(v[i] - mx) : 0.f;
+            s += v[i];
+          }
+          s = warp_sum(s);
+          const float inv = 1.0f / s;
+#pragma unroll
+          for (int i = 0; i < AT_RMAX / 32; ++i) v[i] *= inv;
+        } else {
+          const float* al = p.alpha_in + ((long long)p.ain_blk * p.B + b) * p.ldA;
+          float m = 0.f;
+          float ed[AT_RMAX / 32];
+#pragma unroll
+          for (int i = 0; i < AT_RMAX / 32; ++i) {
+            const int r = lane + 32 * i;
+            v[i] = (r < R) ? al[r] : 0.f;
+            ed[i] = (r < R) ? e[r] : 0.f;
+            m += v[i] * ed[i];
+          }
+          m = warp_sum(m);
+#pragma unroll
+          for (int i = 0; i < AT_RMAX / 32; ++i) v[i] = v[i] * (ed[i] - m);
+        }
+        float* ao = p.alpha_out + row * p.ldA;
+#pragma unroll
+        for (int i = 0; i < AT_RMAX / 32; ++i)
+          if (lane + 32 * i < R) ao[lane + 32 * i] = v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < AT_RMAX / 32; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        __nv_bfloat16 h, l;
+        split_bf16(v[i], h, l);
+        const uint32_t off = a2_w_off(n, lane + 32 * i);
+        *reinterpret_cast<__nv_bfloat16*>(sm.whi + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sm.wlo + off) = l;
+      }
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(&sm.wready);
+    // ---- epilogue: TMEM lane = channel within the tile, column = stream
+    const int q = warp & 3;
+    mbar_wait(&sm.tmem_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * A2_NPAD), r);
+      tmem_ld_wait();
+      const int ch = mt * 128 + q * 32 + lane;
+#pragma unroll
+      for (int v = 0; v < AT_MAXV; ++v) {
+        if (v < p.nv) {
+          const long long row = (long long)p.row_blk[v] * p.B + b;
+          __nv_bfloat16 h, l;
+          split_bf16(__uint_as_float(r[v]), h, l);
+          p.X[row * p.ldX + ch] = h;
+          p.X[row * p.ldX + p.lo_off + ch] = l;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, A2_TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------------------ rev
 struct AttnRevParams {
   const __nv_bfloat16* a;
@@ -172,6 +369,7 @@ struct AttnRevParams {
   const float* edot;                      // [B, ldA] tangent of e for tan_stream (row b)
   __nv_bfloat16* EB; long long ldEB; long long lo_off;  // e_bar hi/lo out (pad columns untouched)
   float* Pbar; long long ldP;             // [B,R] += sum over primal streams of e_bar (may be null)
+  int early_a;                            // see AttnFwdParams
 };
 
 __global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParams p) {
@@ -182,11 +380,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParam
   const int R = p.R;
   const int nchunks = (R + AT_CHUNK_ROWS - 1) / AT_CHUNK_ROWS;
   const __nv_bfloat16* a_b = p.a + (size_t)b * R * AT_C;
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < AT_STAGES; ++s) mbar_init(&sm.full[s], 1);
     mbar_fence_init();
+    if (!p.early_a) pdl_wait();
     for (int c = 0; c < min(AT_STAGES, nchunks); ++c) attn_issue_chunk(sm, a_b, c, R);
   }
+  pdl_wait();
   // z_bar slices: lane owns channels [lane*8, +8) and [256 + lane*8, +8)
   float zb[AT_MAXV_REV][16];
 #pragma unroll
@@ -297,7 +498,199 @@ __global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParam
   }
 }
 
+// ------------------------------------------------------------------------------------ rev on tensor cores
+// alpha_bar_v[r] = <z_bar_v, a[r,:]> is the contraction D[region, stream] = sum_c a[r, c] * zbar[stream, c]:
+// M = regions (UMMA tiles of 128 rows; rows beyond R are zero-filled by TMA without memory traffic), N = streams
+// padded to 16, K = 512 channels.  The annotation tile is the K-major A operand in its natural layout; z_bar is
+// written to shared memory as a bf16 hi/lo pair (B operand).  The softmax reverse then runs on the 4 worker warps.
+constexpr int R2_STAGES = 4;
+constexpr int R2_STAGE_BYTES = 128 * 64 * 2;         // 16 KB: {64 channels x 128 regions}
+constexpr int R2_ZB_BYTES = A2_NPAD * AT_C * 2;      // 16 KB per part: 8 k-blocks of {16 rows x 128 B}
+constexpr int R2_TMEM_COLS = 32;                     // 2 region tiles x 16 streams
+
+struct AttnRev2Smem {
+  uint8_t stage[R2_STAGES][R2_STAGE_BYTES];
+  uint8_t zhi[R2_ZB_BYTES];
+  uint8_t zlo[R2_ZB_BYTES];
+  __align__(16) float w[AT_RMAX][AT_MAXV_REV];       // alpha_bar per region and stream
+  __align__(16) float eb[AT_MAXV_REV][AT_RMAX];      // e_bar per stream
+  uint64_t full[R2_STAGES];
+  uint64_t empty[R2_STAGES];
+  uint64_t zready, tmem_full;
+  uint32_t tmem_ptr;
+};
+
+__global__ void __launch_bounds__(A2_THREADS) attn_rev_mma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const AttnRevParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnRev2Smem& sm = *reinterpret_cast<AttnRev2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.R;
+  const int nmt = (R + 127) / 128;            // region tiles
+  const int nch = nmt * (AT_C / 64);          // ring chunks: (region tile, k-block of 64 channels)
+  pdl_trigger();
+  if (warp == 0 && elect_one()) tma_prefetch_desc(&tmA);
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < R2_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+      mbar_init(&sm.zready, 128);
+      mbar_init(&sm.tmem_full, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm.tmem_ptr, R2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      if (!p.early_a) pdl_wait();
+      for (int c = 0; c < nch; ++c) {
+        const int st = c % R2_STAGES;
+        mbar_wait(&sm.empty[st], ((c / R2_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&sm.full[st], R2_STAGE_BYTES);
+        tma_load_3d(sm.stage[st], &tmA, &sm.full[st], 64 * (c & 7), 128 * (c >> 3), b);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, A2_NPAD, false, false);
+    mbar_wait(&sm.zready, 0);
+    tc_fence_after();
+    const uint32_t zhi = smem_u32(sm.zhi), zlo = smem_u32(sm.zlo);
+    for (int c = 0; c < nch; ++c) {
+      const int st = c % R2_STAGES;
+      mbar_wait(&sm.full[st], (c / R2_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sA = smem_u32(sm.stage[st]);
+        const int kb = c & 7, mt = c >> 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = make_smem_desc(sA + k * 32, 0, 1024);
+          const uint64_t dbh = make_smem_desc(zhi + kb * 2048 + k * 32, 0, 1024);
+          const uint64_t dbl = make_smem_desc(zlo + kb * 2048 + k * 32, 0, 1024);
+          umma_bf16(tmem_base + mt * A2_NPAD, da, dbh, idesc, (kb | k) ? 1u : 0u);
+          umma_bf16(tmem_base + mt * A2_NPAD, da, dbl, idesc, 1u);
+        }
+        umma_commit(&sm.empty[st]);
+        if (c == nch - 1) umma_commit(&sm.tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    pdl_wait();
+    const int wi = warp - 2;
+    const int wtid = threadIdx.x - 64;         // 0..127 among the worker warps
+    // ---- z_bar -> B operand (stream n, channel k), K-major 128B-swizzled, hi/lo; unused streams are zero
+#pragma unroll 1
+    for (int n = wi; n < A2_NPAD; n += 4) {
+      const float* z = (n < p.nv) ? p.XB + ((long long)p.row_blk[n] * p.B + b) * p.ldXB : nullptr;
+#pragma unroll 4
+      for (int i = 0; i < AT_C / 32; ++i) {
+        const int k = lane + 32 * i;
+        const float x = z ? z[k] : 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        const uint32_t off = a2_w_off(n, k);
+        *reinterpret_cast<__nv_bfloat16*>(sm.zhi + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(sm.zlo + off) = l;
+      }
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(&sm.zready);
+    // ---- alpha_bar from TMEM: lane = region within the tile, column = stream
+    const int q = warp & 3;
+    mbar_wait(&sm.tmem_full, 0);
+    tc_fence_after();
+    for (int mt = 0; mt < nmt; ++mt) {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * A2_NPAD), r);
+      tmem_ld_wait();
+      const int row = mt * 128 + q * 32 + lane;
+      if (row < R)
+        *reinterpret_cast<float4*>(sm.w[row]) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]),
+                                                            __uint_as_float(r[2]), __uint_as_float(r[3]));
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ---- softmax reverse: one warp per primal stream
+    const int ns = (p.tan_stream >= 0) ? p.nv - 1 : p.nv;
+    if (wi < ns) {
+      const int v = wi;
+      const long long row = (long long)p.row_blk[v] * p.B + b;
+      const float* al = p.alpha + row * p.ldA;
+      const bool tan = (v == p.tan_stream);
+      float alv[AT_RMAX / 32], ab[AT_RMAX / 32], adb[AT_RMAX / 32], ed[AT_RMAX / 32];
+      float m_t = 0.f, m_e = 0.f;
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        const int r = lane + 32 * i;
+        const bool ok = r < R;
+        alv[i] = ok ? al[r] : 0.f;
+        ab[i] = ok ? sm.w[r][v] : 0.f;
+        adb[i] = (ok && tan) ? sm.w[r][p.nv - 1] : 0.f;
+        ed[i] = (ok && tan) ? p.edot[(long long)b * p.ldA + r] : 0.f;
+        m_t += alv[i] * adb[i];
+        m_e += alv[i] * ed[i];
+      }
+      float s = 0.f;
+      if (tan) {
+        m_t = warp_sum(m_t);
+        m_e = warp_sum(m_e);
+      }
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        if (tan) ab[i] = ab[i] + adb[i] * (ed[i] - m_e) - ed[i] * m_t;  // w = abar + second-order terms
+        s += alv[i] * ab[i];
+      }
+      s = warp_sum(s);
+      __nv_bfloat16* ebh = p.EB + row * p.ldEB;
+      __nv_bfloat16* tbh = tan ? p.EB + ((long long)p.row_blk[p.nv - 1] * p.B + b) * p.ldEB : nullptr;
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        const int r = lane + 32 * i;
+        if (r < R) {
+          const float ebar = alv[i] * (ab[i] - s);
+          sm.eb[v][r] = ebar;
+          __nv_bfloat16 h, l;
+          split_bf16(ebar, h, l);
+          ebh[r] = h;
+          ebh[p.lo_off + r] = l;
+          if (tan) {
+            const float edb = alv[i] * (adb[i] - m_t);
+            split_bf16(edb, h, l);
+            tbh[r] = h;
+            tbh[p.lo_off + r] = l;
+          }
+        }
+      }
+    }
+    if (p.Pbar) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int r = wtid; r < R; r += 128) {
+        float s = 0.f;
+        for (int v = 0; v < ns; ++v) s += sm.eb[v][r];
+        p.Pbar[(long long)b * p.ldP + r] += s;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, R2_TMEM_COLS);
+}
+
 static size_t attn_smem_bytes() { return sizeof(AttnSmem) + 128; }
+
+static size_t attn2_smem_bytes() { return sizeof(Attn2Smem) + 1024; }
+static bool attn_use_simt() {   // SGG_ATTN_SIMT=1 selects the CUDA-core forward kernel (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SGG_ATTN_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 
 int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
   SGG_CHECK(p.R > 0 && p.R <= AT_RMAX, "attn_fwd: R=%d out of range (1..%d)", p.R, AT_RMAX);
@@ -307,15 +700,25 @@ int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
     SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
     SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
     SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2_smem_bytes()));
     configured = true;
   }
+  if (!attn_use_simt()) {
+    CUtensorMap tm;
+    SGG_TRY(make_tmap_bf16_3d(&tm, p.a, (uint64_t)p.B, (uint64_t)p.R, AT_C, 64, A2_ROWS));
+    if (mode == 0)
+      SGG_LAUNCH(attn_fwd_mma_kernel<0>, p.B, A2_THREADS, attn2_smem_bytes(), stream, tm, p);
+    else
+      SGG_LAUNCH(attn_fwd_mma_kernel<1>, p.B, A2_THREADS, attn2_smem_bytes(), stream, tm, p);
+    return 0;
+  }
   if (mode == 0 && p.nv > 4)
-    attn_fwd_kernel<0, 8><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+    SGG_LAUNCH((attn_fwd_kernel<0, 8>), p.B, AT_THREADS, attn_smem_bytes(), stream, p);
   else if (mode == 0)
-    attn_fwd_kernel<0, 4><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
+    SGG_LAUNCH((attn_fwd_kernel<0, 4>), p.B, AT_THREADS, attn_smem_bytes(), stream, p);
   else
-    attn_fwd_kernel<1, 4><<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
-  SGG_LAUNCHED();
+    SGG_LAUNCH((attn_fwd_kernel<1, 4>), p.B, AT_THREADS, attn_smem_bytes(), stream, p);
   return 0;
 }
 
@@ -325,10 +728,17 @@ int attn_rev(const AttnRevParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     SGG_CUDA(cudaFuncSetAttribute(attn_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_rev_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(AttnRev2Smem) + 1024)));
     configured = true;
   }
-  attn_rev_kernel<<<p.B, AT_THREADS, attn_smem_bytes(), stream>>>(p);
-  SGG_LAUNCHED();
+  if (!attn_use_simt()) {
+    CUtensorMap tm;
+    SGG_TRY(make_tmap_bf16_3d(&tm, p.a, (uint64_t)p.B, (uint64_t)p.R, AT_C, 64, 128));
+    SGG_LAUNCH(attn_rev_mma_kernel, p.B, A2_THREADS, sizeof(AttnRev2Smem) + 1024, stream, tm, p);
+    return 0;
+  }
+  SGG_LAUNCH(attn_rev_kernel, p.B, AT_THREADS, attn_smem_bytes(), stream, p);
   return 0;
 }
 

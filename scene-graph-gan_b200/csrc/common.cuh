@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace sgg {
 
 // ---------------------------------------------------------------- error plumbing (host)
@@ -38,11 +40,52 @@ void note_launch();  // counts kernels launched by this library (sgg_launch_coun
     if (rc__ != 0) return rc__; \
   } while (0)
 
+// Programmatic dependent launch (PDL): every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, calls pdl_trigger() first (the next kernel in the stream may
+// then be scheduled as soon as all CTAs of this one are resident) and pdl_wait() before it touches global memory
+// (blocks until the preceding kernel has completed and flushed).  Launch latency, barrier / TMEM / descriptor
+// prologues then overlap the tail of the previous kernel.  SGG_PDL=0 in the environment turns the attribute off.
+bool pdl_enabled();
+// Optional per-launch event timing (SGG_TIMING=1; eager launches only, never during stream capture): warm,
+// in-sequence kernel durations without a profiler.  Read back with sgg_timing_report().
+bool timing_enabled();
+void timing_begin(cudaStream_t stream);
+void timing_end(cudaStream_t stream, const void* func, dim3 grid, dim3 block);
+
 // Encodes a 2-D row-major bf16 tensor map with 128B swizzle.  box = {box_cols (<=64), box_rows}.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* gptr, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_cols, uint32_t box_rows);
 
+int make_tmap_bf16_3d(CUtensorMap* map, const void* gptr, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box0,
+                      uint32_t box1);
+
 #ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (timing_enabled()) {
+    timing_begin(stream);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+    timing_end(stream, reinterpret_cast<const void*>(kern), grid, block);
+    return e;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#define SGG_LAUNCH(kern, grid, block, smem, stream, ...)                                   \
+  do {                                                                                     \
+    SGG_CUDA(::sgg::launch_k(kern, dim3(grid), dim3(block), smem, stream, __VA_ARGS__));   \
+    ::sgg::note_launch();                                                                  \
+  } while (0)
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -131,6 +174,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D tiled load, coordinates {c0 = innermost, c1, c2}.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// Makes generic-proxy writes to shared memory visible to the async proxy (TMA / tcgen05.mma operand reads).
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 1-D bulk copy global -> shared (bytes multiple of 16, 16B aligned).
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -180,6 +233,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -57,6 +57,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int nkb = max(0, kb_end - kb_begin);
   const int b_off = p.nA * A_STAGE_BYTES;   // B parts follow the A parts inside a stage
 
+  pdl_trigger();
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -78,6 +79,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // barriers, TMEM and descriptors are set up; operands / outputs belong to the preceding kernels
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -261,8 +263,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   dim3 grid((kp.M + BM - 1) / BM, (kp.N + BN - 1) / BN, splits);
   const int smem = kp.stages * kp.stage_bytes + 1024 + 256;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, kp);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(kern, grid, GEMM_THREADS, smem, stream, tmA, tmB, kp);
   return 0;
 }
 

@@ -2,6 +2,11 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -21,6 +26,43 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SGG_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// ---- per-launch event timing (debug / profiling aid)
+struct TimedLaunch { cudaEvent_t e0, e1; const void* func; dim3 grid, block; };
+static std::vector<TimedLaunch> g_timed;
+static thread_local cudaEvent_t t_ev0 = nullptr;
+bool timing_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SGG_TIMING");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+void timing_begin(cudaStream_t stream) {
+  t_ev0 = nullptr;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  if (cudaEventCreate(&t_ev0) != cudaSuccess) { t_ev0 = nullptr; return; }
+  cudaEventRecord(t_ev0, stream);
+}
+void timing_end(cudaStream_t stream, const void* func, dim3 grid, dim3 block) {
+  if (!t_ev0) return;
+  TimedLaunch t{t_ev0, nullptr, func, grid, block};
+  if (cudaEventCreate(&t.e1) != cudaSuccess) return;
+  cudaEventRecord(t.e1, stream);
+  g_timed.push_back(t);
+  t_ev0 = nullptr;
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -54,8 +96,66 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* gptr, uint64_t rows, uint64_
   return 0;
 }
 
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous, dense), 128B swizzle, box {box0 (<=64), box1, 1}.  Out-of-bounds rows of
+// a box (d1 beyond the extent) are zero-filled without touching memory: used for the per-sample annotation tiles.
+int make_tmap_bf16_3d(CUtensorMap* map, const void* gptr, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box0,
+                      uint32_t box1) {
+  auto fn = get_encode_fn();
+  SGG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled driver entry point not available (no CUDA driver?)");
+  SGG_CHECK((reinterpret_cast<uintptr_t>(gptr) & 15) == 0, "TMA base pointer %p not 16-byte aligned", gptr);
+  SGG_CHECK((d0 * 2) % 16 == 0 && box0 * 2 <= 128 && box1 <= 256, "TMA 3-D box %ux%u / row %llu unsupported", box0, box1,
+            (unsigned long long)d0);
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SGG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed (%d): dims=%llux%llux%llu box=%ux%u", (int)r,
+            (unsigned long long)d2, (unsigned long long)d1, (unsigned long long)d0, box0, box1);
+  return 0;
+}
+
 }  // namespace sgg
 
 extern "C" const char* sgg_last_error(void) { return sgg::g_err; }
 extern "C" int sgg_version(void) { return 100; }
 extern "C" int64_t sgg_launch_count(void) { return (int64_t)sgg::launch_count(); }
+
+// Synchronises the device and writes "kernel;grid;block;launches;total_us" lines for every launch timed since the
+// last report (SGG_TIMING=1) into buf; returns the number of bytes needed.
+extern "C" int64_t sgg_timing_report(char* buf, int64_t cap) {
+  using namespace sgg;
+  cudaDeviceSynchronize();
+  struct Agg { long long n = 0; double us = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& t : g_timed) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.e0, t.e1);
+    const char* name = nullptr;
+    if (cudaFuncGetName(&name, t.func) != cudaSuccess || !name) name = "?";
+    char key[512];
+    snprintf(key, sizeof(key), "%s;%ux%ux%u;%u", name, t.grid.x, t.grid.y, t.grid.z, t.block.x);
+    auto it = agg.find(key);
+    if (it == agg.end()) { order.push_back(key); it = agg.emplace(key, Agg{}).first; }
+    it->second.n += 1;
+    it->second.us += ms * 1e3;
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  g_timed.clear();
+  std::string out;
+  for (auto& k : order) {
+    char line[640];
+    snprintf(line, sizeof(line), "%s;%lld;%.2f\n", k.c_str(), agg[k].n, agg[k].us);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}

@@ -187,6 +187,8 @@ struct LstmFwdParams {
 };
 
 __global__ void __launch_bounds__(LS_THREADS) lstm_fwd_kernel(const LstmFwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) LstmSmemFwd sm;
   const int G = threadIdx.x >> 5;
   int tog = 0;
@@ -301,6 +303,8 @@ __device__ __forceinline__ void state_fwd(const LstmSmemFwd& sm, const float* c_
 }
 
 __global__ void __launch_bounds__(LS_THREADS) lstm_tan_kernel(const LstmTanParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) LstmSmemFwd sm;
   const int G = threadIdx.x >> 5;
   int tog = 0;
@@ -577,6 +581,8 @@ __device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev
 }
 
 __global__ void __launch_bounds__(LS_THREADS, 3) lstm_rev_kernel(const LstmRevParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t lr_smem_raw[];
   LstmSmemRev& sm = *reinterpret_cast<LstmSmemRev*>(lr_smem_raw);
   RevAcc acc;
@@ -624,6 +630,8 @@ struct LnGradParams {
 };
 constexpr int LNG_SPLIT = 16;
 __global__ void __launch_bounds__(256) lngrad_reduce_kernel(const LnGradParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int k = blockIdx.x * 256 + threadIdx.x;
   if (k > LR_NVEC * LH) return;
   const int per = (p.nslices + LNG_SPLIT - 1) / LNG_SPLIT;
@@ -651,15 +659,13 @@ __global__ void __launch_bounds__(256) lngrad_reduce_kernel(const LnGradParams p
 int lstm_fwd(const LstmFwdParams& p, cudaStream_t stream) {
   if (p.nrows <= 0) return 0;
   const int grid = p.nrows < 148 * 8 ? p.nrows : 148 * 8;
-  lstm_fwd_kernel<<<grid, LS_THREADS, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(lstm_fwd_kernel, grid, LS_THREADS, 0, stream, p);
   return 0;
 }
 int lstm_tan(const LstmTanParams& p, cudaStream_t stream) {
   if (p.nrows <= 0) return 0;
   const int grid = p.nrows < 148 * 8 ? p.nrows : 148 * 8;
-  lstm_tan_kernel<<<grid, LS_THREADS, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(lstm_tan_kernel, grid, LS_THREADS, 0, stream, p);
   return 0;
 }
 int lstm_rev_grid(int nrows) { return nrows < LR_MAX_GRID ? nrows : LR_MAX_GRID; }
@@ -672,13 +678,11 @@ int lstm_rev(const LstmRevParams& p, cudaStream_t stream) {
     SGG_CUDA(cudaFuncSetAttribute(lstm_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LstmSmemRev)));
     configured = true;
   }
-  lstm_rev_kernel<<<lstm_rev_grid(nrows), LS_THREADS, sizeof(LstmSmemRev), stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(lstm_rev_kernel, lstm_rev_grid(nrows), LS_THREADS, sizeof(LstmSmemRev), stream, p);
   return 0;
 }
 int lngrad_reduce(const LnGradParams& p, cudaStream_t stream) {
-  lngrad_reduce_kernel<<<dim3((LR_NVEC * LH + 1 + 255) / 256, LNG_SPLIT), 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(lngrad_reduce_kernel, dim3((LR_NVEC * LH + 1 + 255) / 256, LNG_SPLIT), 256, 0, stream, p);
   return 0;
 }
 

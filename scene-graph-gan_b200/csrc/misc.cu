@@ -19,6 +19,8 @@ struct MeanPoolParams {
 };
 
 __global__ void __launch_bounds__(256) meanpool_kernel(const MeanPoolParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[4][512];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int cg = tid & 63, rg = tid >> 6;
@@ -58,8 +60,7 @@ __global__ void __launch_bounds__(256) meanpool_kernel(const MeanPoolParams p) {
 }
 
 int meanpool(const MeanPoolParams& p, cudaStream_t stream) {
-  meanpool_kernel<<<p.B, 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(meanpool_kernel, p.B, 256, 0, stream, p);
   return 0;
 }
 
@@ -76,6 +77,8 @@ struct PackParams {
   int reps; long long rep_stride;      // the result is written `reps` times, rep_stride elements apart (0/1 = once)
 };
 __global__ void pack_hl_kernel(const PackParams p) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)p.rows * p.cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / p.cols), c = (int)(i % p.cols);
@@ -96,8 +99,7 @@ int pack_hl(const PackParams& p, cudaStream_t stream) {
   const long long n = (long long)p.rows * p.cols;
   if (n <= 0) return 0;
   const int grid = (int)llmin((n + 255) / 256, 148 * 8);
-  pack_hl_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(pack_hl_kernel, grid, 256, 0, stream, p);
   return 0;
 }
 
@@ -115,6 +117,8 @@ struct EmbedMixParams {
   __nv_bfloat16* X; long long ldX; long long x_lo; long long strideT; int uoff; int NR;
 };
 __global__ void embed_mix_kernel(const EmbedMixParams p) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)p.T * p.B * p.E;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int e = (int)(i % p.E);
@@ -144,8 +148,7 @@ __global__ void embed_mix_kernel(const EmbedMixParams p) {
 int embed_mix(const EmbedMixParams& p, cudaStream_t stream) {
   const long long n = (long long)p.T * p.B * p.E;
   const int grid = (int)llmin((n + 255) / 256, 148 * 8);
-  embed_mix_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(embed_mix_kernel, grid, 256, 0, stream, p);
   return 0;
 }
 
@@ -158,6 +161,8 @@ struct EmbedScatterParams {
   float* dWemb;
 };
 __global__ void embed_scatter_kernel(const EmbedScatterParams p) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)p.T * p.B * p.E;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int e = (int)(i % p.E);
@@ -172,8 +177,7 @@ __global__ void embed_scatter_kernel(const EmbedScatterParams p) {
 int embed_scatter(const EmbedScatterParams& p, cudaStream_t stream) {
   const long long n = (long long)p.T * p.B * p.E;
   const int grid = (int)llmin((n + 255) / 256, 148 * 8);
-  embed_scatter_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(embed_scatter_kernel, grid, 256, 0, stream, p);
   return 0;
 }
 
@@ -186,6 +190,8 @@ struct GpSlopesParams {
   float inv_Bglobal;
 };
 __global__ void __launch_bounds__(256) gp_slopes_kernel(const GpSlopesParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   const int b = blockIdx.x;
   float s = 0.f;
@@ -207,8 +213,7 @@ __global__ void __launch_bounds__(256) gp_slopes_kernel(const GpSlopesParams p) 
   }
 }
 int gp_slopes(const GpSlopesParams& p, cudaStream_t stream) {
-  gp_slopes_kernel<<<p.B, 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(gp_slopes_kernel, p.B, 256, 0, stream, p);
   return 0;
 }
 
@@ -216,6 +221,8 @@ int gp_slopes(const GpSlopesParams& p, cudaStream_t stream) {
 // Y [NR, T].  scal[1] += (sum Y[blk_fake] - sum Y[blk_real]) * inv ; scal[3] += -sum Y[blk_fake] * inv
 struct LossParams { int B, T; const float* Y; int blk_fake, blk_real; float inv; float* scal; };
 __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[2][8];
   float sf = 0.f, sr = 0.f;
   const int n = p.B * p.T;
@@ -234,13 +241,14 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
   }
 }
 int losses(const LossParams& p, cudaStream_t stream) {
-  loss_kernel<<<1, 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(loss_kernel, 1, 256, 0, stream, p);
   return 0;
 }
 
 // column sums: out[c] += sum_r src[r, c]
 __global__ void colsum_kernel(const float* src, long long ld, int rows, int cols, float* out) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
@@ -249,8 +257,7 @@ __global__ void colsum_kernel(const float* src, long long ld, int rows, int cols
 }
 int colsum(const float* src, long long ld, int rows, int cols, float* out, cudaStream_t stream) {
   dim3 grid((cols + 127) / 128, min(rows, 32));
-  colsum_kernel<<<grid, 128, 0, stream>>>(src, ld, rows, cols, out);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(colsum_kernel, grid, 128, 0, stream, src, ld, rows, cols, out);
   return 0;
 }
 
@@ -263,60 +270,87 @@ int colsum(const float* src, long long ld, int rows, int cols, float* out, cudaS
 namespace sgg {
 struct AdamSeg { long long off; long long sh_off; int cols; int pitch; long long n; long long lo_off; };
 constexpr int ADAM_MAX_SEG = 24;
+constexpr int ADAM_UNROLL = 4;                         // float4 quadruples in flight per thread and array
+constexpr int ADAM_TILE = 256 * 4 * ADAM_UNROLL;       // floats per CTA
 struct AdamParams {
   float* theta; const float* grad; float* m; float* v; __nv_bfloat16* shadow;
   float lr_t, b1, b2, eps, gscale;
   // device-side step counter (graph replay): step = iter[0] * step_mul + step_add, lr_t recomputed in the kernel
   const long long* iter; long long step_mul, step_add; float lr;
   int nseg; AdamSeg seg[ADAM_MAX_SEG];
+  int blk_start[ADAM_MAX_SEG + 1];                     // CTA range of each segment (one flat 1-D grid)
 };
+// One CTA updates ADAM_TILE consecutive floats of one tensor: all loads of the tile are issued before the first
+// use (16 x 16 B in flight per thread), the bias-corrected step size is computed by one thread meanwhile.
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams p) {
-  const int s = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_lr;
+  int s = 0;
+  while (s + 1 < p.nseg && (int)blockIdx.x >= p.blk_start[s + 1]) ++s;
   const AdamSeg sg = p.seg[s];
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  float lr_t = p.lr_t;
-  if (p.iter) {
-    const double step = (double)(p.iter[0] * p.step_mul + p.step_add);
-    lr_t = (float)((double)p.lr * sqrt(1.0 - pow((double)p.b2, step)) / (1.0 - pow((double)p.b1, step)));
-  }
-  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < sg.n; i += stride) {
+  const long long base = (long long)((int)blockIdx.x - p.blk_start[s]) * ADAM_TILE + threadIdx.x * 4;
+  float th[ADAM_UNROLL][4], g[ADAM_UNROLL][4], m[ADAM_UNROLL][4], v[ADAM_UNROLL][4];
+  const bool aligned = (sg.off & 3) == 0;
+#pragma unroll
+  for (int u = 0; u < ADAM_UNROLL; ++u) {
+    const long long i = base + u * 1024;
     const long long gi = sg.off + i;
-    float th[4], g[4], m[4], v[4];
-    const bool vec = (i + 4 <= sg.n) && ((gi & 3) == 0);
-    if (vec) {
+    if (aligned && i + 4 <= sg.n) {
       const float4 t4 = *reinterpret_cast<const float4*>(p.theta + gi);
-      const float4 g4 = *reinterpret_cast<const float4*>(p.grad + gi);
+      const float4 g4 = __ldcs(reinterpret_cast<const float4*>(p.grad + gi));   // gradients are dead after this read
       const float4 m4 = *reinterpret_cast<const float4*>(p.m + gi);
       const float4 v4 = *reinterpret_cast<const float4*>(p.v + gi);
-      th[0] = t4.x; th[1] = t4.y; th[2] = t4.z; th[3] = t4.w;
-      g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
-      m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
-      v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+      th[u][0] = t4.x; th[u][1] = t4.y; th[u][2] = t4.z; th[u][3] = t4.w;
+      g[u][0] = g4.x; g[u][1] = g4.y; g[u][2] = g4.z; g[u][3] = g4.w;
+      m[u][0] = m4.x; m[u][1] = m4.y; m[u][2] = m4.z; m[u][3] = m4.w;
+      v[u][0] = v4.x; v[u][1] = v4.y; v[u][2] = v4.z; v[u][3] = v4.w;
     } else {
-      for (int e = 0; e < 4; ++e)
-        if (i + e < sg.n) { th[e] = p.theta[gi + e]; g[e] = p.grad[gi + e]; m[e] = p.m[gi + e]; v[e] = p.v[gi + e]; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = i + e < sg.n;
+        th[u][e] = ok ? p.theta[gi + e] : 0.f; g[u][e] = ok ? p.grad[gi + e] : 0.f;
+        m[u][e] = ok ? p.m[gi + e] : 0.f; v[u][e] = ok ? p.v[gi + e] : 0.f;
+      }
     }
+  }
+  if (threadIdx.x == 0) {
+    float lr_t = p.lr_t;
+    if (p.iter) {
+      const double step = (double)(p.iter[0] * p.step_mul + p.step_add);
+      lr_t = (float)((double)p.lr * sqrt(1.0 - pow((double)p.b2, step)) / (1.0 - pow((double)p.b1, step)));
+    }
+    s_lr = lr_t;
+  }
+  __syncthreads();
+  const float lr_t = s_lr;
+#pragma unroll
+  for (int u = 0; u < ADAM_UNROLL; ++u) {
+    const long long i = base + u * 1024;
+    if (i >= sg.n) continue;
+    const long long gi = sg.off + i;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float gg = g[e] * p.gscale;
-      m[e] = p.b1 * m[e] + (1.0f - p.b1) * gg;
-      v[e] = p.b2 * v[e] + (1.0f - p.b2) * gg * gg;
-      th[e] -= lr_t * m[e] / (sqrtf(v[e]) + p.eps);
+      const float gg = g[u][e] * p.gscale;
+      m[u][e] = p.b1 * m[u][e] + (1.0f - p.b1) * gg;
+      v[u][e] = p.b2 * v[u][e] + (1.0f - p.b2) * gg * gg;
+      th[u][e] -= lr_t * m[u][e] / (sqrtf(v[u][e]) + p.eps);
     }
+    const bool vec = aligned && i + 4 <= sg.n;
     if (vec) {
-      *reinterpret_cast<float4*>(p.theta + gi) = make_float4(th[0], th[1], th[2], th[3]);
-      *reinterpret_cast<float4*>(p.m + gi) = make_float4(m[0], m[1], m[2], m[3]);
-      *reinterpret_cast<float4*>(p.v + gi) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p.theta + gi) = make_float4(th[u][0], th[u][1], th[u][2], th[u][3]);
+      *reinterpret_cast<float4*>(p.m + gi) = make_float4(m[u][0], m[u][1], m[u][2], m[u][3]);
+      *reinterpret_cast<float4*>(p.v + gi) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
     } else {
       for (int e = 0; e < 4; ++e)
-        if (i + e < sg.n) { p.theta[gi + e] = th[e]; p.m[gi + e] = m[e]; p.v[gi + e] = v[e]; }
+        if (i + e < sg.n) { p.theta[gi + e] = th[u][e]; p.m[gi + e] = m[u][e]; p.v[gi + e] = v[u][e]; }
     }
     if (p.shadow && sg.sh_off >= 0) {
       // bf16 hi/lo shadow of the updated weights (row pitch may exceed the column count)
       unsigned r = (unsigned)i / (unsigned)sg.cols, c = (unsigned)i - r * (unsigned)sg.cols;
       __nv_bfloat16 h[4], l[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) split_bf16(th[e], h[e], l[e]);
+      for (int e = 0; e < 4; ++e) split_bf16(th[u][e], h[e], l[e]);
       if (vec && ((sg.cols | sg.pitch) & 3) == 0) {   // the 4 elements share a row and are 8-byte aligned
         __nv_bfloat16* dst = p.shadow + sg.sh_off + (long long)r * sg.pitch + c;
         *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
@@ -333,16 +367,23 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
     }
   }
 }
-int adam(const AdamParams& p, long long max_n, cudaStream_t stream) {
-  const int gx = (int)llmin((max_n / 4 + 255) / 256, 148 * 8);
-  dim3 grid(gx > 0 ? gx : 1, p.nseg);
-  adam_kernel<<<grid, 256, 0, stream>>>(p);
-  SGG_LAUNCHED();
+
+int adam(AdamParams p, cudaStream_t stream) {
+  int nb = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    p.blk_start[s] = nb;
+    nb += (int)((p.seg[s].n + ADAM_TILE - 1) / ADAM_TILE);
+  }
+  p.blk_start[p.nseg] = nb;
+  if (nb == 0) return 0;
+  SGG_LAUNCH(adam_kernel, nb, 256, 0, stream, p);
   return 0;
 }
 
 // fp32 master -> bf16 shadow refresh only (initialisation / after loading parameters)
 __global__ void shadow_kernel(const float* theta, __nv_bfloat16* shadow, AdamSeg sg) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / sg.cols, c = i % sg.cols;
     __nv_bfloat16 h, l;
@@ -354,8 +395,7 @@ __global__ void shadow_kernel(const float* theta, __nv_bfloat16* shadow, AdamSeg
 int refresh_shadow(const float* theta, __nv_bfloat16* shadow, const AdamSeg& sg, cudaStream_t stream) {
   if (sg.sh_off < 0 || sg.n <= 0) return 0;
   const int grid = (int)llmin((sg.n + 255) / 256, 148 * 8);
-  shadow_kernel<<<grid, 256, 0, stream>>>(theta, shadow, sg);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(shadow_kernel, grid, 256, 0, stream, theta, shadow, sg);
   return 0;
 }
 
@@ -376,6 +416,8 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1
 // mode 0: uniform [0,1) ; mode 1: standard normal (Box-Muller)
 __global__ void rng_fill_kernel(float* out, long long n, uint64_t seed, uint64_t offset, int mode,
                                 const long long* iter, uint64_t per_iter) {
+  pdl_trigger();
+  pdl_wait();
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q * 4 >= n) return;
   if (iter) offset += (uint64_t)iter[0] * per_iter;   // device-side stream position (graph replay)
@@ -400,16 +442,18 @@ int rng_fill(float* out, long long n, uint64_t seed, uint64_t offset, int mode, 
              const long long* iter = nullptr, uint64_t per_iter = 0) {
   if (n <= 0) return 0;
   const long long quads = (n + 3) / 4;
-  rng_fill_kernel<<<(int)((quads + 255) / 256), 256, 0, stream>>>(out, n, seed, offset, mode, iter, per_iter);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(rng_fill_kernel, (int)((quads + 255) / 256), 256, 0, stream, out, n, seed, offset, mode, iter, per_iter);
   return 0;
 }
 
 // iteration counter that drives the device-side RNG position and Adam step numbers
-__global__ void bump_counter_kernel(long long* ctr) { ctr[0] += 1; }
+__global__ void bump_counter_kernel(long long* ctr) {
+  pdl_trigger();
+  pdl_wait();
+  ctr[0] += 1;
+}
 int bump_counter(long long* ctr, cudaStream_t stream) {
-  bump_counter_kernel<<<1, 1, 0, stream>>>(ctr);
-  SGG_LAUNCHED();
+  SGG_LAUNCH(bump_counter_kernel, 1, 1, 0, stream, ctr);
   return 0;
 }
 

@@ -12,6 +12,17 @@ namespace sgg {
 
 static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
 
+// Set while sgg_train_iteration enqueues its kernels: the annotation tensors are inputs of the whole iteration (no
+// kernel of the iteration writes them), so the attention kernels may start fetching their tiles before the
+// preceding kernel of the stream has finished (see pdl_wait in attn.cu).  The op-level and step-level entry points
+// leave it off: their caller may have produced the annotations with the immediately preceding kernel.
+static thread_local bool t_ann_static = false;
+struct AnnStaticScope {
+  bool prev;
+  AnnStaticScope() : prev(t_ann_static) { t_ann_static = true; }
+  ~AnnStaticScope() { t_ann_static = prev; }
+};
+
 // ============================================================================ parameter layout
 struct ParamLayout {
   bool gen;
@@ -263,7 +274,7 @@ static int net_forward(const Net& n, int nblk) {
   for (int t = 0; t < m.T; ++t) {
     SGG_TRY(net_scores(n, t, 0, rows, false));
     AttnFwdParams ap{};
-    ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk;
+    ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk; ap.early_a = t_ann_static;
     for (int v = 0; v < nblk; ++v) { ap.row_blk[v] = v; ap.e_blk[v] = v; }
     ap.E = n.w.EA + t * n.sEA(); ap.ldE = m.RP;
     ap.alpha_out = n.w.EA + t * n.sEA(); ap.ldA = m.RP;
@@ -294,7 +305,7 @@ static int net_tangent(const Net& n, int pblk, int tblk) {
     if (t > 0) {  // cdot_0 = 0 => edot_0 = adot_0 = zdot_0 = 0 (z columns of X[0] tangent rows stay zero)
       SGG_TRY(net_scores(n, t, tblk * m.B, m.B, true));
       AttnFwdParams ap{};
-      ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = 1;
+      ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = 1; ap.early_a = t_ann_static;
       ap.row_blk[0] = tblk; ap.e_blk[0] = 0; ap.ain_blk = pblk;
       ap.E = n.w.ED + (long long)t * m.B * m.RP; ap.ldE = m.RP;
       ap.alpha_in = n.w.EA + t * n.sEA();
@@ -366,7 +377,7 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     }
     if (t == 0 && !rc.wgrad) break;  // data path: nothing upstream of the step-0 attention is needed
     AttnRevParams ap{};
-    ap.a = n.a; ap.B = m.B; ap.R = m.R;
+    ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.early_a = t_ann_static;
     ap.nv = rc.nblk + (tan ? 1 : 0);
     ap.tan_stream = tan ? (rc.tan_pblk - rc.blk0) : -1;
     for (int v = 0; v < rc.nblk; ++v) ap.row_blk[v] = rc.blk0 + v;
@@ -591,9 +602,7 @@ static int adam_dev(int net, const sgg_dims_t& d, float* theta, const float* gra
   p.lr = h.lr; p.b1 = h.b1; p.b2 = h.b2; p.eps = h.eps; p.gscale = 1.0f;
   p.iter = iter; p.step_mul = step_mul; p.step_add = step_add;
   p.nseg = fill_adam_segs(L, p.seg);
-  long long mx = 0;
-  for (int i = 0; i < p.nseg; ++i) mx = p.seg[i].n > mx ? p.seg[i].n : mx;
-  return adam(p, mx, st);
+  return adam(p, st);
 }
 
 extern "C" int sgg_adam_step(int net, const sgg_dims_t* d, float* theta, const float* grad, float* m, float* v,
@@ -608,9 +617,7 @@ extern "C" int sgg_adam_step(int net, const sgg_dims_t* d, float* theta, const f
   p.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
   p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.gscale = grad_scale;
   p.nseg = fill_adam_segs(L, p.seg);
-  long long mx = 0;
-  for (int i = 0; i < p.nseg; ++i) mx = p.seg[i].n > mx ? p.seg[i].n : mx;
-  return adam(p, mx, (cudaStream_t)stream);
+  return adam(p, (cudaStream_t)stream);
 }
 
 extern "C" int sgg_rng_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream) {
@@ -683,7 +690,10 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
   const float invBT = 1.0f / ((float)B * a->world * T);
-  SGG_CUDA(cudaMemsetAsync(a->d_grad, 0, (size_t)d.L.total * 4, st));
+  {  // the dW_a block (first R*C*R floats of the bucket) is overwritten by its GEMM; everything else accumulates
+    const long long skip = (long long)m.R * m.C * m.R;
+    SGG_CUDA(cudaMemsetAsync(a->d_grad + skip, 0, (size_t)(d.L.total - skip) * 4, st));
+  }
   SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
   // 2. embeddings of the three streams
   SGG_TRY(embed_dense(d, w, fake));
@@ -788,7 +798,10 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
   const float invBT = 1.0f / ((float)B * a->world * T);
-  SGG_CUDA(cudaMemsetAsync(a->g_grad, 0, (size_t)g.L.total * 4, st));
+  {
+    const long long skip = (long long)m.R * m.C * m.R;   // dW_a is overwritten by its GEMM
+    SGG_CUDA(cudaMemsetAsync(a->g_grad + skip, 0, (size_t)(g.L.total - skip) * 4, st));
+  }
   SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
   SGG_TRY(gen_forward(g, w, noise, 1, 0, recompute_proj, a->logits_out));
   // D(fake), single stream
@@ -859,6 +872,7 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
             it->critic_iters, a->dims.S);
   SGG_CHECK(it->counters && it->noise_all && it->gp_alpha_all && it->scalars_all, "sgg_train_iteration: missing buffers");
   cudaStream_t st = (cudaStream_t)stream;
+  AnnStaticScope ann_static;
   const sgg_dims_t& dd = a->dims;
   const Ws w = ws_layout(dd, a->workspace);
   const Dm m = derive(dd);
