@@ -272,9 +272,9 @@ __global__ void __launch_bounds__(A2_THREADS) attn_fwd_mma_kernel(const __grid_c
     pdl_wait();
     const int wi = warp - 2;
 #pragma unroll 1
-    for (int n = wi; n < A2_NPAD; n += 4) {
+    for (int n = wi; n < p.nv; n += 4) {   // rows of unused streams stay unwritten: their D columns are never read
       float v[AT_RMAX / 32];
-      if (n < p.nv) {
+      {
         const long long row = (long long)p.row_blk[n] * p.B + b;
         const float* e = p.E + ((long long)p.e_blk[n] * p.B + b) * p.ldE;
         if (MODE == 0) {
@@ -315,9 +315,6 @@ __global__ void __launch_bounds__(A2_THREADS) attn_fwd_mma_kernel(const __grid_c
 #pragma unroll
         for (int i = 0; i < AT_RMAX / 32; ++i)
           if (lane + 32 * i < R) ao[lane + 32 * i] = v[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < AT_RMAX / 32; ++i) v[i] = 0.f;
       }
 #pragma unroll
       for (int i = 0; i < AT_RMAX / 32; ++i) {
@@ -586,23 +583,39 @@ __global__ void __launch_bounds__(A2_THREADS) attn_rev_mma_kernel(const __grid_c
     pdl_wait();
     const int wi = warp - 2;
     const int wtid = threadIdx.x - 64;         // 0..127 among the worker warps
-    // ---- z_bar -> B operand (stream n, channel k), K-major 128B-swizzled, hi/lo; unused streams are zero
-#pragma unroll 1
-    for (int n = wi; n < A2_NPAD; n += 4) {
-      const float* z = (n < p.nv) ? p.XB + ((long long)p.row_blk[n] * p.B + b) * p.ldXB : nullptr;
-#pragma unroll 4
-      for (int i = 0; i < AT_C / 32; ++i) {
-        const int k = lane + 32 * i;
-        const float x = z ? z[k] : 0.f;
-        __nv_bfloat16 h, l;
-        split_bf16(x, h, l);
-        const uint32_t off = a2_w_off(n, k);
-        *reinterpret_cast<__nv_bfloat16*>(sm.zhi + off) = h;
-        *reinterpret_cast<__nv_bfloat16*>(sm.zlo + off) = l;
+    // ---- z_bar -> B operand (stream n, channel k), K-major 128B-swizzled, hi/lo.  Thread owns 4 channels of every
+    // stream; rows of unused streams stay unwritten (their D columns are never read).
+    {
+      float4 zv[AT_MAXV_REV];
+#pragma unroll
+      for (int n = 0; n < AT_MAXV_REV; ++n)
+        zv[n] = (n < p.nv) ? *reinterpret_cast<const float4*>(p.XB + ((long long)p.row_blk[n] * p.B + b) * p.ldXB + wtid * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < AT_MAXV_REV; ++n) {
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(zv[n].x, h[0], l[0]); split_bf16(zv[n].y, h[1], l[1]);
+        split_bf16(zv[n].z, h[2], l[2]); split_bf16(zv[n].w, h[3], l[3]);
+        const uint32_t off = a2_w_off(n, wtid * 4);
+        *reinterpret_cast<uint2*>(sm.zhi + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        *reinterpret_cast<uint2*>(sm.zlo + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
       }
     }
     fence_proxy_async_smem();
     mbar_arrive(&sm.zready);
+    // ---- loads of the softmax reverse that do not depend on the contraction go out before waiting for it
+    const int ns = (p.tan_stream >= 0) ? p.nv - 1 : p.nv;
+    const bool tan = (wi == p.tan_stream);
+    float alv[AT_RMAX / 32], ed[AT_RMAX / 32];
+    if (wi < ns) {
+      const float* al = p.alpha + ((long long)p.row_blk[wi] * p.B + b) * p.ldA;
+#pragma unroll
+      for (int i = 0; i < AT_RMAX / 32; ++i) {
+        const int r = lane + 32 * i;
+        alv[i] = (r < R) ? al[r] : 0.f;
+        ed[i] = (r < R && tan) ? p.edot[(long long)b * p.ldA + r] : 0.f;
+      }
+    }
     // ---- alpha_bar from TMEM: lane = region within the tile, column = stream
     const int q = warp & 3;
     mbar_wait(&sm.tmem_full, 0);
@@ -618,22 +631,17 @@ __global__ void __launch_bounds__(A2_THREADS) attn_rev_mma_kernel(const __grid_c
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     // ---- softmax reverse: one warp per primal stream
-    const int ns = (p.tan_stream >= 0) ? p.nv - 1 : p.nv;
     if (wi < ns) {
       const int v = wi;
       const long long row = (long long)p.row_blk[v] * p.B + b;
-      const float* al = p.alpha + row * p.ldA;
-      const bool tan = (v == p.tan_stream);
-      float alv[AT_RMAX / 32], ab[AT_RMAX / 32], adb[AT_RMAX / 32], ed[AT_RMAX / 32];
+      float ab[AT_RMAX / 32], adb[AT_RMAX / 32];
       float m_t = 0.f, m_e = 0.f;
 #pragma unroll
       for (int i = 0; i < AT_RMAX / 32; ++i) {
         const int r = lane + 32 * i;
         const bool ok = r < R;
-        alv[i] = ok ? al[r] : 0.f;
         ab[i] = ok ? sm.w[r][v] : 0.f;
         adb[i] = (ok && tan) ? sm.w[r][p.nv - 1] : 0.f;
-        ed[i] = (ok && tan) ? p.edot[(long long)b * p.ldA + r] : 0.f;
         m_t += alv[i] * adb[i];
         m_e += alv[i] * ed[i];
       }
@@ -674,7 +682,7 @@ __global__ void __launch_bounds__(A2_THREADS) attn_rev_mma_kernel(const __grid_c
       for (int r = wtid; r < R; r += 128) {
         float s = 0.f;
         for (int v = 0; v < ns; ++v) s += sm.eb[v][r];
-        p.Pbar[(long long)b * p.ldP + r] += s;
+        atomicAdd(p.Pbar + (long long)b * p.ldP + r, s);   // fire-and-forget reduction (one writer per address and launch)
       }
     }
   }

@@ -20,6 +20,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*);   // NCCL >= 2.18 (optional)
   const char* (*GetErrorString)(ncclResult_t);
   bool ok;
 };
@@ -37,6 +38,7 @@ static NcclApi* nccl() {
       api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
       api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
       api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.CommSplit = (decltype(api.CommSplit))dlsym(h, "ncclCommSplit");
       api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
     }
   }
@@ -52,16 +54,25 @@ static NcclApi* nccl() {
     }                                                                                        \
   } while (0)
 
+// Two communicators over the same ranks: collectives on one communicator must be issued in one order on one stream,
+// so the side stream of an optimiser step (plan.cu) gets its own "lane".
 struct Comm {
   ncclComm_t nccl;
+  ncclComm_t side;   // may be null (ncclCommSplit unavailable): callers then serialise on lane 0
   int rank, world;
 };
 
-int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st) {
+bool comm_has_side_lane(void* comm) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  return c && (c->world == 1 || c->side != nullptr);
+}
+
+int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st, int lane) {
   Comm* c = reinterpret_cast<Comm*>(comm);
   SGG_CHECK(c && buf && n >= 0, "comm_allreduce: bad argument");
   if (c->world == 1 || n == 0) return 0;
-  SGG_NCCL(nccl()->AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, c->nccl, st));
+  SGG_CHECK(lane == 0 || c->side, "comm_allreduce: no side communicator");
+  SGG_NCCL(nccl()->AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, lane == 0 ? c->nccl : c->side, st));
   return 0;
 }
 
@@ -80,7 +91,7 @@ extern "C" int sgg_comm_init(const void* id, int32_t rank, int32_t world, void**
   SGG_CHECK(id && comm_out, "sgg_comm_init: null argument");
   SGG_CHECK(world >= 1 && rank >= 0 && rank < world, "sgg_comm_init: bad rank %d / world %d", rank, world);
   SGG_CHECK(nccl() != nullptr, "sgg_comm_init: libnccl.so.2 not found in this process");
-  Comm* c = new Comm{nullptr, rank, world};
+  Comm* c = new Comm{nullptr, nullptr, rank, world};
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof(uid));
   ncclResult_t r = nccl()->CommInitRank(&c->nccl, world, uid, rank);
@@ -89,6 +100,9 @@ extern "C" int sgg_comm_init(const void* id, int32_t rank, int32_t world, void**
     delete c;
     return -3;
   }
+  if (world > 1 && nccl()->CommSplit) {
+    if (nccl()->CommSplit(c->nccl, 0, rank, &c->side, nullptr) != 0) c->side = nullptr;
+  }
   *comm_out = c;
   return 0;
 }
@@ -96,11 +110,12 @@ extern "C" int sgg_comm_init(const void* id, int32_t rank, int32_t world, void**
 extern "C" int sgg_comm_destroy(void* comm) {
   Comm* c = reinterpret_cast<Comm*>(comm);
   if (!c) return 0;
+  if (c->side && nccl()) nccl()->CommDestroy(c->side);
   if (c->nccl && nccl()) nccl()->CommDestroy(c->nccl);
   delete c;
   return 0;
 }
 
 extern "C" int sgg_comm_allreduce_sum(void* comm, float* buf, int64_t n, sgg_stream_t stream) {
-  return comm_allreduce(comm, buf, (long long)n, reinterpret_cast<cudaStream_t>(stream));
+  return comm_allreduce(comm, buf, (long long)n, reinterpret_cast<cudaStream_t>(stream), 0);
 }

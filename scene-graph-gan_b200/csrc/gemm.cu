@@ -34,11 +34,14 @@ struct GemmKParams {
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_SMEM_BUDGET = 200 * 1024;   // operand ring; + 1 KB alignment slack + barriers
 
-template <int BN, bool A_MN, bool B_MN>
+// MT = m-tiles (of 128 rows) per CTA.  MT = 2 keeps two accumulators (2 x BN TMEM columns) so that a wide B tile is
+// fetched once per 256 output rows: used for the W_a contractions, whose shared-memory fill is dominated by B.
+template <int BN, bool A_MN, bool B_MN, int MT = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmKParams p) {
   constexpr int B_PART_BYTES = BN * BK * 2;
+  constexpr int A_PART_BYTES = MT * A_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
@@ -47,7 +50,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.x * BM;
+  const int m0 = blockIdx.x * (BM * MT);
   const int n0 = blockIdx.y * BN;
   // split-K range for this CTA
   const int splits = gridDim.z;
@@ -55,7 +58,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kb_begin = blockIdx.z * kb_per;
   const int kb_end = min(p.total_kb, kb_begin + kb_per);
   const int nkb = max(0, kb_end - kb_begin);
-  const int b_off = p.nA * A_STAGE_BYTES;   // B parts follow the A parts inside a stage
+  const int b_off = p.nA * A_PART_BYTES;   // B parts follow the A parts inside a stage
 
   pdl_trigger();
   if (warp == 0 && elect_one()) {
@@ -72,7 +75,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, BN);
+    tmem_alloc(tmem_ptr, MT * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -92,13 +95,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_expect_tx(&full_bar[stage], p.stage_bytes);
         const int kc = (kb_begin + i) * BK;
         for (int pa = 0; pa < p.nA; ++pa) {
-          uint8_t* sA = st + pa * A_STAGE_BYTES;
-          if (!A_MN) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], p.a_k[pa] + kc, m0 + p.a_mn[pa]);
-          } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + p.a_mn[pa] + 64 * j, p.a_k[pa] + kc);
+          for (int mt = 0; mt < MT; ++mt) {
+            uint8_t* sA = st + pa * A_PART_BYTES + mt * A_STAGE_BYTES;
+            if (!A_MN) {
+              tma_load_2d(sA, &tmA, &full_bar[stage], p.a_k[pa] + kc, m0 + mt * BM + p.a_mn[pa]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + mt * BM + p.a_mn[pa] + 64 * j, p.a_k[pa] + kc);
+            }
           }
         }
         for (int pb = 0; pb < p.nB; ++pb) {
@@ -119,7 +125,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // the MMA spans only the valid columns of a ragged last n-tile (N rounded up to the UMMA granule of 16)
+    const int n_valid = p.N - n0;
+    const uint32_t idesc = make_idesc_bf16(BM, n_valid >= BN ? BN : ((n_valid + 15) & ~15), A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < nkb; ++i) {
@@ -131,18 +139,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint32_t ao = A_MN ? k * 2048 : k * 32, bo = B_MN ? k * 2048 : k * 32;
-          const uint64_t da0 = A_MN ? make_smem_desc(sA0 + ao, BK * 128, 1024) : make_smem_desc(sA0 + ao, 0, 1024);
           const uint64_t db0 = B_MN ? make_smem_desc(sB0 + bo, BK * 128, 1024) : make_smem_desc(sB0 + bo, 0, 1024);
-          umma_bf16(tmem_base, da0, db0, idesc, (i | k) ? 1u : 0u);
-          if (p.nA == 2) {
-            const uint32_t sA1 = sA0 + A_STAGE_BYTES;
-            const uint64_t da1 = A_MN ? make_smem_desc(sA1 + ao, BK * 128, 1024) : make_smem_desc(sA1 + ao, 0, 1024);
-            umma_bf16(tmem_base, da1, db0, idesc, 1u);
-          }
-          if (p.nB == 2) {
-            const uint32_t sB1 = sB0 + B_PART_BYTES;
-            const uint64_t db1 = B_MN ? make_smem_desc(sB1 + bo, BK * 128, 1024) : make_smem_desc(sB1 + bo, 0, 1024);
-            umma_bf16(tmem_base, da0, db1, idesc, 1u);
+          const uint32_t sB1 = sB0 + B_PART_BYTES;
+          const uint64_t db1 = B_MN ? make_smem_desc(sB1 + bo, BK * 128, 1024) : make_smem_desc(sB1 + bo, 0, 1024);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t sAm = sA0 + mt * A_STAGE_BYTES;
+            const uint32_t acc = tmem_base + mt * BN;
+            const uint64_t da0 = A_MN ? make_smem_desc(sAm + ao, BK * 128, 1024) : make_smem_desc(sAm + ao, 0, 1024);
+            umma_bf16(acc, da0, db0, idesc, (i | k) ? 1u : 0u);
+            if (p.nA == 2) {
+              const uint32_t sA1 = sAm + A_PART_BYTES;
+              const uint64_t da1 = A_MN ? make_smem_desc(sA1 + ao, BK * 128, 1024) : make_smem_desc(sA1 + ao, 0, 1024);
+              umma_bf16(acc, da1, db0, idesc, 1u);
+            }
+            if (p.nB == 2) umma_bf16(acc, da0, db1, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -157,9 +168,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (nkb > 0) {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row = m0 + q * 32 + (int)lane_id();
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+#pragma unroll 1
+   for (int mt = 0; mt < MT; ++mt) {
+    const int row = m0 + mt * BM + q * 32 + (int)lane_id();
     const bool row_ok = row < p.M;
     long long orow = row;
     if (p.rm_d0 > 0) {
@@ -167,12 +178,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       orow = (long long)(row / p.rm_d0) * p.rm_s0 + (long long)(rem / p.rm_d1) * p.rm_s1 + (rem % p.rm_d1);
     }
     const float* addrow = p.addm ? p.addm + (long long)(row % p.add_mod) * p.ld_addm : nullptr;
+    if (addrow && blockIdx.z == 0) {   // broadcast-add operand: into L1 while the main loop runs
+      for (int c = 0; c < BN / 32; ++c)
+        if (n0 + c * 32 < p.N) prefetch_l1(addrow + n0 + c * 32);
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;
       uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c * 32), r);
       tmem_ld_wait();
       if (!row_ok) continue;
       float v[32];
@@ -244,24 +261,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+   }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, MT * BN);
 }
 
 static int gemm_smem_bytes() { return GEMM_SMEM_BUDGET + 1024 + 256; }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MT = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, int splits,
                        cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, MT>;
   static bool configured = false;
   if (!configured) {
     SGG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes()));
     configured = true;
   }
-  dim3 grid((kp.M + BM - 1) / BM, (kp.N + BN - 1) / BN, splits);
+  dim3 grid((kp.M + BM * MT - 1) / (BM * MT), (kp.N + BN - 1) / BN, splits);
   const int smem = kp.stages * kp.stage_bytes + 1024 + 256;
   SGG_LAUNCH(kern, grid, GEMM_THREADS, smem, stream, tmA, tmB, kp);
   return 0;
@@ -269,7 +287,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 template <int BN>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                          const GemmKParams& kp, int splits, cudaStream_t stream) {
+                          const GemmKParams& kp, int splits, cudaStream_t stream, int mt = 1) {
+  if (BN == 256 && mt == 2) {   // the two W_a contractions: K1 (A K-major, B MN-major) and dW_a (both MN-major)
+    if (!a_mn && b_mn) return launch_gemm<256, false, true, 2>(tmA, tmB, kp, splits, stream);
+    if (a_mn && b_mn) return launch_gemm<256, true, true, 2>(tmA, tmB, kp, splits, stream);
+  }
   if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, kp, splits, stream);
   if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, kp, splits, stream);
   if (a_mn && b_mn) return launch_gemm<BN, true, true>(tmA, tmB, kp, splits, stream);
@@ -287,7 +309,22 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   const int nprod = kp.nA + kp.nB - 1;
   const bool can_split = d.C && !d.Chl;
   int bn = d.block_n, splits = d.splits > 1 ? d.splits : 1;
-  if (d.splits <= 0 || d.block_n == 0) {
+  // B-heavy contractions (single A part, hi/lo B, N <= 256: the two W_a GEMMs): 256-row CTAs with two accumulators, so
+  // the wide B tile enters shared memory once per 256 output rows.
+  const bool wide_b = kp.nA == 1 && kp.nB == 2 && d.b_mn_major && d.M >= 2 * BM && d.N > 128 && d.N <= 256 &&
+                      (d.block_n == 0 || d.block_n == 256);
+  const int mt = wide_b ? 2 : 1;
+  if (wide_b) {
+    bn = 256;
+    if (d.splits <= 0) {
+      const int tiles = (d.M + 2 * BM - 1) / (2 * BM);
+      splits = (can_split && tiles < 148) ? 148 / tiles : 1;
+      if (splits > kp.total_kb / 2) splits = kp.total_kb / 2 > 0 ? kp.total_kb / 2 : 1;
+    }
+  } else if (d.splits <= 0 || d.block_n == 0) {
+    // Cost model (cycles), constants fitted to graph-replayed timings of the step's GEMM shapes on B200
+    // (tools/gemm_micro.py, profiles/): fixed launch + prologue + pipeline fill, per-k-block max(operand feed, MMA issue),
+    // epilogue per output column, and a penalty for split-K (output memset node + fp32 reductions).
     double best = 1e30;
     int best_bn = 128, best_sp = 1;
     const int bn_lo = d.block_n ? d.block_n : 64, bn_hi = d.block_n ? d.block_n : 256;
@@ -295,19 +332,20 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
       if (b > 64 && d.N <= b / 2 && !d.block_n) continue;         // do not pad N by more than 2x
       const int tiles = tm * ((d.N + b - 1) / b);
       const int sp_lo = d.splits > 0 ? splits : 1;
-      const int sp_hi = d.splits > 0 ? splits : (can_split && tiles < 148 ? 148 / tiles : 1);
+      const int sp_hi = d.splits > 0 ? splits : (can_split ? (tiles < 148 && 148 / tiles > 8 ? 148 / tiles : 8) : 1);
       for (int sp = sp_lo; sp <= sp_hi; ++sp) {
         if (sp > kp.total_kb) break;
         const int kb_per = (kp.total_kb + sp - 1) / sp;
         if (sp > 1 && kb_per < 2) break;
         const int ctas = tiles * sp;
+        if (sp > sp_lo && ctas > 3 * 148) break;
         const int waves = (ctas + 147) / 148;
         const int conc = ctas < 148 ? ctas : 148;                  // CTAs competing for the L2 -> SM feed
-        const double feed = 6300.0 / conc < 100.0 ? 6300.0 / conc : 100.0;   // bytes / cycle / SM
+        const double feed = 13440.0 / conc < 88.0 ? 13440.0 / conc : 88.0;   // bytes / cycle / SM
         const double stage_b = (double)kp.nA * A_STAGE_BYTES + (double)kp.nB * b * BK * 2;
-        const double kb_cyc = fmax(stage_b / feed, nprod * 2.0 * b);   // TMA-bound vs MMA-bound k-block
-        const double epi = 600.0 + 6.0 * b * (sp > 1 ? 2.0 : 1.0);
-        const double cost = waves * (2500.0 + kb_per * kb_cyc + epi) + (sp > 1 ? 1500.0 : 0.0);
+        const double kb_cyc = fmax(stage_b / feed, nprod * 1.93 * b);   // TMA-bound vs MMA-bound k-block
+        const double epi = 3140.0 + 69.0 * b * (sp > 1 ? 0.2 : 1.0);
+        const double cost = waves * (8885.0 + kb_per * kb_cyc + epi) + (sp > 1 ? 6370.0 : 0.0);
         if (cost < best) { best = cost; best_bn = b; best_sp = sp; }
       }
     }
@@ -322,7 +360,7 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
     SGG_CUDA(cudaMemset2DAsync(d.C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, stream));
     kp.atomic = 1;
   }
-  kp.stage_bytes = kp.nA * A_STAGE_BYTES + kp.nB * bn * BK * 2;
+  kp.stage_bytes = kp.nA * mt * A_STAGE_BYTES + kp.nB * bn * BK * 2;
   kp.stages = GEMM_SMEM_BUDGET / kp.stage_bytes;
   if (kp.stages > GEMM_MAX_STAGES) kp.stages = GEMM_MAX_STAGES;
   const int kb_per = (kp.total_kb + splits - 1) / splits;
@@ -335,7 +373,7 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   switch (bn) {
     case 64: return dispatch_major<64>(amn, bmn, tmA, tmB, kp, splits, stream);
     case 128: return dispatch_major<128>(amn, bmn, tmA, tmB, kp, splits, stream);
-    default: return dispatch_major<256>(amn, bmn, tmA, tmB, kp, splits, stream);
+    default: return dispatch_major<256>(amn, bmn, tmA, tmB, kp, splits, stream, mt);
   }
 }
 

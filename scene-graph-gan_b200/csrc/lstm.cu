@@ -141,6 +141,9 @@ struct LstmLN {
 //   n, r      : normalised pre-activation and 1/std (kept for the reverse gate phase)
 //   xd, nd    : tangent pre-activation and its LN tangent (TAN only)
 //   act, actd : gate activation and its tangent
+// G (= warp index) is a run-time value: one copy of the gate code serves the four gates (the kernels were instruction-
+// fetch bound with one specialised copy per gate).  sigmoid and tanh share one exponential and one reciprocal:
+//   e = exp(-k |a|), r = 1/(1+e);  tanh(a) = sign(a) (1-e) r  (k = 2);  sigmoid(a) = a >= 0 ? r : e r  (k = 1).
 template <bool TAN>
 __device__ __forceinline__ void gate_fwd(int G, const float* q, const float* qd, const LstmLN& ln, V16& n, float& r,
                                          V16& xd, V16& nd, V16& act, V16& actd) {
@@ -151,18 +154,17 @@ __device__ __forceinline__ void gate_fwd(int G, const float* q, const float* qd,
   ld16(ln.beta[G], bt);
   ln_norm(x, n, r);
   if (TAN) ln_proj(n, r, xd, nd);
+  const bool is_tanh = (G == 1);
+  const float fb = (G == 2) ? FORGET_BIAS_F : 0.f;
+  const float k = is_tanh ? -2.0f : -1.0f;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const float a = fmaf(n[j], g[j], bt[j]);
-    if (G == 1) {
-      const float t = tanhf_(a);
-      act[j] = t;
-      if (TAN) actd[j] = (1.f - t * t) * nd[j] * g[j];
-    } else {
-      const float s = sigmoidf_(G == 2 ? a + FORGET_BIAS_F : a);
-      act[j] = s;
-      if (TAN) actd[j] = s * (1.f - s) * nd[j] * g[j];
-    }
+    const float a = fmaf(n[j], g[j], bt[j]) + fb;
+    const float e = __expf(k * fabsf(a));
+    const float rr = 1.0f / (1.0f + e);
+    const float y = is_tanh ? copysignf((1.0f - e) * rr, a) : (a >= 0.f ? rr : e * rr);
+    act[j] = y;
+    if (TAN) actd[j] = (is_tanh ? (1.f - y * y) : y * (1.f - y)) * nd[j] * g[j];
   }
 }
 
@@ -193,16 +195,12 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_fwd_kernel(const LstmFwdParam
   const int G = threadIdx.x >> 5;
   int tog = 0;
   for (int row = blockIdx.x; row < p.nrows; row += gridDim.x) {
+    prefetch_l1(p.Cin + (long long)row * LH + threadIdx.x * 4);   // state-phase operand: fetched under the gate phase
     {
       V16 n, xd, nd, act, actd;
       float r;
       const float* q = p.Q + (long long)row * p.ldQ;
-      switch (G) {   // G is warp-uniform; the switch makes it a compile-time constant inside
-        case 0: gate_fwd<false>(0, q, q, p.ln, n, r, xd, nd, act, actd); break;
-        case 1: gate_fwd<false>(1, q, q, p.ln, n, r, xd, nd, act, actd); break;
-        case 2: gate_fwd<false>(2, q, q, p.ln, n, r, xd, nd, act, actd); break;
-        default: gate_fwd<false>(3, q, q, p.ln, n, r, xd, nd, act, actd); break;
-      }
+      gate_fwd<false>(G, q, q, p.ln, n, r, xd, nd, act, actd);
       st16(sm.xa[G], act);
     }
     __syncthreads();
@@ -310,17 +308,14 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_tan_kernel(const LstmTanParam
   int tog = 0;
   for (int i = blockIdx.x; i < p.nrows; i += gridDim.x) {
     const long long prow = p.prow0 + i, trow = p.trow0 + i;
+    prefetch_l1(p.C + prow * LH + threadIdx.x * 4);
+    prefetch_l1(p.C + trow * LH + threadIdx.x * 4);
     {
       V16 n, xd, nd, act, actd;
       float r;
       const float* q = p.Q + prow * p.ldQ;
       const float* qd = p.Q + trow * p.ldQ;
-      switch (G) {
-        case 0: gate_fwd<true>(0, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-        case 1: gate_fwd<true>(1, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-        case 2: gate_fwd<true>(2, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-        default: gate_fwd<true>(3, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-      }
+      gate_fwd<true>(G, q, qd, p.ln, n, r, xd, nd, act, actd);
       st16(sm.xa[G], act);
       st16(sm.xad[G], actd);
     }
@@ -447,17 +442,24 @@ __device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev
   const int G = threadIdx.x >> 5;
   const float* q = p.Q + prow * p.ldQ;
   const float* qd = p.Q + trow * p.ldQ;
+  {  // operands of the state phase: fetched into L1 under the gate phase (each is one 2 KB row, 16 B per thread)
+    const int c4 = threadIdx.x * 4;
+    prefetch_l1(p.C + prow * LH + c4);
+    if (p.XBn) prefetch_l1(p.XBn + prow * p.ldXB + p.hoff + c4);
+    if (p.HB) prefetch_l1(p.HB + prow * p.ldHB + c4);
+    if (p.CBn) prefetch_l1(p.CBn + prow * LH + c4);
+    if (TAN) {
+      prefetch_l1(p.C + trow * LH + c4);
+      if (p.XBn) prefetch_l1(p.XBn + trow * p.ldXB + p.hoff + c4);
+      if (p.CBn) prefetch_l1(p.CBn + trow * LH + c4);
+    }
+  }
   // ---- phase A (warp = gate): recompute the gate activations (and tangents); n, r, xd, nd stay in registers
   V16 n, xd, nd;
   float r;
   {
     V16 act, actd;
-    switch (G) {
-      case 0: gate_fwd<TAN>(0, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-      case 1: gate_fwd<TAN>(1, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-      case 2: gate_fwd<TAN>(2, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-      default: gate_fwd<TAN>(3, q, qd, p.ln, n, r, xd, nd, act, actd); break;
-    }
+    gate_fwd<TAN>(G, q, qd, p.ln, n, r, xd, nd, act, actd);
     st16(sm.f.xa[G], act);
     if (TAN) st16(sm.f.xad[G], actd);
   }
@@ -570,12 +572,7 @@ __device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev
   }
   __syncthreads();
   // ---- phase C (warp = gate): reverse through the nonlinearity and its LayerNorm
-  switch (G) {
-    case 0: gate_rev<TAN>(0, p, sm, prow, trow, n, r, xd, nd, acc); break;
-    case 1: gate_rev<TAN>(1, p, sm, prow, trow, n, r, xd, nd, acc); break;
-    case 2: gate_rev<TAN>(2, p, sm, prow, trow, n, r, xd, nd, acc); break;
-    default: gate_rev<TAN>(3, p, sm, prow, trow, n, r, xd, nd, acc); break;
-  }
+  gate_rev<TAN>(G, p, sm, prow, trow, n, r, xd, nd, acc);
   // No barrier needed here: the next row's phase A writes xa[G] / xad[G], which only warp G reads in phase C,
   // and every other buffer is rewritten only after the next row's post-phase-A barrier.
 }

@@ -3,6 +3,7 @@
 // kernels in gemm.cu / attn.cu / lstm.cu / misc.cu.  The maths follows tests/plan_mirror.py
 // (hoisted attention projection, pass batching, reverse over a forward tangent for the
 // gradient penalty); every sequence is enqueued on the caller's stream, nothing allocates.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -22,6 +23,47 @@ struct AnnStaticScope {
   AnnStaticScope() : prev(t_ann_static) { t_ann_static = true; }
   ~AnnStaticScope() { t_ann_static = prev; }
 };
+
+// ---------------------------------------------------------------------------- side stream (fork / join)
+// The W_a chain of an optimiser step -- dW_a GEMM (HBM-bound, 79 MB written), its all-reduce and the Adam update of
+// W_a (85 % of the parameters) -- is independent of the other weight-gradient GEMMs.  It runs on a library-owned side
+// stream that forks from the caller's stream after the reverse time loop and joins it again before the next step, so
+// the HBM-bound chain overlaps the tensor-bound one.  Fork and join are event edges, hence capturable into a graph.
+// SGG_SIDE_STREAM=0 keeps everything on the caller's stream.
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+static SideStream* side_stream() {
+  static thread_local SideStream ss[16] = {};
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("SGG_SIDE_STREAM"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& x = ss[dev];
+  if (!x.ok) {
+    if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    x.ok = true;
+  }
+  return &x;
+}
+// side stream starts after everything enqueued on `st` so far
+static int side_fork(cudaStream_t st, cudaStream_t* out) {
+  SideStream* ss = side_stream();
+  if (!ss) { *out = st; return 0; }
+  SGG_CUDA(cudaEventRecord(ss->fork, st));
+  SGG_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+  *out = ss->s;
+  return 0;
+}
+// `st` continues after everything enqueued on the side stream so far
+static int side_join(cudaStream_t st, cudaStream_t s1) {
+  if (s1 == st) return 0;
+  SideStream* ss = side_stream();
+  SGG_CUDA(cudaEventRecord(ss->join, s1));
+  SGG_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
+  return 0;
+}
 
 // ============================================================================ parameter layout
 struct ParamLayout {
@@ -53,7 +95,8 @@ static ParamLayout param_layout(bool gen, const sgg_dims_t& d) {
   L.total = o;
   long long s = 0;
   auto stake = [&](long long n) { long long r = s; s = rup(s + n, 128); return r; };
-  L.pAtt = (int)rup(d.R, 8); L.pK = 4 * d.H; L.pWdec = (int)rup(L.OUT, 8); L.pWemb = (int)rup(d.E, 8);
+  // row pitches are multiples of 128 bytes: every 64-column TMA box row is then exactly one aligned L2 line
+  L.pAtt = (int)rup(d.R, 64); L.pK = 4 * d.H; L.pWdec = (int)rup(L.OUT, 64); L.pWemb = (int)rup(d.E, 64);
   L.rWa = (int)rup((long long)d.R * d.C, 64); L.rWh = (int)rup(d.H, 64); L.rK = (int)rup(L.KX, 64);
   L.rWdec = (int)rup(d.H, 64); L.rWemb = (int)rup(d.V, 64);
   L.sWa = stake(2LL * L.rWa * L.pAtt);
@@ -338,7 +381,7 @@ struct RevCfg {
 
 // Reverse pass over T steps.  With wgrad: LN / head gradients inside lstm_rev, P_bar in attn_rev, and
 // the weight-gradient GEMMs afterwards (contraction over all rows and timesteps at once).
-static int net_reverse(const Net& n, const RevCfg& rc) {
+static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = nullptr) {
   const Dm& m = n.m;
   const bool tan = rc.tan_blk >= 0;
   const int row0 = rc.blk0 * m.B;
@@ -410,6 +453,23 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
   // ---------------- weight gradients: one GEMM per kernel over all timesteps / streams
   const long long rowsT = (long long)m.T * n.NR;   // requires blk0 == 0 and nrows_all == NR
   SGG_CHECK(rc.blk0 == 0 && nrows_all == n.NR, "net_reverse: weight gradients need all active rows");
+  SGG_TRY(colsum(n.w.PB, m.RP, m.B, m.R, n.grad + n.L.batt, n.st));   // db_att = column sums of P_bar
+  {  // dW_a = flat(a)^T P_bar  [R*C, R]: on the side stream when the caller takes it over (it joins later)
+    cudaStream_t s1 = n.st;
+    if (side_out) { SGG_TRY(side_fork(n.st, &s1)); *side_out = s1; }
+    PackParams pk{};
+    pk.rows = m.B; pk.cols = m.R; pk.src = n.w.PB; pk.ld = m.RP;
+    pk.dst = n.w.PBH; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
+    SGG_TRY(pack_hl(pk, s1));
+    sgg_gemm_desc_t g = gd_zero();
+    const long long K = (long long)m.R * m.C;
+    g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 1;
+    g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
+    g.M = (int)K; g.N = m.R; g.nseg = 2;
+    g.seg_klen[0] = g.seg_klen[1] = m.B; g.seg_b_mn[1] = m.RP;
+    g.C = n.grad + n.L.Watt; g.ldc = m.R; g.atomic = 0; g.splits = 1;
+    SGG_TRY(gemm(g, s1));
+  }
   {  // dK = X^T QB   [KX, 4H], three hi/lo products
     sgg_gemm_desc_t g = gd_zero();
     g.A = n.w.X; g.a_rows = rowsT; g.a_cols = 2 * n.KXP; g.a_ld = 2 * n.KXP; g.a_mn_major = 1;
@@ -429,21 +489,6 @@ static int net_reverse(const Net& n, const RevCfg& rc) {
     g.seg_b_mn[1] = m.RP; g.seg_a_mn[2] = m.H;
     g.C = n.grad + n.L.Watt + (long long)m.R * m.C * m.R; g.ldc = m.R; g.atomic = 1;
     SGG_TRY(gemm(g, n.st));
-  }
-  {  // dW_a = flat(a)^T P_bar  [R*C, R] ; db_att = column sums of P_bar
-    PackParams pk{};
-    pk.rows = m.B; pk.cols = m.R; pk.src = n.w.PB; pk.ld = m.RP;
-    pk.dst = n.w.PBH; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
-    SGG_TRY(pack_hl(pk, n.st));
-    sgg_gemm_desc_t g = gd_zero();
-    const long long K = (long long)m.R * m.C;
-    g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 1;
-    g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
-    g.M = (int)K; g.N = m.R; g.nseg = 2;
-    g.seg_klen[0] = g.seg_klen[1] = m.B; g.seg_b_mn[1] = m.RP;
-    g.C = n.grad + n.L.Watt; g.ldc = m.R; g.atomic = 0; g.splits = 1;
-    SGG_TRY(gemm(g, n.st));
-    SGG_TRY(colsum(n.w.PB, m.RP, m.B, m.R, n.grad + n.L.batt, n.st));
   }
   return 0;
 }
@@ -592,16 +637,27 @@ extern "C" int sgg_refresh_shadow(int net, const sgg_dims_t* d, const float* the
 }
 
 struct AdamHyper { float lr, b1, b2, eps; };
-namespace sgg { int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st); }  // comm.cu
+namespace sgg {
+int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st, int lane = 0);  // comm.cu
+bool comm_has_side_lane(void* comm);
+}
 // Adam with the step number taken from the device counter: step = iter[0] * step_mul + step_add.
+// which: 0 = every tensor, 1 = only W_a (the annotation rows of the attention kernel), 2 = everything but W_a
 static int adam_dev(int net, const sgg_dims_t& d, float* theta, const float* grad, float* mm, float* vv, void* shadow,
-                    const AdamHyper& h, const long long* iter, long long step_mul, long long step_add, cudaStream_t st) {
+                    const AdamHyper& h, const long long* iter, long long step_mul, long long step_add, cudaStream_t st,
+                    int which = 0) {
   const ParamLayout L = param_layout(net == 0, d);
   AdamParams p{};
   p.theta = theta; p.grad = grad; p.m = mm; p.v = vv; p.shadow = (__nv_bfloat16*)shadow;
   p.lr = h.lr; p.b1 = h.b1; p.b2 = h.b2; p.eps = h.eps; p.gscale = 1.0f;
   p.iter = iter; p.step_mul = step_mul; p.step_add = step_add;
   p.nseg = fill_adam_segs(L, p.seg);
+  if (which == 1) {
+    p.nseg = 1;                                   // segment 0 is W_a (fill_adam_segs)
+  } else if (which == 2) {
+    for (int i = 1; i < p.nseg; ++i) p.seg[i - 1] = p.seg[i];
+    p.nseg -= 1;
+  }
   return adam(p, st);
 }
 
@@ -683,8 +739,10 @@ extern "C" int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, 
 // One discriminator step (train:365): grads of disc_cost = mean D(G(z)) - mean D(real) + lam * GP
 // w.r.t. every Discriminator* variable into d_grad; scalars[1] = w_disc, scalars[2] = gp.
 // `fake` = the generator's logits for this step (hi/lo rows t*B+b, a constant here), already computed.
+// side_out: when non-null the dW_a chain is left running on the side stream returned through it (the caller enqueues
+// the W_a optimiser work there and joins); when null the step joins before returning.
 static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bfloat16* fake, const float* gp_alpha,
-                          float* scalars, cudaStream_t st) {
+                          float* scalars, cudaStream_t st, cudaStream_t* side_out = nullptr) {
   const sgg_dims_t& dd = a->dims;
   const Net d = make_net(false, dd, a->d_theta, a->d_shadow, a->d_grad, a->ann_d, w.d, 4 * dd.B, st, w.LNP);
   const Dm& m = d.m;
@@ -742,7 +800,8 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   rv.blk0 = 0; rv.nblk = 3; rv.tan_pblk = 2; rv.tan_blk = 3;
   rv.ybar_blk[0] = invBT; rv.ybar_blk[1] = -invBT; rv.ybar_blk[2] = 0.f; rv.ydot_bar = a->lam;
   rv.wgrad = true;
-  SGG_TRY(net_reverse(d, rv));
+  cudaStream_t s1 = st;
+  SGG_TRY(net_reverse(d, rv, &s1));
   // 7. embedding gradient: fake^T (ub_f + al ub_i) + scatter(labels, ub_r + (1-al) ub_i) + v^T udot_bar
   {
     PackParams pk{};
@@ -773,6 +832,8 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     es.blk_real = 1; es.blk_int = 2; es.dWemb = a->d_grad + d.L.Wemb;
     SGG_TRY(embed_scatter(es, st));
   }
+  if (side_out) *side_out = s1;
+  else SGG_TRY(side_join(st, s1));
   return 0;
 }
 
@@ -791,7 +852,7 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
 // One generator step (train:368): grads of gen_cost = -mean D(G(z)) w.r.t. every Generator*
 // variable into g_grad; scalars[3] = gen_cost.
 static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noise, bool recompute_proj, float* scalars,
-                         cudaStream_t st) {
+                         cudaStream_t st, cudaStream_t* side_out = nullptr) {
   const sgg_dims_t& dd = a->dims;
   const Net g = make_net(true, dd, a->g_theta, a->g_shadow, a->g_grad, a->ann_g, w.g, dd.B, st, w.LNP);
   const Net d = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, dd.B, st);
@@ -833,7 +894,8 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   }
   RevCfg rg{};
   rg.blk0 = 0; rg.nblk = 1; rg.tan_pblk = -1; rg.tan_blk = -1; rg.HB = w.HB; rg.wgrad = true;
-  SGG_TRY(net_reverse(g, rg));
+  cudaStream_t s1 = st;
+  SGG_TRY(net_reverse(g, rg, &s1));
   {  // dW_dec = H^T dfake [H, V], db_dec = column sums of dfake
     sgg_gemm_desc_t q = gd_zero();
     q.A = g.w.X + g.sX(); q.a_rows = (long long)T * B; q.a_cols = 2 * g.KXP; q.a_ld = 2 * g.KXP; q.a_mn_major = 1;
@@ -845,6 +907,8 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
     SGG_TRY(gemm(q, st));
     SGG_TRY(colsum(w.DFAKE, m.VP, T * B, m.V, a->g_grad + g.L.bdec, st));
   }
+  if (side_out) *side_out = s1;
+  else SGG_TRY(side_join(st, s1));
   return 0;
 }
 
@@ -893,17 +957,32 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
   }
   // ---- critic steps
   AdamHyper hp{it->lr, it->beta1, it->beta2, it->eps};
+  // Each optimiser step is split in two independent chains that meet again before the next step:
+  //   side stream : dW_a GEMM -> [all-reduce of the W_a block] -> Adam on W_a           (HBM- / NVLink-bound)
+  //   main stream : the other weight gradients -> [all-reduce of the rest] -> Adam on the rest
+  const bool side_ok = !it->comm || comm_has_side_lane(it->comm);
+  auto optimise = [&](int net, float* theta, float* grad, float* mm, float* vv, void* shadow, long long step_mul,
+                      long long step_add, cudaStream_t s1) -> int {
+    const ParamLayout L = param_layout(net == 0, dd);
+    const long long n_wa = (long long)m.R * m.C * m.R;
+    if (s1 != st && !side_ok) { SGG_TRY(side_join(st, s1)); s1 = st; }
+    if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad, n_wa, s1, s1 != st ? 1 : 0));
+    SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1));
+    if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad + n_wa, L.total - n_wa, st, 0));
+    SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, st, 2));
+    return side_join(st, s1);
+  };
   for (int i = 0; i < nc; ++i) {
-    SGG_TRY(disc_step_core(a, w, fake_slot(w, m, i), it->gp_alpha_all + (long long)i * m.B, it->scalars_all + 4 * i, st));
-    if (it->comm) SGG_TRY(comm_allreduce(it->comm, a->d_grad, param_layout(false, dd).total, st));
-    SGG_TRY(adam_dev(1, dd, const_cast<float*>(a->d_theta), a->d_grad, it->d_m, it->d_v, const_cast<void*>(a->d_shadow), hp,
-                     iter, nc, i + 1, st));
+    cudaStream_t s1 = st;
+    SGG_TRY(disc_step_core(a, w, fake_slot(w, m, i), it->gp_alpha_all + (long long)i * m.B, it->scalars_all + 4 * i, st, &s1));
+    SGG_TRY(optimise(1, const_cast<float*>(a->d_theta), a->d_grad, it->d_m, it->d_v, const_cast<void*>(a->d_shadow), nc, i + 1, s1));
   }
   // ---- generator step (its own forward keeps the activations the reverse pass needs)
-  SGG_TRY(gen_step_core(a, w, it->noise_all + (long long)nc * m.B * m.C, fresh, it->scalars_all + 4 * nc, st));
-  if (it->comm) SGG_TRY(comm_allreduce(it->comm, a->g_grad, param_layout(true, dd).total, st));
-  SGG_TRY(adam_dev(0, dd, const_cast<float*>(a->g_theta), a->g_grad, it->g_m, it->g_v, const_cast<void*>(a->g_shadow), hp,
-                   iter, 1, 1, st));
+  {
+    cudaStream_t s1 = st;
+    SGG_TRY(gen_step_core(a, w, it->noise_all + (long long)nc * m.B * m.C, fresh, it->scalars_all + 4 * nc, st, &s1));
+    SGG_TRY(optimise(0, const_cast<float*>(a->g_theta), a->g_grad, it->g_m, it->g_v, const_cast<void*>(a->g_shadow), 1, 1, s1));
+  }
   return bump_counter(reinterpret_cast<long long*>(it->counters), st);
 }
 

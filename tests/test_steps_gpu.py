@@ -112,7 +112,7 @@ def test_steps_can_interleave_on_one_workspace():
     g1 = eng.g.grad.clone()
     eng.disc_step(); torch.cuda.synchronize()
     assert ((eng.d.grad - d1).norm() / d1.norm()).item() < 1e-4   # split-K / scatter atomics reorder fp32 sums
-    assert torch.allclose(eng.scalars[1:3], s1[1:3], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(eng.scalars[1:3], s1[1:3], rtol=1e-4, atol=1e-6)   # split-K atomics: run-to-run fp32 summation order
     eng.gen_step(); torch.cuda.synchronize()
     assert ((eng.g.grad - g1).norm() / g1.norm()).item() < 1e-4
 
