@@ -41,6 +41,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-profile", action="store_true", help="only run the roofline kernel micro-timing")
+    ap.add_argument("--workload", default="train", choices=["train", "sample"],
+                    help="train = BASELINE configs[1] (default, the headline metric); sample = configs[4] generator-only "
+                         "inference decoding (defaults: --batch 8192 --timesteps 30 --vocab 5000)")
+    ap.add_argument("--mode", default="greedy", choices=["greedy", "gumbel"], help="--workload sample: decoding mode")
+    ap.add_argument("--chunk", type=int, default=0, help="--workload sample: images per pass (0 = library default)")
     return ap.parse_args()
 
 
@@ -367,8 +372,92 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_sample_arm(args):
+    """BASELINE configs[4]: generator-only inference (forward + train:270 argmax / Gumbel-max decoding), images/s.
+    Not the headline metric: a separate line for the sampling path (sgg_gen_sample)."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sgg_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from sgg_b200._lib import lib
+    from sgg_b200.params import GEN, ParamBucket, make_dims
+    from sgg_b200.sampling import GeneratorSampler
+    import ctypes as C
+    B, T, V, R = args.batch, args.timesteps, args.vocab, 196
+    bucket = ParamBucket(GEN, make_dims(B, T, V, R))
+    bucket.init_reference(1)
+    smp = GeneratorSampler(bucket, B, T, R, chunk=args.chunk, seed=rank)
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    anns = [torch.randn(B, R, 512, generator=g, device="cuda").to(torch.bfloat16) for _ in range(2)]   # 2 x 1.6 GB >> L2
+    L = lib()
+    L.sgg_launch_count.restype = C.c_int64
+    for i in range(max(3, args.warmup)):
+        smp.sample(anns[i % 2], args.mode)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = L.sgg_launch_count()
+    e0.record(st)
+    for i in range(args.steps):
+        smp.sample(anns[i % 2], args.mode)
+    e1.record(st)
+    torch.cuda.synchronize()
+    launches = L.sgg_launch_count() - n0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    secs = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = t[0].item()
+    if rank == 0:
+        pk = peaks()
+        ann_bytes = (T + 1) * B * R * 512 * 2          # T attention steps + the projection pass (SURVEY 8d, config 5)
+        flops = B * (2.0 * R * 512 * R * 2 + T * (2.0 * 512 * R * 3 + 2.0 * 1536 * 2048 * 3 + 2.0 * 512 * V * 3))
+        line = {
+            "metric": "generator sampling images/sec (forward + decoding)", "value": B * world * args.steps / secs, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 tensor-core operands (hi/lo split), fp32 accumulate", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: generator-only {args.mode} decoding, batch {B}/GPU, {T // 3} triples (T={T}), "
+                                   f"vocab {V}, chunk {smp.chunk or 1024}", "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "two alternating 1.6 GB annotation tensors (>> 126 MB L2)"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "whole call (annotation re-reads dominate)", "achieved": ann_bytes * args.steps / secs / 1e9,
+                         "peak": pk["hbm"], "unit": "GB/s", "frac": ann_bytes * args.steps / secs / 1e9 / pk["hbm"], "traffic": None,
+                         "peak_source": pk["source"], "tensor_tflops_3product": flops * args.steps / secs / 1e12},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if args.workload == "sample":
+        if args.batch == 256 and args.timesteps == 3 and args.vocab == 2000:
+            args.batch, args.timesteps, args.vocab = 8192, 30, 5000
+        if args.steps == 100:
+            args.steps = 10
+        return run_sample_arm(args)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -86,6 +86,12 @@ typedef struct sgg_gemm_desc {
    * of C / Chl (e.g. [t][stream][b] rows -> [stream][t][b]). */
   int32_t out_d0, out_d1;
   int64_t out_s0, out_s1;
+  /* optional sampling epilogue (train:270 tf.argmax over the vocabulary; Gumbel-max sampling as an extension):
+   * argmax_keys[row * argmax_stride] (device uint64, zero-filled by the caller) receives, by 64-bit atomic max over
+   * the n-tiles, (orderable bits of max_n D[row,n] (+ Gumbel noise)) << 32 | (0xFFFFFFFF - argmax column); the lowest
+   * column wins ties.  gumbel != 0 adds g = -log(-log u), u = Philox4x32-10(gumbel_seed; gumbel_offset + row, n). */
+  uint64_t* argmax_keys; int64_t argmax_stride;
+  int32_t gumbel; uint64_t gumbel_seed, gumbel_offset;
 } sgg_gemm_desc_t;
 
 int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream);
@@ -178,6 +184,29 @@ int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream);
 int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------
+ * Generator sampling (inference): gen:74-91 forward only, then the reference's test-time decoding
+ * (train:270: tf.argmax(generator_output, axis=2)) or, as an extension, Gumbel-max sampling
+ * token ~ softmax(logits).  The batch is processed in chunks of `chunk` images whose buffers are
+ * reused every timestep; the logits only reach HBM when logits_out is given.
+ * -------------------------------------------------------------------------------------- */
+#define SGG_SAMPLE_GREEDY 0
+#define SGG_SAMPLE_GUMBEL 1
+typedef struct sgg_sample_args {
+  sgg_dims_t dims;            /* B = images of this call; S and E are ignored */
+  const float* g_theta; const void* g_shadow;
+  const void* ann_g;          /* [B,R,C] bf16 annotations */
+  const float* noise;         /* [B,C] N(0,1) (gen:81), or NULL: drawn on the device from (seed, offset) */
+  int32_t mode;               /* SGG_SAMPLE_GREEDY | SGG_SAMPLE_GUMBEL */
+  int32_t chunk;              /* images per pass (0 = default 1024) */
+  uint64_t seed, offset;      /* Philox key / position of the noise and Gumbel draws */
+  void* workspace; int64_t workspace_bytes;   /* sgg_sample_workspace_bytes(dims, chunk) */
+  int32_t* tokens_out;        /* [B,T] token ids */
+  float* logits_out;          /* optional [B,T,V] fp32 raw logits */
+} sgg_sample_args_t;
+int64_t sgg_sample_workspace_bytes(const sgg_dims_t* d, int32_t chunk);
+int sgg_gen_sample(const sgg_sample_args_t* a, sgg_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------
  * Data-parallel exchange (the reference is single-GPU).  One process per GPU; the
  * batch is sharded over ranks and every loss is normalised by the GLOBAL batch (args.world), so
  * the only exchange is a sum of the flat gradient bucket before each optimiser step.  The
@@ -201,6 +230,22 @@ int sgg_comm_allreduce_sum(void* comm, float* buf, int64_t n, sgg_stream_t strea
  * the RNG position and the Adam step numbers lives in `counters`, so a stream capture of one
  * call can be replayed as a CUDA graph.
  * -------------------------------------------------------------------------------------- */
+/* Row-sharded attention projection (world > 1, optional but recommended).  Data parallelism replicates every tensor
+ * except the annotation rows W_a of attention_perceptron/kernel (85 % of the parameters): rank r owns the contraction
+ * indices [r*Ks, (r+1)*Ks), Ks = R*C/world, of  P = flat(a) W_a  for the GLOBAL batch.  Per iteration the ranks exchange
+ * annotation column slabs (all-to-all); per optimiser step the block needs a reduce-scatter of the partial projections
+ * [B*world, R] and an all-gather of P_bar instead of an all-reduce of its 79 MB gradient, and its HBM traffic per GPU
+ * (K1 operand, dW_a, Adam) drops by 1/world.  Only rows [r*Ks, (r+1)*Ks) of W_a (theta, m, v, shadow) are maintained
+ * on rank r; gather them before reading the full tensor.  Results equal the replicated scheme up to fp32 summation
+ * order. */
+typedef struct sgg_wa_shard {
+  int32_t enabled;
+  void* slab_g; void* slab_d;            /* device bf16 [B*world, Ks] each: sgg_wa_shard_slab_elems() elements */
+  void* scratch; int64_t scratch_bytes;  /* sgg_wa_shard_scratch_bytes() */
+} sgg_wa_shard_t;
+int64_t sgg_wa_shard_scratch_bytes(const sgg_dims_t* d, int32_t world);
+int64_t sgg_wa_shard_slab_elems(const sgg_dims_t* d, int32_t world);
+
 typedef struct sgg_iter_args {
   sgg_step_args_t step;
   int32_t critic_iters;              /* train:30 CRITIC_ITERS; <= step.dims.S */
@@ -213,6 +258,7 @@ typedef struct sgg_iter_args {
   float* gp_alpha_all;               /* device [critic_iters, B] scratch */
   float* scalars_all;                /* device [(critic_iters+1), 4]: per-step {-, w_disc, gp, gen_cost} */
   void* comm;                        /* sgg_comm_init handle, or NULL for a single GPU */
+  sgg_wa_shard_t shard;              /* row-sharded attention projection (ignored unless comm != NULL and world > 1) */
 } sgg_iter_args_t;
 
 int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t stream);

@@ -34,6 +34,8 @@ class GemmDesc(C.Structure):
         ("block_n", C.c_int32),
         ("splits", C.c_int32),
         ("out_d0", C.c_int32), ("out_d1", C.c_int32), ("out_s0", C.c_int64), ("out_s1", C.c_int64),
+        ("argmax_keys", C.c_void_p), ("argmax_stride", C.c_int64),
+        ("gumbel", C.c_int32), ("gumbel_seed", C.c_uint64), ("gumbel_offset", C.c_uint64),
     ]
 
 
@@ -86,6 +88,11 @@ class StepArgs(C.Structure):
     ]
 
 
+class WaShard(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("slab_g", C.c_void_p), ("slab_d", C.c_void_p),
+                ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
+
+
 class IterArgs(C.Structure):
     _fields_ = [
         ("step", StepArgs), ("critic_iters", C.c_int32),
@@ -93,11 +100,22 @@ class IterArgs(C.Structure):
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("seed", C.c_uint64), ("counters", C.c_void_p),
         ("noise_all", C.c_void_p), ("gp_alpha_all", C.c_void_p), ("scalars_all", C.c_void_p),
-        ("comm", C.c_void_p),
+        ("comm", C.c_void_p), ("shard", WaShard),
+    ]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [
+        ("dims", Dims),
+        ("g_theta", C.c_void_p), ("g_shadow", C.c_void_p), ("ann_g", C.c_void_p), ("noise", C.c_void_p),
+        ("mode", C.c_int32), ("chunk", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("tokens_out", C.c_void_p), ("logits_out", C.c_void_p),
     ]
 
 
 FLAG_REFRESH_GEN_PROJ = 1
+SAMPLE_GREEDY, SAMPLE_GUMBEL = 0, 1
 
 # every symbol include/sgg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -105,4 +123,5 @@ EXPORTS = [
     "sgg_rng_fill_normal", "sgg_rng_fill_uniform", "sgg_workspace_bytes", "sgg_gen_forward",
     "sgg_disc_forward", "sgg_disc_step", "sgg_gen_step", "sgg_ws_lookup", "sgg_train_iteration",
     "sgg_comm_unique_id", "sgg_comm_init", "sgg_comm_destroy", "sgg_comm_allreduce_sum",
+    "sgg_sample_workspace_bytes", "sgg_gen_sample", "sgg_wa_shard_scratch_bytes", "sgg_wa_shard_slab_elems",
 ]

@@ -47,3 +47,18 @@ class Generator(AttentionNet):
         logits = e.gen_forward().clone()
         self.alpha = e.ws_view("g.EA", (e.T, B, 256), torch.float32)[e.T - 1, :, :R].clone()
         return logits
+
+    def sample(self, images, mode: str = "greedy", noise: Optional[torch.Tensor] = None, chunk: int = 0):
+        """Test-time decoding of train:269-270 (``tf.argmax(generator_output, axis=2)``) without materialising the
+        logits; ``mode="gumbel"`` draws token ~ softmax(logits) instead (extension).  Returns tokens [B, T] int32."""
+        from ..sampling import GeneratorSampler
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ann = as_annotations(images, dev)
+        B, R = ann.shape[0], ann.numel() // (ann.shape[0] * 512)
+        e = self._ensure_engine(B, R)
+        key = (B, R, chunk)
+        if getattr(self, "_sampler_key", None) != key:
+            self._sampler = GeneratorSampler(e.g, B, self.n_steps, R, chunk=chunk)
+            self._sampler_key = key
+        self._set_context(ann)
+        return self._sampler.sample(ann.view(B, R, 512), mode=mode, noise=noise).clone()

@@ -13,7 +13,7 @@ namespace sgg {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[SGG_COMM_ID_BYTES]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat32 = 7, ncclSum = 0 };
+enum { ncclInt8 = 0, ncclFloat32 = 7, ncclSum = 0 };
 
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
@@ -21,6 +21,12 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*);   // NCCL >= 2.18 (optional)
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
   const char* (*GetErrorString)(ncclResult_t);
   bool ok;
 };
@@ -39,7 +45,14 @@ static NcclApi* nccl() {
       api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
       api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
       api.CommSplit = (decltype(api.CommSplit))dlsym(h, "ncclCommSplit");
-      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+      api.ReduceScatter = (decltype(api.ReduceScatter))dlsym(h, "ncclReduceScatter");
+      api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+      api.Send = (decltype(api.Send))dlsym(h, "ncclSend");
+      api.Recv = (decltype(api.Recv))dlsym(h, "ncclRecv");
+      api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString &&
+               api.ReduceScatter && api.AllGather && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
     }
   }
   return api.ok ? &api : nullptr;
@@ -73,6 +86,47 @@ int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st, int lan
   if (c->world == 1 || n == 0) return 0;
   SGG_CHECK(lane == 0 || c->side, "comm_allreduce: no side communicator");
   SGG_NCCL(nccl()->AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, lane == 0 ? c->nccl : c->side, st));
+  return 0;
+}
+
+int comm_rank(void* comm) { return comm ? reinterpret_cast<Comm*>(comm)->rank : 0; }
+int comm_world(void* comm) { return comm ? reinterpret_cast<Comm*>(comm)->world : 1; }
+
+// out[n_per_rank] = sum over ranks of their in[rank * n_per_rank ...]
+int comm_reduce_scatter(void* comm, const float* in, float* out, long long n_per_rank, cudaStream_t st, int lane) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  SGG_CHECK(c && in && out && n_per_rank >= 0, "comm_reduce_scatter: bad argument");
+  SGG_CHECK(lane == 0 || c->side, "comm_reduce_scatter: no side communicator");
+  SGG_NCCL(nccl()->ReduceScatter(in, out, (size_t)n_per_rank, ncclFloat32, ncclSum, lane == 0 ? c->nccl : c->side, st));
+  return 0;
+}
+// out[rank * n_per_rank ...] = every rank's in[n_per_rank]
+int comm_all_gather(void* comm, const float* in, float* out, long long n_per_rank, cudaStream_t st, int lane) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  SGG_CHECK(c && in && out && n_per_rank >= 0, "comm_all_gather: bad argument");
+  SGG_CHECK(lane == 0 || c->side, "comm_all_gather: no side communicator");
+  SGG_NCCL(nccl()->AllGather(in, out, (size_t)n_per_rank, ncclFloat32, lane == 0 ? c->nccl : c->side, st));
+  return 0;
+}
+// Block p (bytes_per_rank bytes) of `send` goes to rank p; block p of `recv` comes from rank p.
+int comm_all_to_all(void* comm, const void* send, void* recv, long long bytes_per_rank, cudaStream_t st, int lane) {
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  SGG_CHECK(c && send && recv && bytes_per_rank >= 0, "comm_all_to_all: bad argument");
+  SGG_CHECK(lane == 0 || c->side, "comm_all_to_all: no side communicator");
+  ncclComm_t nc = lane == 0 ? c->nccl : c->side;
+  SGG_NCCL(nccl()->GroupStart());
+  for (int p = 0; p < c->world; ++p) {
+    const char* sp = reinterpret_cast<const char*>(send) + (long long)p * bytes_per_rank;
+    char* rp = reinterpret_cast<char*>(recv) + (long long)p * bytes_per_rank;
+    ncclResult_t r1 = nccl()->Send(sp, (size_t)bytes_per_rank, ncclInt8, p, nc, st);
+    ncclResult_t r2 = nccl()->Recv(rp, (size_t)bytes_per_rank, ncclInt8, p, nc, st);
+    if (r1 != 0 || r2 != 0) {
+      nccl()->GroupEnd();
+      set_error("ncclSend/ncclRecv failed: %s", nccl()->GetErrorString(r1 != 0 ? r1 : r2));
+      return -3;
+    }
+  }
+  SGG_NCCL(nccl()->GroupEnd());
   return 0;
 }
 

@@ -29,6 +29,10 @@ struct GemmKParams {
   const float* addm; long long ld_addm; int add_mod;
   float alpha;
   int rm_d0, rm_d1; long long rm_s0, rm_s1;   // output row permutation (rm_d0 == 0: identity)
+  // sampling epilogue (train:270 argmax / Gumbel-max): per output row the running maximum of v[n] (+ Gumbel noise) and
+  // its column, packed as (orderable float bits << 32) | ~column and merged across n-tiles with a 64-bit atomicMax
+  unsigned long long* amax; long long amax_stride;
+  int gumbel; unsigned long long gseed, goff;
 };
 
 constexpr int GEMM_MAX_STAGES = 8;
@@ -184,6 +188,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    float best_v = -INFINITY;
+    int best_c = 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = n0 + c * 32;
@@ -205,6 +211,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (full || col0 + j < p.N) v[j] += __ldg(addrow + col0 + j);
+      }
+      if (p.amax) {
+        float g[32];
+        if (p.gumbel) {   // g = -log(-log u), u = Philox(seed; row, column quad): the draw of element (row, n) is fixed
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const unsigned long long ctr = p.goff + (unsigned long long)orow;
+            const uint4 rr = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)((col0 + j) >> 2), 0x9E37u),
+                                           make_uint2((uint32_t)p.gseed, (uint32_t)(p.gseed >> 32)));
+            g[j] = -__logf(-__logf(u01(rr.x))); g[j + 1] = -__logf(-__logf(u01(rr.y)));
+            g[j + 2] = -__logf(-__logf(u01(rr.z))); g[j + 3] = -__logf(-__logf(u01(rr.w)));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (full || col0 + j < p.N) {
+            const float s = p.gumbel ? v[j] + g[j] : v[j];
+            if (s > best_v) { best_v = s; best_c = col0 + j; }   // strict: the lowest column wins a tie (tf.argmax)
+          }
+        }
       }
       if (p.C) {
         float* crow = p.C + orow * p.ldc + col0;
@@ -261,6 +287,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
+    if (p.amax && row_ok && n0 < p.N) {
+      uint32_t b = __float_as_uint(best_v);
+      b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+      atomicMax(p.amax + orow * p.amax_stride, ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)best_c));
+    }
    }
   }
   tc_fence_before();
@@ -307,7 +338,7 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   // whatever the output already holds).
   const int tm = (d.M + BM - 1) / BM;
   const int nprod = kp.nA + kp.nB - 1;
-  const bool can_split = d.C && !d.Chl;
+  const bool can_split = d.C && !d.Chl && !d.argmax_keys;
   int bn = d.block_n, splits = d.splits > 1 ? d.splits : 1;
   // B-heavy contractions (single A part, hi/lo B, N <= 256: the two W_a GEMMs): 256-row CTAs with two accumulators, so
   // the wide B tile enters shared memory once per 256 output rows.
@@ -381,7 +412,7 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
   SGG_CHECK(d.A && d.B, "sgg_gemm: null operand");
   SGG_CHECK(d.M > 0 && d.N > 0, "sgg_gemm: bad M/N (%d, %d)", d.M, d.N);
   SGG_CHECK(d.nseg >= 1 && d.nseg <= SGG_GEMM_MAX_SEG, "sgg_gemm: nseg=%d out of range", d.nseg);
-  SGG_CHECK(d.C || d.Chl, "sgg_gemm: no output");
+  SGG_CHECK(d.C || d.Chl || d.argmax_keys, "sgg_gemm: no output");
   GemmKParams kp{};
   kp.M = d.M;
   kp.N = d.N;
@@ -391,6 +422,9 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
   kp.addm = d.addm; kp.ld_addm = d.ld_addm; kp.add_mod = d.add_mod > 0 ? d.add_mod : 1;
   kp.alpha = d.alpha;
   kp.rm_d0 = d.out_d0; kp.rm_d1 = d.out_d1 > 0 ? d.out_d1 : 1; kp.rm_s0 = d.out_s0; kp.rm_s1 = d.out_s1;
+  kp.amax = reinterpret_cast<unsigned long long*>(d.argmax_keys); kp.amax_stride = d.argmax_stride > 0 ? d.argmax_stride : 1;
+  kp.gumbel = d.gumbel; kp.gseed = d.gumbel_seed; kp.goff = d.gumbel_offset;
+  SGG_CHECK(!d.argmax_keys || d.splits <= 1, "sgg_gemm: the argmax epilogue cannot be combined with split-K");
   for (int s = 0; s < d.nseg; ++s)
     SGG_CHECK(d.seg_klen[s] > 0, "sgg_gemm: segment %d has length %d", s, d.seg_klen[s]);
   // ---- recognise the hi/lo product pattern: every segment pairs A0 or B0 of segment 0 with at most one other part
@@ -416,7 +450,7 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
     return gemm_fused(d, kp, stream);
   }
   // ---- general segment lists: one accumulate-launch per segment
-  SGG_CHECK(d.C && !d.Chl && d.out_d0 == 0, "sgg_gemm: this segment pattern needs the plain fp32 output");
+  SGG_CHECK(d.C && !d.Chl && d.out_d0 == 0 && !d.argmax_keys, "sgg_gemm: this segment pattern needs the plain fp32 output");
   if (!d.atomic) SGG_CUDA(cudaMemset2DAsync(d.C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, stream));
   for (int s = 0; s < d.nseg; ++s) {
     sgg_gemm_desc_t e = d;

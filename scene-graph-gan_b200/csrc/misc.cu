@@ -400,19 +400,6 @@ int refresh_shadow(const float* theta, __nv_bfloat16* shadow, const AdamSeg& sg,
 }
 
 // ------------------------------------------------------------------------------------ Philox RNG
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
-  }
-  return ctr;
-}
-__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
-
 // mode 0: uniform [0,1) ; mode 1: standard normal (Box-Muller)
 __global__ void rng_fill_kernel(float* out, long long n, uint64_t seed, uint64_t offset, int mode,
                                 const long long* iter, uint64_t per_iter) {
@@ -454,6 +441,40 @@ __global__ void bump_counter_kernel(long long* ctr) {
 }
 int bump_counter(long long* ctr, cudaStream_t stream) {
   SGG_LAUNCH(bump_counter_kernel, 1, 1, 0, stream, ctr);
+  return 0;
+}
+
+// Row-sharded attention projection: columns [p*Ks, (p+1)*Ks) of flat(a) [B, K] -> send[p][b][0:Ks] (zero beyond K).
+__global__ void slab_pack_kernel(const uint4* a, uint4* send, int B, long long K8, long long Ks8, int world) {
+  pdl_trigger();
+  pdl_wait();
+  const long long n = (long long)world * B * Ks8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long j = i % Ks8, pb = i / Ks8;
+    const int b = (int)(pb % B), p = (int)(pb / B);
+    const long long col = p * Ks8 + j;
+    send[i] = col < K8 ? __ldg(a + (long long)b * K8 + col) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+int slab_pack(const __nv_bfloat16* a, __nv_bfloat16* send, int B, long long K, long long Ks, int world, cudaStream_t st) {
+  if ((K & 7) || (Ks & 7)) { set_error("slab_pack: K and Ks must be multiples of 8"); return -1; }
+  const long long n = (long long)world * B * (Ks / 8);
+  const int grid = (int)llmin((n + 255) / 256, 148 * 16);
+  SGG_LAUNCH(slab_pack_kernel, grid, 256, 0, st, reinterpret_cast<const uint4*>(a), reinterpret_cast<uint4*>(send), B, K / 8,
+             Ks / 8, world);
+  return 0;
+}
+
+// argmax keys of the decoder GEMM's sampling epilogue -> token ids (train:270)
+__global__ void decode_keys_kernel(const unsigned long long* keys, int32_t* tokens, long long n) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tokens[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+}
+int decode_keys(const unsigned long long* keys, int32_t* tokens, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  SGG_LAUNCH(decode_keys_kernel, (int)((n + 255) / 256), 256, 0, st, keys, tokens, n);
   return 0;
 }
 

@@ -24,6 +24,33 @@ struct AnnStaticScope {
   ~AnnStaticScope() { t_ann_static = prev; }
 };
 
+// ---------------------------------------------------------------------------- row-sharded attention projection
+// Data parallelism keeps every tensor replicated EXCEPT the annotation rows W_a of the attention kernel (85 % of the
+// parameters): with world > 1 rank r owns the contraction indices [r*Ks, (r+1)*Ks) of flat(a) W_a for the GLOBAL batch.
+// Once per iteration the ranks exchange annotation column slabs (all-to-all over NVLink); per step the only traffic of
+// this block is a reduce-scatter of the partial projections P [B_global, R] and an all-gather of P_bar -- instead of
+// an all-reduce of the 79 MB gradient -- and W_a's HBM traffic (K1 operand, dW_a, Adam) shrinks by 1/world per GPU.
+struct ShardCtx {
+  void* comm; int rank, world;
+  long long Ks;                                 // contraction indices per rank (multiple of 64)
+  const __nv_bfloat16* slab_g; const __nv_bfloat16* slab_d;   // [B*world, Ks]
+  __nv_bfloat16* send;                          // [world][B][Ks] all-to-all staging
+  float* Ppart; float* PBall; __nv_bfloat16* PBHall;          // [B*world, RP] / [B*world, 2RP]
+};
+static thread_local const ShardCtx* t_shard = nullptr;
+struct ShardScope {
+  const ShardCtx* prev;
+  explicit ShardScope(const ShardCtx* c) : prev(t_shard) { t_shard = c; }
+  ~ShardScope() { t_shard = prev; }
+};
+int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st, int lane);
+int comm_reduce_scatter(void* comm, const float* in, float* out, long long n_per_rank, cudaStream_t st, int lane);
+int comm_all_gather(void* comm, const float* in, float* out, long long n_per_rank, cudaStream_t st, int lane);
+int comm_all_to_all(void* comm, const void* send, void* recv, long long bytes_per_rank, cudaStream_t st, int lane);
+bool comm_has_side_lane(void* comm);
+int comm_rank(void* comm);
+int comm_world(void* comm);
+
 // ---------------------------------------------------------------------------- side stream (fork / join)
 // The W_a chain of an optimiser step -- dW_a GEMM (HBM-bound, 79 MB written), its all-reduce and the Adam update of
 // W_a (85 % of the parameters) -- is independent of the other weight-gradient GEMMs.  It runs on a library-owned side
@@ -217,6 +244,11 @@ struct Net {
   int NR;        // active rows per timestep (streams * B)
   int KXP, U, uoff, hoff;
   cudaStream_t st;
+  // Forward-only sampling keeps no history: state / input buffers alternate between two slots and the per-step
+  // scratch (scores, gate pre-activations) is reused, so the working set of a chunk stays in L2.
+  bool roll = false;
+  long long t2(int t) const { return roll ? (t & 1) : t; }
+  long long t1(int t) const { return roll ? 0 : t; }
   // strides (elements) between timesteps, for the active NR
   long long sX() const { return (long long)NR * 2 * KXP; }
   long long sCf() const { return (long long)NR * m.H; }
@@ -260,10 +292,22 @@ static sgg_gemm_desc_t gd_zero() { sgg_gemm_desc_t g; memset(&g, 0, sizeof(g)); 
 int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream);
 
 // K1: P = flat(a) W_a  (bias is added where P is consumed); hoisted out of the time loop (gen:14-15).
-static int net_attn_proj(const Net& n) {
+// lane: communicator lane (= stream) of the sharded variant's reduce-scatter.
+static int net_attn_proj(const Net& n, int lane = 0) {
   const Dm& m = n.m;
   sgg_gemm_desc_t g = gd_zero();
   const long long K = (long long)m.R * m.C;
+  if (t_shard) {   // partial projection of the GLOBAL batch over this rank's contraction slice, then reduce-scatter
+    const ShardCtx& sc = *t_shard;
+    const long long Bg = (long long)m.B * sc.world, k0 = sc.rank * sc.Ks;
+    g.A = n.gen ? sc.slab_g : sc.slab_d; g.a_rows = Bg; g.a_cols = sc.Ks; g.a_ld = sc.Ks; g.a_mn_major = 0;
+    g.B = n.sh + n.L.sWa; g.b_rows = 2LL * n.L.rWa; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
+    g.M = (int)Bg; g.N = m.R; g.nseg = 2; g.seg_klen[0] = g.seg_klen[1] = (int)sc.Ks;
+    g.seg_b_k[0] = (int)k0; g.seg_b_k[1] = n.L.rWa + (int)k0;
+    g.C = sc.Ppart; g.ldc = m.RP;
+    SGG_TRY(gemm(g, n.st));
+    return comm_reduce_scatter(sc.comm, sc.Ppart, n.w.P, (long long)m.B * m.RP, n.st, lane);
+  }
   g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 0;
   g.B = n.sh + n.L.sWa; g.b_rows = 2LL * n.L.rWa; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
   g.M = m.B; g.N = m.R; g.nseg = 2; g.seg_klen[0] = g.seg_klen[1] = (int)K; g.seg_b_k[1] = n.L.rWa;  // a is bf16-exact
@@ -284,14 +328,14 @@ static int net_init_state(const Net& n, int nblk) {
 static int net_scores(const Net& n, int t, int row0, int nrows, bool tangent) {
   const Dm& m = n.m;
   sgg_gemm_desc_t g = gd_zero();
-  g.A = n.w.CH + t * n.sCH() + (long long)row0 * 2 * m.H; g.a_rows = nrows; g.a_cols = 2 * m.H; g.a_ld = 2 * m.H;
+  g.A = n.w.CH + n.t2(t) * n.sCH() + (long long)row0 * 2 * m.H; g.a_rows = nrows; g.a_cols = 2 * m.H; g.a_ld = 2 * m.H;
   g.B = n.sh + n.L.sWh; g.b_rows = 2LL * n.L.rWh; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
   g.M = nrows; g.N = m.R;
   segs_act_weight(g, 0, m.H, n.L.rWh, true, m.H);
   if (tangent) {
     g.C = n.w.ED + (long long)t * m.B * m.RP; g.ldc = m.RP;
   } else {
-    g.C = n.w.EA + t * n.sEA() + (long long)row0 * m.RP; g.ldc = m.RP;
+    g.C = n.w.EA + n.t1(t) * n.sEA() + (long long)row0 * m.RP; g.ldc = m.RP;
     g.bias = n.theta + n.L.batt;
     g.addm = n.w.P; g.ld_addm = m.RP; g.add_mod = m.B;   // row0 is a multiple of B
   }
@@ -302,42 +346,45 @@ static int net_scores(const Net& n, int t, int row0, int nrows, bool tangent) {
 static int net_gates(const Net& n, int t, int row0, int nrows) {
   const Dm& m = n.m;
   sgg_gemm_desc_t g = gd_zero();
-  g.A = n.w.X + t * n.sX() + (long long)row0 * 2 * n.KXP; g.a_rows = nrows; g.a_cols = 2 * n.KXP; g.a_ld = 2 * n.KXP;
+  g.A = n.w.X + n.t2(t) * n.sX() + (long long)row0 * 2 * n.KXP; g.a_rows = nrows; g.a_cols = 2 * n.KXP; g.a_ld = 2 * n.KXP;
   g.B = n.sh + n.L.sK; g.b_rows = 2LL * n.L.rK; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 1;
   g.M = nrows; g.N = 4 * m.H;
   segs_act_weight(g, 0, n.KXP, n.L.rK, true, n.KXP);
-  g.C = n.w.Q + t * n.sQ() + (long long)row0 * 4 * m.H; g.ldc = 4 * m.H;
+  g.C = n.w.Q + n.t1(t) * n.sQ() + (long long)row0 * 4 * m.H; g.ldc = 4 * m.H;
   return gemm(g, n.st);
+}
+
+// One primal forward step (scores, attention, gates, cell) for stream blocks [0, nblk).
+static int net_forward_step(const Net& n, int t, int nblk) {
+  const Dm& m = n.m;
+  const int rows = nblk * m.B;
+  SGG_TRY(net_scores(n, t, 0, rows, false));
+  AttnFwdParams ap{};
+  ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk; ap.early_a = t_ann_static;
+  for (int v = 0; v < nblk; ++v) { ap.row_blk[v] = v; ap.e_blk[v] = v; }
+  ap.E = n.w.EA + n.t1(t) * n.sEA(); ap.ldE = m.RP;
+  ap.alpha_out = n.w.EA + n.t1(t) * n.sEA(); ap.ldA = m.RP;
+  ap.X = n.w.X + n.t2(t) * n.sX(); ap.ldX = 2 * n.KXP; ap.lo_off = n.KXP;
+  SGG_TRY(attn_fwd(ap, 0, n.st));
+  SGG_TRY(net_gates(n, t, 0, rows));
+  LstmFwdParams lp{};
+  lp.nrows = rows;
+  lp.Q = n.w.Q + n.t1(t) * n.sQ(); lp.ldQ = 4 * m.H;
+  lp.Cin = n.w.Cf + n.t2(t) * n.sCf();
+  lp.ln = n.ln();
+  lp.Cout = n.w.Cf + n.t2(t + 1) * n.sCf();
+  lp.CH = n.w.CH + n.t2(t + 1) * n.sCH(); lp.ldCH = 2 * m.H; lp.ch_lo = m.H;
+  lp.Xn = n.w.X + n.t2(t + 1) * n.sX(); lp.ldX = 2 * n.KXP; lp.x_lo = n.KXP; lp.hoff = n.hoff;
+  if (!n.gen) {
+    lp.wdec = n.theta + n.L.Wdec; lp.bdec = n.theta + n.L.bdec;
+    lp.Y = n.w.Y + t; lp.ldY = m.T;
+  }
+  return lstm_fwd(lp, n.st);
 }
 
 // Primal forward over T steps for stream blocks [0, nblk).  Needs: X[t] u-columns filled, P, state 0.
 static int net_forward(const Net& n, int nblk) {
-  const Dm& m = n.m;
-  const int rows = nblk * m.B;
-  for (int t = 0; t < m.T; ++t) {
-    SGG_TRY(net_scores(n, t, 0, rows, false));
-    AttnFwdParams ap{};
-    ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk; ap.early_a = t_ann_static;
-    for (int v = 0; v < nblk; ++v) { ap.row_blk[v] = v; ap.e_blk[v] = v; }
-    ap.E = n.w.EA + t * n.sEA(); ap.ldE = m.RP;
-    ap.alpha_out = n.w.EA + t * n.sEA(); ap.ldA = m.RP;
-    ap.X = n.w.X + t * n.sX(); ap.ldX = 2 * n.KXP; ap.lo_off = n.KXP;
-    SGG_TRY(attn_fwd(ap, 0, n.st));
-    SGG_TRY(net_gates(n, t, 0, rows));
-    LstmFwdParams lp{};
-    lp.nrows = rows;
-    lp.Q = n.w.Q + t * n.sQ(); lp.ldQ = 4 * m.H;
-    lp.Cin = n.w.Cf + t * n.sCf();
-    lp.ln = n.ln();
-    lp.Cout = n.w.Cf + (t + 1) * n.sCf();
-    lp.CH = n.w.CH + (t + 1) * n.sCH(); lp.ldCH = 2 * m.H; lp.ch_lo = m.H;
-    lp.Xn = n.w.X + (t + 1) * n.sX(); lp.ldX = 2 * n.KXP; lp.x_lo = n.KXP; lp.hoff = n.hoff;
-    if (!n.gen) {
-      lp.wdec = n.theta + n.L.Wdec; lp.bdec = n.theta + n.L.bdec;
-      lp.Y = n.w.Y + t; lp.ldY = m.T;
-    }
-    SGG_TRY(lstm_fwd(lp, n.st));
-  }
+  for (int t = 0; t < n.m.T; ++t) SGG_TRY(net_forward_step(n, t, nblk));
   return 0;
 }
 
@@ -457,18 +504,34 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
   {  // dW_a = flat(a)^T P_bar  [R*C, R]: on the side stream when the caller takes it over (it joins later)
     cudaStream_t s1 = n.st;
     if (side_out) { SGG_TRY(side_fork(n.st, &s1)); *side_out = s1; }
-    PackParams pk{};
-    pk.rows = m.B; pk.cols = m.R; pk.src = n.w.PB; pk.ld = m.RP;
-    pk.dst = n.w.PBH; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
-    SGG_TRY(pack_hl(pk, s1));
-    sgg_gemm_desc_t g = gd_zero();
+    const int lane = s1 != n.st ? 1 : 0;
     const long long K = (long long)m.R * m.C;
-    g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 1;
-    g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
-    g.M = (int)K; g.N = m.R; g.nseg = 2;
-    g.seg_klen[0] = g.seg_klen[1] = m.B; g.seg_b_mn[1] = m.RP;
-    g.C = n.grad + n.L.Watt; g.ldc = m.R; g.atomic = 0; g.splits = 1;
-    SGG_TRY(gemm(g, s1));
+    PackParams pk{};
+    sgg_gemm_desc_t g = gd_zero();
+    if (t_shard) {   // rows [k0, k0+Ks) of dW_a over the GLOBAL batch: all-gather P_bar, contract with this rank's slab
+      const ShardCtx& sc = *t_shard;
+      const long long Bg = (long long)m.B * sc.world, k0 = sc.rank * sc.Ks;
+      SGG_TRY(comm_all_gather(sc.comm, n.w.PB, sc.PBall, (long long)m.B * m.RP, s1, lane));
+      pk.rows = (int)Bg; pk.cols = m.R; pk.src = sc.PBall; pk.ld = m.RP;
+      pk.dst = sc.PBHall; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
+      SGG_TRY(pack_hl(pk, s1));
+      g.A = n.gen ? sc.slab_g : sc.slab_d; g.a_rows = Bg; g.a_cols = sc.Ks; g.a_ld = sc.Ks; g.a_mn_major = 1;
+      g.B = sc.PBHall; g.b_rows = Bg; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
+      g.M = (int)sc.Ks; g.N = m.R; g.nseg = 2;
+      g.seg_klen[0] = g.seg_klen[1] = (int)Bg; g.seg_b_mn[1] = m.RP;
+      g.C = n.grad + n.L.Watt + k0 * m.R; g.ldc = m.R; g.atomic = 0; g.splits = 0;
+      SGG_TRY(gemm(g, s1));
+    } else {
+      pk.rows = m.B; pk.cols = m.R; pk.src = n.w.PB; pk.ld = m.RP;
+      pk.dst = n.w.PBH; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
+      SGG_TRY(pack_hl(pk, s1));
+      g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 1;
+      g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
+      g.M = (int)K; g.N = m.R; g.nseg = 2;
+      g.seg_klen[0] = g.seg_klen[1] = m.B; g.seg_b_mn[1] = m.RP;
+      g.C = n.grad + n.L.Watt; g.ldc = m.R; g.atomic = 0; g.splits = 1;
+      SGG_TRY(gemm(g, s1));
+    }
   }
   {  // dK = X^T QB   [KX, 4H], three hi/lo products
     sgg_gemm_desc_t g = gd_zero();
@@ -637,15 +700,11 @@ extern "C" int sgg_refresh_shadow(int net, const sgg_dims_t* d, const float* the
 }
 
 struct AdamHyper { float lr, b1, b2, eps; };
-namespace sgg {
-int comm_allreduce(void* comm, float* buf, long long n, cudaStream_t st, int lane = 0);  // comm.cu
-bool comm_has_side_lane(void* comm);
-}
 // Adam with the step number taken from the device counter: step = iter[0] * step_mul + step_add.
 // which: 0 = every tensor, 1 = only W_a (the annotation rows of the attention kernel), 2 = everything but W_a
 static int adam_dev(int net, const sgg_dims_t& d, float* theta, const float* grad, float* mm, float* vv, void* shadow,
                     const AdamHyper& h, const long long* iter, long long step_mul, long long step_add, cudaStream_t st,
-                    int which = 0) {
+                    int which = 0, long long wa_row0 = 0, long long wa_rows = -1) {
   const ParamLayout L = param_layout(net == 0, d);
   AdamParams p{};
   p.theta = theta; p.grad = grad; p.m = mm; p.v = vv; p.shadow = (__nv_bfloat16*)shadow;
@@ -654,6 +713,11 @@ static int adam_dev(int net, const sgg_dims_t& d, float* theta, const float* gra
   p.nseg = fill_adam_segs(L, p.seg);
   if (which == 1) {
     p.nseg = 1;                                   // segment 0 is W_a (fill_adam_segs)
+    if (wa_rows >= 0) {                           // only the rows this rank owns (row-sharded projection)
+      p.seg[0].off += wa_row0 * p.seg[0].cols;
+      p.seg[0].sh_off += wa_row0 * p.seg[0].pitch;
+      p.seg[0].n = wa_rows * p.seg[0].cols;
+    }
   } else if (which == 2) {
     for (int i = 1; i < p.nseg; ++i) p.seg[i - 1] = p.seg[i];
     p.nseg -= 1;
@@ -919,6 +983,48 @@ extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
   return gen_step_core(a, w, a->noise, (a->flags & SGG_FLAG_REFRESH_GEN_PROJ) != 0, a->scalars, (cudaStream_t)stream);
 }
 
+// ============================================================================ row-sharded projection: buffers
+namespace sgg { int slab_pack(const __nv_bfloat16* a, __nv_bfloat16* send, int B, long long K, long long Ks, int world, cudaStream_t st); }
+struct ShardScratch { __nv_bfloat16* send; float* Ppart; float* PBall; __nv_bfloat16* PBHall; long long bytes; };
+static long long shard_ks(const sgg_dims_t& d, int world) {
+  const long long kb = ((long long)d.R * d.C + 63) / 64;
+  return (kb + world - 1) / world * 64;
+}
+static ShardScratch shard_scratch_layout(const sgg_dims_t& d, int world, void* base) {
+  const Dm m = derive(d);
+  const long long Ks = shard_ks(d, world), Bg = (long long)m.B * world;
+  ShardScratch s{};
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  long long o = 0;
+  auto take = [&](long long bytes) { uint8_t* r = p ? p + o : nullptr; o = rup(o + bytes, 256); return (void*)r; };
+  s.send = (__nv_bfloat16*)take(2LL * world * m.B * Ks * 2);   // generator and discriminator staging
+  s.Ppart = (float*)take(Bg * m.RP * 4);
+  s.PBall = (float*)take(Bg * m.RP * 4);
+  s.PBHall = (__nv_bfloat16*)take(Bg * 2 * m.RP * 2);
+  s.bytes = o;
+  return s;
+}
+static int shard_ctx(const sgg_dims_t& d, int world, int rank, void* comm, const sgg_wa_shard_t& sh, ShardCtx* out) {
+  SGG_CHECK(((long long)d.R * d.C / 64) % world == 0, "row-sharded projection: R*C/64 = %lld is not divisible by world = %d",
+            (long long)d.R * d.C / 64, world);
+  SGG_CHECK(sh.slab_g && sh.slab_d && sh.scratch, "row-sharded projection: missing slab / scratch buffers");
+  const ShardScratch s = shard_scratch_layout(d, world, sh.scratch);
+  SGG_CHECK(sh.scratch_bytes >= s.bytes, "row-sharded projection: scratch too small (%lld < %lld)", (long long)sh.scratch_bytes,
+            (long long)s.bytes);
+  out->comm = comm; out->rank = rank; out->world = world; out->Ks = shard_ks(d, world);
+  out->slab_g = (const __nv_bfloat16*)sh.slab_g; out->slab_d = (const __nv_bfloat16*)sh.slab_d;
+  out->send = s.send; out->Ppart = s.Ppart; out->PBall = s.PBall; out->PBHall = s.PBHall;
+  return 0;
+}
+extern "C" int64_t sgg_wa_shard_scratch_bytes(const sgg_dims_t* d, int32_t world) {
+  if (!d || check_dims(*d) != 0 || world < 1) return -1;
+  return shard_scratch_layout(*d, world, nullptr).bytes;
+}
+extern "C" int64_t sgg_wa_shard_slab_elems(const sgg_dims_t* d, int32_t world) {
+  if (!d || check_dims(*d) != 0 || world < 1) return -1;
+  return (int64_t)d->B * world * shard_ks(*d, world);
+}
+
 // ============================================================================ one training iteration
 // train:362-368 on one batch (train:185-187): critic_iters x {D step, Adam(D)} then {G step, Adam(G)}, with
 // fresh noise / interpolation coefficients per step drawn on the device.  The generator is constant during the
@@ -942,6 +1048,26 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
   const Dm m = derive(dd);
   const int nc = it->critic_iters;
   const long long* iter = reinterpret_cast<const long long*>(it->counters);
+  // ---- row-sharded attention projection (world > 1): exchange the annotation column slabs of this batch
+  ShardCtx sc{};
+  const bool shard = it->comm && a->world > 1 && it->shard.enabled;
+  if (shard) {
+    SGG_CHECK(comm_world(it->comm) == a->world, "sgg_train_iteration: communicator has %d ranks, step.world = %d",
+              comm_world(it->comm), a->world);
+    SGG_TRY(shard_ctx(dd, a->world, comm_rank(it->comm), it->comm, it->shard, &sc));
+  }
+  ShardScope shard_scope(shard ? &sc : nullptr);
+  cudaStream_t s_ex = st;
+  if (shard) {
+    const long long per = (long long)m.B * sc.Ks;
+    SGG_TRY(slab_pack((const __nv_bfloat16*)a->ann_g, sc.send, m.B, (long long)m.R * m.C, sc.Ks, a->world, st));
+    SGG_TRY(comm_all_to_all(it->comm, sc.send, const_cast<__nv_bfloat16*>(sc.slab_g), per * 2, st, 0));
+    // the discriminator's slab is first needed by the first critic step: exchange it beside the generator forwards
+    if (comm_has_side_lane(it->comm)) SGG_TRY(side_fork(st, &s_ex));
+    __nv_bfloat16* send_d = sc.send + (long long)a->world * per;
+    SGG_TRY(slab_pack((const __nv_bfloat16*)a->ann_d, send_d, m.B, (long long)m.R * m.C, sc.Ks, a->world, s_ex));
+    SGG_TRY(comm_all_to_all(it->comm, send_d, const_cast<__nv_bfloat16*>(sc.slab_d), per * 2, s_ex, s_ex != st ? 1 : 0));
+  }
   // ---- fresh randomness for every step of this iteration (Philox position = f(iteration counter))
   const long long n_noise = (long long)(nc + 1) * m.B * m.C, n_alpha = (long long)nc * m.B;
   const uint64_t per_iter = (uint64_t)((n_noise + 3) / 4 + (n_alpha + 3) / 4);
@@ -955,6 +1081,7 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
     SGG_TRY(gen_forward(g, w, it->noise_all + (long long)s0 * m.B * m.C, ns, s0, fresh, nullptr));
     fresh = false;
   }
+  if (shard) SGG_TRY(side_join(st, s_ex));
   // ---- critic steps
   AdamHyper hp{it->lr, it->beta1, it->beta2, it->eps};
   // Each optimiser step is split in two independent chains that meet again before the next step:
@@ -966,24 +1093,134 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
     const ParamLayout L = param_layout(net == 0, dd);
     const long long n_wa = (long long)m.R * m.C * m.R;
     if (s1 != st && !side_ok) { SGG_TRY(side_join(st, s1)); s1 = st; }
-    if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad, n_wa, s1, s1 != st ? 1 : 0));
-    SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1));
+    if (shard) {   // this rank's rows of dW_a are already sums over the global batch: no exchange, 1/world of the update
+      SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1, sc.rank * sc.Ks, sc.Ks));
+    } else {
+      if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad, n_wa, s1, s1 != st ? 1 : 0));
+      SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1));
+    }
     if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad + n_wa, L.total - n_wa, st, 0));
     SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, st, 2));
     return side_join(st, s1);
   };
+  const bool use_side = !shard || side_ok;   // sharded: the side chain issues collectives, which need their own lane
   for (int i = 0; i < nc; ++i) {
     cudaStream_t s1 = st;
-    SGG_TRY(disc_step_core(a, w, fake_slot(w, m, i), it->gp_alpha_all + (long long)i * m.B, it->scalars_all + 4 * i, st, &s1));
+    SGG_TRY(disc_step_core(a, w, fake_slot(w, m, i), it->gp_alpha_all + (long long)i * m.B, it->scalars_all + 4 * i, st,
+                           use_side ? &s1 : nullptr));
     SGG_TRY(optimise(1, const_cast<float*>(a->d_theta), a->d_grad, it->d_m, it->d_v, const_cast<void*>(a->d_shadow), nc, i + 1, s1));
   }
   // ---- generator step (its own forward keeps the activations the reverse pass needs)
   {
     cudaStream_t s1 = st;
-    SGG_TRY(gen_step_core(a, w, it->noise_all + (long long)nc * m.B * m.C, fresh, it->scalars_all + 4 * nc, st, &s1));
+    SGG_TRY(gen_step_core(a, w, it->noise_all + (long long)nc * m.B * m.C, fresh, it->scalars_all + 4 * nc, st,
+                          use_side ? &s1 : nullptr));
     SGG_TRY(optimise(0, const_cast<float*>(a->g_theta), a->g_grad, it->g_m, it->g_v, const_cast<void*>(a->g_shadow), 1, 1, s1));
   }
   return bump_counter(reinterpret_cast<long long*>(it->counters), st);
+}
+
+// ============================================================================ generator sampling (inference)
+// Forward-only generator (gen:74-91) followed by the reference's test-time decoding (train:270 tf.argmax over the
+// vocabulary) or Gumbel-max sampling.  Nothing is kept for a reverse pass: the batch is walked in chunks whose state,
+// input and scratch buffers are reused every timestep, the hoisted projection P is computed once for the whole batch
+// and the vocabulary logits never reach HBM unless the caller asks for them -- the decoder GEMM's epilogue reduces each
+// n-tile to a (max, column) key.
+struct SampleWs {
+  float* P; float* noise; unsigned long long* keys;
+  NetWs g;
+  long long bytes;
+};
+static int sample_chunk(const sgg_dims_t& d, int chunk) {
+  int c = chunk > 0 ? chunk : 1024;
+  return c < d.B ? c : d.B;
+}
+static SampleWs sample_ws_layout(const sgg_dims_t& d, int chunk, void* base) {
+  const Dm m = derive(d);
+  const int Bc = sample_chunk(d, chunk);
+  SampleWs w{};
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  long long o = 0;
+  auto take = [&](long long bytes) { uint8_t* r = p ? p + o : nullptr; o = rup(o + bytes, 256); return (void*)r; };
+  w.P = (float*)take((long long)m.B * m.RP * 4);
+  w.noise = (float*)take((long long)m.B * m.C * 4);
+  w.keys = (unsigned long long*)take((long long)m.B * m.T * 8);
+  w.g.NRmax = Bc;
+  w.g.X = (__nv_bfloat16*)take(2LL * Bc * 2 * m.KXG * 2);
+  w.g.Cf = (float*)take(2LL * Bc * m.H * 4);
+  w.g.CH = (__nv_bfloat16*)take(2LL * Bc * 2 * m.H * 2);
+  w.g.EA = (float*)take((long long)Bc * m.RP * 4);
+  w.g.Q = (float*)take((long long)Bc * 4 * m.H * 4);
+  w.bytes = o;
+  return w;
+}
+
+namespace sgg { int decode_keys(const unsigned long long* keys, int32_t* tokens, long long n, cudaStream_t st); }
+
+extern "C" int64_t sgg_sample_workspace_bytes(const sgg_dims_t* d, int32_t chunk) {
+  if (!d || check_dims(*d) != 0) return -1;
+  return sample_ws_layout(*d, chunk, nullptr).bytes;
+}
+
+extern "C" int sgg_gen_sample(const sgg_sample_args_t* a, sgg_stream_t stream) {
+  SGG_CHECK(a != nullptr, "sgg_gen_sample: null args");
+  SGG_TRY(check_dims(a->dims));
+  SGG_CHECK(a->g_theta && a->g_shadow && a->ann_g && a->tokens_out, "sgg_gen_sample: missing inputs / outputs");
+  SGG_CHECK(a->mode == SGG_SAMPLE_GREEDY || a->mode == SGG_SAMPLE_GUMBEL, "sgg_gen_sample: unknown mode %d", a->mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  const sgg_dims_t& dd = a->dims;
+  const SampleWs w = sample_ws_layout(dd, a->chunk, a->workspace);
+  SGG_CHECK(a->workspace && a->workspace_bytes >= w.bytes, "sgg_gen_sample: workspace too small (%lld < %lld)",
+            (long long)a->workspace_bytes, (long long)w.bytes);
+  const Dm m = derive(dd);
+  const int Bc = sample_chunk(dd, a->chunk);
+  AnnStaticScope ann_static;   // the annotations are an input of the whole call
+  const float* noise = a->noise;
+  if (!noise) {  // gen:81: one N(0,1) draw per image, shared by all timesteps
+    SGG_TRY(rng_fill(w.noise, (long long)m.B * m.C, a->seed, a->offset, 1, st));
+    noise = w.noise;
+  }
+  SGG_CUDA(cudaMemsetAsync(w.keys, 0, (size_t)m.B * m.T * 8, st));
+  {  // K1 for the whole batch: W_a streams through the SMs once (tensor-bound at large B)
+    NetWs wa = w.g; wa.P = w.P;
+    const Net g = make_net(true, dd, a->g_theta, a->g_shadow, nullptr, a->ann_g, wa, m.B, st);
+    SGG_TRY(net_attn_proj(g));
+  }
+  for (int c0 = 0; c0 < m.B; c0 += Bc) {
+    sgg_dims_t dc = dd;
+    dc.B = m.B - c0 < Bc ? m.B - c0 : Bc;
+    dc.S = 1;
+    NetWs wc = w.g;
+    wc.P = w.P + (long long)c0 * m.RP;
+    Net g = make_net(true, dc, a->g_theta, a->g_shadow, nullptr,
+                     (const __nv_bfloat16*)a->ann_g + (long long)c0 * m.R * m.C, wc, dc.B, st);
+    g.roll = true;
+    SGG_TRY(net_init_state(g, 1));
+    {
+      PackParams pk{};
+      pk.rows = dc.B; pk.cols = m.C; pk.src = noise + (long long)c0 * m.C; pk.ld = m.C;
+      pk.dst = g.w.X + g.uoff; pk.ldd = 2 * g.KXP; pk.lo_off = g.KXP;
+      pk.reps = 2; pk.rep_stride = g.sX();
+      SGG_TRY(pack_hl(pk, st));
+    }
+    for (int t = 0; t < m.T; ++t) {
+      SGG_TRY(net_forward_step(g, t, 1));
+      // logits_t = h_{t+1} W_dec + b (gen:88) with the decoding fused into the epilogue
+      sgg_gemm_desc_t q = gd_zero();
+      q.A = g.w.X + g.t2(t + 1) * g.sX(); q.a_rows = dc.B; q.a_cols = 2 * g.KXP; q.a_ld = 2 * g.KXP;
+      q.B = g.sh + g.L.sWdec; q.b_rows = 2LL * g.L.rWdec; q.b_cols = m.V; q.b_ld = g.L.pWdec; q.b_mn_major = 1;
+      q.M = dc.B; q.N = m.V;
+      segs_act_weight(q, g.hoff, g.KXP, g.L.rWdec, true, m.H);
+      q.bias = g.theta + g.L.bdec;
+      q.splits = 1;
+      q.argmax_keys = reinterpret_cast<uint64_t*>(w.keys + (long long)c0 * m.T + t); q.argmax_stride = m.T;
+      q.gumbel = a->mode == SGG_SAMPLE_GUMBEL; q.gumbel_seed = a->seed ^ 0x5851F42D4C957F2DULL;
+      q.gumbel_offset = a->offset + (unsigned long long)c0 + (unsigned long long)t * (unsigned long long)m.B;
+      if (a->logits_out) { q.C = a->logits_out + ((long long)c0 * m.T + t) * m.V; q.ldc = (long long)m.T * m.V; }
+      SGG_TRY(gemm(q, st));
+    }
+  }
+  return decode_keys(w.keys, a->tokens_out, (long long)m.B * m.T, st);
 }
 
 // Debug / test accessor: location of an intermediate buffer inside the workspace.

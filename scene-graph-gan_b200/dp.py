@@ -33,3 +33,20 @@ def broadcast_comm_id(dist, group, rank: int, make_id: Callable[[], bytes]) -> b
     if not isinstance(box[0], (bytes, bytearray)) or len(box[0]) == 0:
         raise RuntimeError("communicator id was not delivered")
     return bytes(box[0])
+
+
+def wa_shard_rows(regions: int, channels: int, rank: int, world: int) -> Tuple[int, int]:
+    """Row-sharded attention projection (include/sgg_b200.h, sgg_wa_shard_t): the rows of W_a = the contraction indices
+    of P = flat(a) W_a that `rank` owns.  Slices are whole 64-wide k-blocks of the tensor-core GEMM and must be equal."""
+    k_blocks = regions * channels // 64
+    if regions * channels % 64 or k_blocks % world:
+        raise ValueError(f"R*C/64 = {regions * channels / 64} is not divisible by the world size {world}")
+    ks = k_blocks // world * 64
+    return rank * ks, (rank + 1) * ks
+
+
+def slab_send_layout(flat_ann, world: int):
+    """[B, K] local annotations -> [world, B, K/world]: block p holds the columns rank p owns (the all-to-all send
+    buffer; block p of the receive buffer then holds rank p's rows of this rank's column slab)."""
+    B, K = flat_ann.shape
+    return flat_ann.reshape(B, world, K // world).transpose(0, 1).contiguous()

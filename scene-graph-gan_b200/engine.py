@@ -6,6 +6,8 @@ from typing import Optional
 
 import torch
 
+import os
+
 from ._lib import FLAG_REFRESH_GEN_PROJ, Dims, IterArgs, StepArgs, check, lib, stream_ptr
 from .params import DISC, GEN, ParamBucket, make_dims
 
@@ -46,6 +48,21 @@ class Engine:
         self.noise_all = torch.zeros(nc + 1, B, 512, dtype=torch.float32, device=device)
         self.gp_alpha_all = torch.zeros(nc, B, dtype=torch.float32, device=device)
         self.scalars_all = torch.zeros(nc + 1, 4, dtype=torch.float32, device=device)
+        # row-sharded attention projection (include/sgg_b200.h: sgg_wa_shard_t): on by default when world > 1 and the
+        # contraction splits evenly; SGG_WA_SHARD=0 keeps W_a replicated (all-reduce of its gradient) for comparison
+        self.shard = (self.world > 1 and os.environ.get("SGG_WA_SHARD", "1") != "0" and (R * 512 // 64) % self.world == 0)
+        self.slab_g = self.slab_d = self.shard_scratch = None
+        if self.shard:
+            L = lib()
+            L.sgg_wa_shard_scratch_bytes.restype = C.c_int64
+            L.sgg_wa_shard_slab_elems.restype = C.c_int64
+            n_slab = L.sgg_wa_shard_slab_elems(C.byref(self.dims), C.c_int32(self.world))
+            n_scr = L.sgg_wa_shard_scratch_bytes(C.byref(self.dims), C.c_int32(self.world))
+            if n_slab <= 0 or n_scr <= 0:
+                raise RuntimeError("sgg_wa_shard_*: " + L.sgg_last_error().decode())
+            self.slab_g = torch.zeros(n_slab, dtype=torch.bfloat16, device=device)
+            self.slab_d = torch.zeros(n_slab, dtype=torch.bfloat16, device=device)
+            self.shard_scratch = torch.zeros(n_scr, dtype=torch.uint8, device=device)
 
     # ------------------------------------------------------------------ inputs
     def set_batch(self, ann_g: torch.Tensor, ann_d: torch.Tensor, labels: Optional[torch.Tensor]) -> None:
@@ -128,8 +145,31 @@ class Engine:
         it.noise_all, it.gp_alpha_all = self.noise_all.data_ptr(), self.gp_alpha_all.data_ptr()
         it.scalars_all = self.scalars_all.data_ptr()
         it.comm = comm
+        if self.shard and comm is not None:
+            it.shard.enabled = 1
+            it.shard.slab_g, it.shard.slab_d = self.slab_g.data_ptr(), self.slab_d.data_ptr()
+            it.shard.scratch, it.shard.scratch_bytes = self.shard_scratch.data_ptr(), self.shard_scratch.numel()
         check(lib().sgg_train_iteration(C.byref(it), stream_ptr(stream)), "sgg_train_iteration")
         self._refresh = True   # the generator was updated
+
+    def wa_rows(self, rank: int):
+        """Rows of attention_perceptron/kernel rank `rank` maintains under the row-sharded projection."""
+        ks = (self.R * 512 // 64) // self.world * 64
+        return rank * ks, (rank + 1) * ks
+
+    def gather_sharded(self, dist, group=None, rank: int = 0) -> None:
+        """Row-sharded projection: every rank keeps only its rows of W_a (theta, Adam moments, shadow) current.  This
+        all-gathers the rows so that the full tensors can be read (checkpointing, evaluation, tests)."""
+        if not self.shard:
+            return
+        for bucket in (self.g, self.d):
+            name, off, rows, cols, soff, pitch = next(e for e in bucket.entries if e[0].endswith("attention_perceptron/kernel"))
+            r0, r1 = self.wa_rows(rank)
+            n = (r1 - r0) * cols
+            for flat in (bucket.theta, bucket.m, bucket.v):
+                block = flat[off:off + self.world * n]
+                dist.all_gather_into_tensor(block, block[rank * n:(rank + 1) * n].clone(), group=group)
+            bucket.refresh_shadow()
 
     def ws_view(self, name: str, shape, dtype) -> torch.Tensor:
         """Test accessor: a view of a named workspace buffer."""

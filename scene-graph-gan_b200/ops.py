@@ -18,7 +18,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, *, a_mn: bool = False
          segs: Sequence[Tuple[int, int, int, int, int]] = (), out: Optional[torch.Tensor] = None,
          atomic: bool = False, out_hl: Optional[torch.Tensor] = None, lo_off: int = 0,
          bias: Optional[torch.Tensor] = None, addm: Optional[torch.Tensor] = None, add_mod: int = 0,
-         alpha: float = 1.0, block_n: int = 0, splits: int = 1, stream=None) -> None:
+         alpha: float = 1.0, block_n: int = 0, splits: int = 1, argmax_keys: Optional[torch.Tensor] = None,
+         argmax_stride: int = 1, gumbel: bool = False, gumbel_seed: int = 0, gumbel_offset: int = 0, stream=None) -> None:
     """D = alpha * sum_seg A_seg B_seg^T (+bias)(+addm[m % add_mod]).  A, B: 2-D bf16, last dim
     contiguous.  segs: (a_k, a_mn, b_k, b_mn, klen) per segment."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.dim() == 2 and B.dim() == 2
@@ -44,6 +45,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, *, a_mn: bool = False
     d.alpha = alpha
     d.block_n = block_n
     d.splits = splits
+    if argmax_keys is not None:   # sampling epilogue: uint64 keys viewed as int64, zero-filled by the caller
+        assert argmax_keys.dtype == torch.int64 and argmax_keys.is_contiguous()
+        d.argmax_keys, d.argmax_stride = argmax_keys.data_ptr(), argmax_stride
+        d.gumbel, d.gumbel_seed, d.gumbel_offset = int(gumbel), gumbel_seed, gumbel_offset
     check(lib().sgg_gemm(C.byref(d), stream_ptr(stream)), "sgg_gemm")
 
 
@@ -56,3 +61,8 @@ def split_hl(x: torch.Tensor, kpad: int) -> torch.Tensor:
     out[:, :K] = hi
     out[:, kpad:kpad + K] = lo
     return out
+
+
+def decode_argmax_keys(keys: torch.Tensor) -> torch.Tensor:
+    """Column index held in the low half of the sampling epilogue's (value, ~column) keys."""
+    return (0xFFFFFFFF - (keys & 0xFFFFFFFF)).to(torch.int64)

@@ -71,6 +71,13 @@ class HotPathTrainer:
         check(lib().sgg_comm_init(ident, C.c_int32(self.rank), C.c_int32(self.world), C.byref(handle)), "sgg_comm_init")
         return handle
 
+    def gather_sharded(self) -> None:
+        """With world > 1 the annotation rows of attention_perceptron/kernel are row-sharded over the ranks (see
+        sgg_wa_shard_t); call this before reading the full parameter / optimiser tensors."""
+        if self.world > 1:
+            torch.cuda.synchronize()
+            self.eng.gather_sharded(self.dist, self.pg, self.rank)
+
     def close(self) -> None:
         if self.comm is not None:
             torch.cuda.synchronize()

@@ -85,3 +85,58 @@ def test_shard_bounds_reject_ragged_batches():
         dp.shard_bounds(10, 0, 4)
     with pytest.raises(ValueError):
         dp.shard_bounds(8, 4, 4)
+
+
+def _shard_worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sgg_b200 import dp
+        Bl, Rr, Cc, N = 3, 4, 64, 5            # local batch, regions, channels (one 64-wide k-block per region), outputs
+        g = torch.Generator().manual_seed(11)
+        a_all = torch.randn(world * Bl, Rr * Cc, generator=g, dtype=torch.float64)      # every rank's annotations
+        Wa = torch.randn(Rr * Cc, N, generator=g, dtype=torch.float64)
+        Pbar_all = torch.randn(world * Bl, N, generator=g, dtype=torch.float64)
+        a_loc = a_all[rank * Bl:(rank + 1) * Bl]
+        r0, r1 = dp.wa_shard_rows(Rr, Cc, rank, world)
+        # all-to-all of column slabs (emulated with all_gather: gloo has no all_to_all on CPU tensors in every build)
+        send = dp.slab_send_layout(a_loc, world)                                        # [world, Bl, Ks]
+        gathered = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(gathered, send)
+        slab = torch.cat([gathered[p][rank] for p in range(world)], dim=0)              # [world*Bl, Ks]
+        assert torch.equal(slab, a_all[:, r0:r1])
+        # K1: partial projection of the GLOBAL batch over this rank's rows, reduce-scatter (all_reduce + slice here)
+        part = slab @ Wa[r0:r1]
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        P_loc = part[rank * Bl:(rank + 1) * Bl]
+        assert torch.allclose(P_loc, a_loc @ Wa, rtol=1e-12, atol=1e-12)
+        # dW_a rows of this rank: all-gather of P_bar, contraction over the global batch -> equals the all-reduced gradient
+        pb = [torch.empty(Bl, N, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(pb, Pbar_all[rank * Bl:(rank + 1) * Bl].contiguous())
+        dWa_rows = slab.t() @ torch.cat(pb, dim=0)
+        full = a_all.t() @ Pbar_all
+        assert torch.allclose(dWa_rows, full[r0:r1], rtol=1e-12, atol=1e-12)
+        torch.save({"ok": True}, os.path.join(out_dir, f"shard{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_projection_algebra_world2(tmp_path):
+    """The exchange pattern of sgg_wa_shard_t (slab all-to-all, reduce-scatter of P, all-gather of P_bar) reproduces the
+    replicated computation: host-side layout helpers of dp.py under gloo, world_size 2."""
+    world = 2
+    mp.spawn(_shard_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert torch.load(os.path.join(str(tmp_path), f"shard{r}.pt"))["ok"]
+
+
+def test_wa_shard_rows_cover_the_contraction():
+    from sgg_b200 import dp
+    import pytest
+    for world in (1, 2, 4, 8):
+        rows = [dp.wa_shard_rows(196, 512, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 196 * 512
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+        assert all((b - a) % 64 == 0 for a, b in rows)
+    with pytest.raises(ValueError):
+        dp.wa_shard_rows(196, 512, 0, 3)

@@ -29,6 +29,8 @@ def _setup(B, T, V, R=196, seed=0, lam=10.0):
 
 
 CASES = [(8, 3, 96, 196), (5, 4, 130, 196), (130, 3, 200, 196), (3, 2, 2000, 100), (1, 1, 8, 1)]
+# BASELINE configs[2]: 10 triples = 30 timesteps (the reference's loop bound gen:85 generalised), small batch / regions
+LONG_CASES = [(3, 30, 70, 24)]
 
 
 @pytest.mark.parametrize("B,T,V,R", CASES)
@@ -63,7 +65,7 @@ def test_discriminator_forward_scores(B, T, V, R):
     assert rel(got, ref) < TOL
 
 
-@pytest.mark.parametrize("B,T,V,R", CASES)
+@pytest.mark.parametrize("B,T,V,R", CASES + LONG_CASES)
 def test_disc_step_matches_oracle(B, T, V, R):
     """train:365 (minus Adam): w_disc, GP and every Discriminator* gradient, incl. the double backward."""
     from oracle import sgg_oracle as O
@@ -88,7 +90,7 @@ def test_disc_step_matches_oracle(B, T, V, R):
             assert rel(gv[k], v) < TOL, k
 
 
-@pytest.mark.parametrize("B,T,V,R", CASES)
+@pytest.mark.parametrize("B,T,V,R", CASES + LONG_CASES)
 def test_gen_step_matches_oracle(B, T, V, R):
     """train:368 (minus Adam): gen_cost and every Generator* gradient (through D's input path)."""
     from oracle import sgg_oracle as O
