@@ -199,10 +199,19 @@ def kernel_rooflines(trainer, args, pk, dev_batches):
     anns = [t for hb in dev_batches for t in hb[:2]]
     out = []
 
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the same
+    # kernels at this shape (profiles/r1b_*_kernels.raw.csv); only valid for the default config 2 shape
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and (B, T, V) == (256, 3, 2000):
+        with open(tpath) as f:
+            traffic = json.load(f)
+
     def entry(name, secs, nbytes, note):
         ach = nbytes / secs / 1e9
+        key = name.split(" ")[0].split("<")[0]
         return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None, "us_per_launch": secs * 1e6, "algorithmic_bytes": nbytes, "peak_source": pk["source"],
+                "traffic": traffic.get(key), "us_per_launch": secs * 1e6, "algorithmic_bytes": nbytes, "peak_source": pk["source"],
                 "l2": note}
 
     # ---- attention step forward, 3 streams (fake / real / interpolate) sharing one tile read
@@ -218,7 +227,23 @@ def kernel_rooflines(trainer, args, pk, dev_batches):
                                  C.c_int64(1344), stream_ptr()), "sgg_attn_forward")
     t = _time_launches(attn, 24)
     nbytes = B * (R * 512 * 2 + nv * (4 * R + 4 * R + 2 * 2 * 512))
-    out.append(entry("attn_fwd_kernel<0> (3 streams share one annotation read)", t, nbytes,
+    out.append(entry("attn_fwd_mma_kernel<0> (3 streams share one annotation read)", t, nbytes,
+                     f"24 back-to-back launches over {len(anns)} annotation tensors ({len(anns) * B * R * 1024 >> 20} MB > L2)"))
+
+    # ---- attention step reverse, 3 first-order streams sharing one tile read (alpha_bar, softmax reverse, P_bar)
+    zb = torch.randn(nv * B, 1344, device=dev)
+    EBh = torch.empty(nv * B, 512, dtype=torch.bfloat16, device=dev)
+    PB = torch.zeros(B, 256, device=dev)
+
+    def attn_r(i):
+        a = anns[i % len(anns)]
+        check(L.sgg_attn_reverse(C.c_void_p(a.data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv), C.c_void_p(zb.data_ptr()),
+                                 C.c_int64(1344), C.c_void_p(alpha.data_ptr()), C.c_int64(256), C.c_void_p(EBh.data_ptr()),
+                                 C.c_int64(512), C.c_int64(256), C.c_void_p(PB.data_ptr()), C.c_int64(256), stream_ptr()),
+              "sgg_attn_reverse")
+    t = _time_launches(attn_r, 24)
+    nbytes = B * (R * 512 * 2 + nv * (4 * 512 + 4 * R + 2 * 2 * R) + 4 * R)
+    out.append(entry("attn_rev_mma_kernel (3 streams share one annotation read)", t, nbytes,
                      f"24 back-to-back launches over {len(anns)} annotation tensors ({len(anns) * B * R * 1024 >> 20} MB > L2)"))
 
     # ---- K1: P = flat(a) W_a (hi/lo weight: 2 products), split-K tcgen05 GEMM, HBM-bound at this B
@@ -234,7 +259,7 @@ def kernel_rooflines(trainer, args, pk, dev_batches):
                  out=P[:, :R], splits=0)
     t = _time_launches(k1, 12)
     nbytes = B * R * 512 * 2 + 2 * R * 512 * R * 2 + 4 * B * R
-    out.append(entry("gemm_kernel K1: P = flat(a) W_a (M=B, N=196, K=100352, hi/lo weight)", t, nbytes,
+    out.append(entry("gemm_kernel_K1 : P = flat(a) W_a (M=B, N=196, K=100352, hi/lo weight)", t, nbytes,
                      "12 back-to-back launches, rotating annotation tensors; W_a hi/lo (79 MB) + annotations (51 MB) per launch"))
 
     # ---- Adam over the discriminator bucket (+ hi/lo shadow rewrite)

@@ -107,6 +107,16 @@ int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream);
 int sgg_attn_forward(const void* a, int32_t B, int32_t R, int32_t nv, const float* e, float* alpha, int64_t ld_e,
                      void* z_hl, int64_t ld_z, int64_t lo_off, sgg_stream_t stream);
 
+/* Reverse of the attention step (the gradient TF registers for gen:16-17) for `nv` <= 4 streams sharing a tile:
+ *   alpha_bar[r] = <z_bar, a[b,r,:]>,  e_bar = alpha * (alpha_bar - <alpha, alpha_bar>)   (softmax reverse)
+ *   z_bar    [nv*B, ld_zb]   fp32 upstream of z_hat (columns [0,512))
+ *   alpha    [nv*B, ld_alpha] fp32 saved softmax
+ *   e_bar_hl [nv*B, ld_eb]   bf16 out: hi part at columns [0,R), lo part at [lo_off, lo_off+R)
+ *   p_bar    [B, ld_p]       fp32, optional: += sum over streams of e_bar (the gradient of P = flat(a) W_a) */
+int sgg_attn_reverse(const void* a, int32_t B, int32_t R, int32_t nv, const float* z_bar, int64_t ld_zb,
+                     const float* alpha, int64_t ld_alpha, void* e_bar_hl, int64_t ld_eb, int64_t lo_off,
+                     float* p_bar, int64_t ld_p, sgg_stream_t stream);
+
 /* ----------------------------------------------------------------------------------------
  * Parameters.  Each network keeps ONE flat fp32 bucket (master weights; gradients and Adam
  * moments use the same layout) plus a bf16 "shadow" bucket holding the GEMM operands as a

@@ -768,3 +768,23 @@ extern "C" int sgg_attn_forward(const void* a, int32_t B, int32_t R, int32_t nv,
   p.X = reinterpret_cast<__nv_bfloat16*>(z_hl); p.ldX = ld_z; p.lo_off = lo_off;
   return attn_fwd(p, 0, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// Op-level entry point: reverse of the attention step for nv first-order streams sharing a tile.
+extern "C" int sgg_attn_reverse(const void* a, int32_t B, int32_t R, int32_t nv, const float* z_bar, int64_t ld_zb,
+                                const float* alpha, int64_t ld_alpha, void* e_bar_hl, int64_t ld_eb, int64_t lo_off,
+                                float* p_bar, int64_t ld_p, sgg_stream_t stream) {
+  using namespace sgg;
+  SGG_CHECK(a && z_bar && alpha && e_bar_hl, "sgg_attn_reverse: null argument");
+  SGG_CHECK(B >= 1 && nv >= 1 && nv <= AT_MAXV_REV && ld_zb >= AT_C && ld_alpha >= R && ld_eb >= lo_off + R && lo_off >= R,
+            "sgg_attn_reverse: bad shape/pitch");
+  SGG_CHECK((ld_zb % 4) == 0 && (reinterpret_cast<uintptr_t>(z_bar) % 16) == 0, "sgg_attn_reverse: z_bar must be 16-byte aligned rows");
+  AttnRevParams p{};
+  p.a = reinterpret_cast<const __nv_bfloat16*>(a);
+  p.B = B; p.R = R; p.nv = nv; p.tan_stream = -1;
+  for (int v = 0; v < AT_MAXV_REV; ++v) p.row_blk[v] = v;
+  p.XB = z_bar; p.ldXB = ld_zb;
+  p.alpha = alpha; p.ldA = ld_alpha;
+  p.EB = reinterpret_cast<__nv_bfloat16*>(e_bar_hl); p.ldEB = ld_eb; p.lo_off = lo_off;
+  p.Pbar = p_bar; p.ldP = ld_p;
+  return attn_rev(p, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -805,8 +805,12 @@ extern "C" int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, 
 // `fake` = the generator's logits for this step (hi/lo rows t*B+b, a constant here), already computed.
 // side_out: when non-null the dW_a chain is left running on the side stream returned through it (the caller enqueues
 // the W_a optimiser work there and joins); when null the step joins before returning.
+// pre: what the caller has already enqueued for this step's discriminator pass (sgg_train_iteration only):
+//   proj_stream != null : P = flat(a_d) W_a is being computed on that stream (join it before the first scores GEMM)
+//   state_ready         : c0 = h0 of the stream blocks is still in the workspace from the previous critic step
+struct StepPre { cudaStream_t proj_stream; bool have_proj; bool state_ready; };
 static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bfloat16* fake, const float* gp_alpha,
-                          float* scalars, cudaStream_t st, cudaStream_t* side_out = nullptr) {
+                          float* scalars, cudaStream_t st, cudaStream_t* side_out = nullptr, const StepPre* pre = nullptr) {
   const sgg_dims_t& dd = a->dims;
   const Net d = make_net(false, dd, a->d_theta, a->d_shadow, a->d_grad, a->ann_d, w.d, 4 * dd.B, st, w.LNP);
   const Dm& m = d.m;
@@ -826,8 +830,9 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
   SGG_TRY(embed_mix(em, st));
   // 3. D forward on fake | real | interp (one annotation read per timestep)
-  SGG_TRY(net_attn_proj(d));
-  SGG_TRY(net_init_state(d, 3));
+  if (!(pre && pre->have_proj)) SGG_TRY(net_attn_proj(d));
+  if (!(pre && pre->state_ready)) SGG_TRY(net_init_state(d, 3));
+  if (pre && pre->have_proj && pre->proj_stream != st) SGG_TRY(side_join(st, pre->proj_stream));
   SGG_TRY(net_forward(d, 3));
   LossParams lp{B, T, d.w.Y, 0, 1, invBT, scalars};
   SGG_TRY(losses(lp, st));
@@ -916,7 +921,7 @@ extern "C" int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream) {
 // One generator step (train:368): grads of gen_cost = -mean D(G(z)) w.r.t. every Generator*
 // variable into g_grad; scalars[3] = gen_cost.
 static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noise, bool recompute_proj, float* scalars,
-                         cudaStream_t st, cudaStream_t* side_out = nullptr) {
+                         cudaStream_t st, cudaStream_t* side_out = nullptr, const StepPre* pre = nullptr) {
   const sgg_dims_t& dd = a->dims;
   const Net g = make_net(true, dd, a->g_theta, a->g_shadow, a->g_grad, a->ann_g, w.g, dd.B, st, w.LNP);
   const Net d = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, dd.B, st);
@@ -936,8 +941,9 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   em.blk_fake = 0; em.blk_real = -1; em.blk_int = -1;
   em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
   SGG_TRY(embed_mix(em, st));
-  SGG_TRY(net_attn_proj(d));
+  if (!(pre && pre->have_proj)) SGG_TRY(net_attn_proj(d));
   SGG_TRY(net_init_state(d, 1));
+  if (pre && pre->have_proj && pre->proj_stream != st) SGG_TRY(side_join(st, pre->proj_stream));
   SGG_TRY(net_forward(d, 1));
   LossParams lp{B, T, d.w.Y, 0, -1, invBT, scalars};
   SGG_TRY(losses(lp, st));
@@ -1068,6 +1074,18 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
     SGG_TRY(slab_pack((const __nv_bfloat16*)a->ann_d, send_d, m.B, (long long)m.R * m.C, sc.Ks, a->world, s_ex));
     SGG_TRY(comm_all_to_all(it->comm, send_d, const_cast<__nv_bfloat16*>(sc.slab_d), per * 2, s_ex, s_ex != st ? 1 : 0));
   }
+  // ---- first critic step's projection / initial state on the side stream, beside the generator forwards
+  static int prefetch_proj = -1;             // SGG_PROJ_PREFETCH=0 disables these overlaps (A/B measurements)
+  if (prefetch_proj < 0) { const char* e = getenv("SGG_PROJ_PREFETCH"); prefetch_proj = (e && e[0] == '0') ? 0 : 1; }
+  const bool side_ok = !it->comm || comm_has_side_lane(it->comm);
+  const bool use_side = !shard || side_ok;   // sharded: the side chain issues collectives, which need their own lane
+  cudaStream_t s_pre = s_ex;
+  if (prefetch_proj != 0 && nc > 0 && use_side && side_stream() != nullptr) {
+    if (s_pre == st) SGG_TRY(side_fork(st, &s_pre));
+    const Net dn = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, 4 * m.B, s_pre);
+    SGG_TRY(net_attn_proj(dn, s_pre != st ? 1 : 0));
+    SGG_TRY(net_init_state(dn, 3));
+  }
   // ---- fresh randomness for every step of this iteration (Philox position = f(iteration counter))
   const long long n_noise = (long long)(nc + 1) * m.B * m.C, n_alpha = (long long)nc * m.B;
   const uint64_t per_iter = (uint64_t)((n_noise + 3) / 4 + (n_alpha + 3) / 4);
@@ -1081,15 +1099,16 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
     SGG_TRY(gen_forward(g, w, it->noise_all + (long long)s0 * m.B * m.C, ns, s0, fresh, nullptr));
     fresh = false;
   }
-  if (shard) SGG_TRY(side_join(st, s_ex));
   // ---- critic steps
   AdamHyper hp{it->lr, it->beta1, it->beta2, it->eps};
   // Each optimiser step is split in two independent chains that meet again before the next step:
   //   side stream : dW_a GEMM -> [all-reduce of the W_a block] -> Adam on W_a           (HBM- / NVLink-bound)
   //   main stream : the other weight gradients -> [all-reduce of the rest] -> Adam on the rest
-  const bool side_ok = !it->comm || comm_has_side_lane(it->comm);
+  // `next_proj`: the discriminator's projection for the NEXT pass (P = flat(a_d) W_a with the updated W_a) is enqueued
+  // right behind the W_a update on the side stream, where it overlaps the main stream's weight-gradient GEMMs; the
+  // side stream is then joined by the next pass just before its first scores GEMM instead of here.
   auto optimise = [&](int net, float* theta, float* grad, float* mm, float* vv, void* shadow, long long step_mul,
-                      long long step_add, cudaStream_t s1) -> int {
+                      long long step_add, cudaStream_t s1, bool next_proj, cudaStream_t* pending) -> int {
     const ParamLayout L = param_layout(net == 0, dd);
     const long long n_wa = (long long)m.R * m.C * m.R;
     if (s1 != st && !side_ok) { SGG_TRY(side_join(st, s1)); s1 = st; }
@@ -1099,23 +1118,40 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
       if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad, n_wa, s1, s1 != st ? 1 : 0));
       SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1));
     }
+    if (next_proj) {
+      const Net dn = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, m.B, s1);
+      SGG_TRY(net_attn_proj(dn, s1 != st ? 1 : 0));
+    }
     if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad + n_wa, L.total - n_wa, st, 0));
     SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, st, 2));
+    if (next_proj && pending) { *pending = s1; return 0; }
     return side_join(st, s1);
   };
-  const bool use_side = !shard || side_ok;   // sharded: the side chain issues collectives, which need their own lane
+  StepPre pre{st, false, false};
+  if (prefetch_proj != 0 && nc > 0 && use_side && side_stream() != nullptr) {
+    // the first critic step's projection and initial state do not depend on the generator: they were enqueued on the
+    // side stream (behind the discriminator's slab exchange when sharded) and ran beside the generator forwards
+    pre.proj_stream = s_pre; pre.have_proj = true; pre.state_ready = true;
+  } else if (s_ex != st) {
+    SGG_TRY(side_join(st, s_ex));
+  }
   for (int i = 0; i < nc; ++i) {
     cudaStream_t s1 = st;
     SGG_TRY(disc_step_core(a, w, fake_slot(w, m, i), it->gp_alpha_all + (long long)i * m.B, it->scalars_all + 4 * i, st,
-                           use_side ? &s1 : nullptr));
-    SGG_TRY(optimise(1, const_cast<float*>(a->d_theta), a->d_grad, it->d_m, it->d_v, const_cast<void*>(a->d_shadow), nc, i + 1, s1));
+                           use_side ? &s1 : nullptr, &pre));
+    cudaStream_t pending = st;
+    SGG_TRY(optimise(1, const_cast<float*>(a->d_theta), a->d_grad, it->d_m, it->d_v, const_cast<void*>(a->d_shadow), nc, i + 1, s1,
+                     prefetch_proj != 0, &pending));
+    pre.have_proj = prefetch_proj != 0; pre.proj_stream = pending;
+    pre.state_ready = true;                  // same batch, same row layout: c0 = h0 stay valid for the next critic step
   }
   // ---- generator step (its own forward keeps the activations the reverse pass needs)
   {
     cudaStream_t s1 = st;
     SGG_TRY(gen_step_core(a, w, it->noise_all + (long long)nc * m.B * m.C, fresh, it->scalars_all + 4 * nc, st,
-                          use_side ? &s1 : nullptr));
-    SGG_TRY(optimise(0, const_cast<float*>(a->g_theta), a->g_grad, it->g_m, it->g_v, const_cast<void*>(a->g_shadow), 1, 1, s1));
+                          use_side ? &s1 : nullptr, &pre));
+    SGG_TRY(optimise(0, const_cast<float*>(a->g_theta), a->g_grad, it->g_m, it->g_v, const_cast<void*>(a->g_shadow), 1, 1, s1,
+                     false, nullptr));
   }
   return bump_counter(reinterpret_cast<long long*>(it->counters), st);
 }

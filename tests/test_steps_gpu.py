@@ -331,6 +331,34 @@ def test_attention_step_kernel(B, R, nv):
     assert ((got_z.cpu() - ref_z).norm() / ref_z.norm()).item() < 1e-5
 
 
+@pytest.mark.parametrize("B,R,nv", [(7, 196, 3), (3, 100, 1), (2, 29, 4)])
+def test_attention_step_reverse_kernel(B, R, nv):
+    """sgg_attn_reverse vs autograd of gen:16-17: e_bar for every stream and P_bar = sum over streams."""
+    import ctypes as C
+    from sgg_b200._lib import check, lib, stream_ptr
+    g = torch.Generator().manual_seed(B * 77 + R)
+    a = torch.randn(B, R, 512, generator=g).bfloat16()
+    e = (torch.randn(nv * B, R, generator=g, dtype=torch.float64) * 2).requires_grad_(True)
+    zb = torch.randn(nv * B, 512, generator=g, dtype=torch.float64)
+    al = torch.softmax(e, -1)
+    z = torch.einsum("sbr,brc->sbc", al.reshape(nv, B, R), a.double()).reshape(nv * B, 512)
+    (z * zb).sum().backward()
+    ref_eb = e.grad
+    alpha_d = torch.zeros(nv * B, 256, device="cuda"); alpha_d[:, :R] = al.detach().float().cuda()
+    zb_d = zb.float().cuda().contiguous()
+    eb = torch.zeros(nv * B, 512, dtype=torch.bfloat16, device="cuda")
+    pb = torch.zeros(B, 256, device="cuda")
+    check(lib().sgg_attn_reverse(C.c_void_p(a.cuda().data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv),
+                                 C.c_void_p(zb_d.data_ptr()), C.c_int64(512), C.c_void_p(alpha_d.data_ptr()), C.c_int64(256),
+                                 C.c_void_p(eb.data_ptr()), C.c_int64(512), C.c_int64(256), C.c_void_p(pb.data_ptr()),
+                                 C.c_int64(256), stream_ptr()), "attn_rev")
+    torch.cuda.synchronize()
+    got = eb[:, :R].float().double().cpu() + eb[:, 256:256 + R].float().double().cpu()
+    assert ((got - ref_eb).norm() / ref_eb.norm()).item() < 1e-4
+    ref_pb = ref_eb.reshape(nv, B, R).sum(0)
+    assert ((pb[:, :R].double().cpu() - ref_pb).norm() / ref_pb.norm()).item() < 1e-4
+
+
 def test_train_iteration_entry_point_matches_oracle():
     """sgg_train_iteration (one C call per train.py:362-368 loop body, device-side RNG and Adam step counters,
     batched generator forwards) vs the oracle's train_iteration fed with the SAME noise / alpha draws."""
