@@ -35,7 +35,8 @@ struct ShardCtx {
   long long Ks;                                 // contraction indices per rank (multiple of 64)
   const __nv_bfloat16* slab_g; const __nv_bfloat16* slab_d;   // [B*world, Ks]
   __nv_bfloat16* send;                          // [world][B][Ks] all-to-all staging
-  float* Ppart; float* PBall; __nv_bfloat16* PBHall;          // [B*world, RP] / [B*world, 2RP]
+  // per network (index 0 = generator, 1 = discriminator): the two networks' projections run on different streams
+  float* Ppart[2]; float* PBall[2]; __nv_bfloat16* PBHall[2];   // [B*world, RP] / [B*world, 2RP]
 };
 static thread_local const ShardCtx* t_shard = nullptr;
 struct ShardScope {
@@ -123,7 +124,11 @@ static ParamLayout param_layout(bool gen, const sgg_dims_t& d) {
   long long s = 0;
   auto stake = [&](long long n) { long long r = s; s = rup(s + n, 128); return r; };
   // row pitches are multiples of 128 bytes: every 64-column TMA box row is then exactly one aligned L2 line
-  L.pAtt = (int)rup(d.R, 64); L.pK = 4 * d.H; L.pWdec = (int)rup(L.OUT, 64); L.pWemb = (int)rup(d.E, 64);
+  // (W_a alone may instead be packed to an 8-element pitch -- 400 B rows for R = 196, 22 % fewer bytes per K1 pass but
+  // rows that straddle L2 lines: SGG_WA_PITCH=dense selects it for A/B measurements)
+  static int dense_att = -1;
+  if (dense_att < 0) { const char* e = getenv("SGG_WA_PITCH"); dense_att = (e && e[0] == 'd') ? 1 : 0; }
+  L.pAtt = dense_att ? (int)rup(d.R, 8) : (int)rup(d.R, 64); L.pK = 4 * d.H; L.pWdec = (int)rup(L.OUT, 64); L.pWemb = (int)rup(d.E, 64);
   L.rWa = (int)rup((long long)d.R * d.C, 64); L.rWh = (int)rup(d.H, 64); L.rK = (int)rup(L.KX, 64);
   L.rWdec = (int)rup(d.H, 64); L.rWemb = (int)rup(d.V, 64);
   L.sWa = stake(2LL * L.rWa * L.pAtt);
@@ -304,9 +309,10 @@ static int net_attn_proj(const Net& n, int lane = 0) {
     g.B = n.sh + n.L.sWa; g.b_rows = 2LL * n.L.rWa; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
     g.M = (int)Bg; g.N = m.R; g.nseg = 2; g.seg_klen[0] = g.seg_klen[1] = (int)sc.Ks;
     g.seg_b_k[0] = (int)k0; g.seg_b_k[1] = n.L.rWa + (int)k0;
-    g.C = sc.Ppart; g.ldc = m.RP;
+    float* part = sc.Ppart[n.gen ? 0 : 1];
+    g.C = part; g.ldc = m.RP;
     SGG_TRY(gemm(g, n.st));
-    return comm_reduce_scatter(sc.comm, sc.Ppart, n.w.P, (long long)m.B * m.RP, n.st, lane);
+    return comm_reduce_scatter(sc.comm, part, n.w.P, (long long)m.B * m.RP, n.st, lane);
   }
   g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 0;
   g.B = n.sh + n.L.sWa; g.b_rows = 2LL * n.L.rWa; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 1;
@@ -511,12 +517,14 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
     if (t_shard) {   // rows [k0, k0+Ks) of dW_a over the GLOBAL batch: all-gather P_bar, contract with this rank's slab
       const ShardCtx& sc = *t_shard;
       const long long Bg = (long long)m.B * sc.world, k0 = sc.rank * sc.Ks;
-      SGG_TRY(comm_all_gather(sc.comm, n.w.PB, sc.PBall, (long long)m.B * m.RP, s1, lane));
-      pk.rows = (int)Bg; pk.cols = m.R; pk.src = sc.PBall; pk.ld = m.RP;
-      pk.dst = sc.PBHall; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
+      float* pball = sc.PBall[n.gen ? 0 : 1];
+      __nv_bfloat16* pbhall = sc.PBHall[n.gen ? 0 : 1];
+      SGG_TRY(comm_all_gather(sc.comm, n.w.PB, pball, (long long)m.B * m.RP, s1, lane));
+      pk.rows = (int)Bg; pk.cols = m.R; pk.src = pball; pk.ld = m.RP;
+      pk.dst = pbhall; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
       SGG_TRY(pack_hl(pk, s1));
       g.A = n.gen ? sc.slab_g : sc.slab_d; g.a_rows = Bg; g.a_cols = sc.Ks; g.a_ld = sc.Ks; g.a_mn_major = 1;
-      g.B = sc.PBHall; g.b_rows = Bg; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
+      g.B = pbhall; g.b_rows = Bg; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
       g.M = (int)sc.Ks; g.N = m.R; g.nseg = 2;
       g.seg_klen[0] = g.seg_klen[1] = (int)Bg; g.seg_b_mn[1] = m.RP;
       g.C = n.grad + n.L.Watt + k0 * m.R; g.ldc = m.R; g.atomic = 0; g.splits = 0;
@@ -991,7 +999,7 @@ extern "C" int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream) {
 
 // ============================================================================ row-sharded projection: buffers
 namespace sgg { int slab_pack(const __nv_bfloat16* a, __nv_bfloat16* send, int B, long long K, long long Ks, int world, cudaStream_t st); }
-struct ShardScratch { __nv_bfloat16* send; float* Ppart; float* PBall; __nv_bfloat16* PBHall; long long bytes; };
+struct ShardScratch { __nv_bfloat16* send; float* Ppart[2]; float* PBall[2]; __nv_bfloat16* PBHall[2]; long long bytes; };
 static long long shard_ks(const sgg_dims_t& d, int world) {
   const long long kb = ((long long)d.R * d.C + 63) / 64;
   return (kb + world - 1) / world * 64;
@@ -1004,9 +1012,11 @@ static ShardScratch shard_scratch_layout(const sgg_dims_t& d, int world, void* b
   long long o = 0;
   auto take = [&](long long bytes) { uint8_t* r = p ? p + o : nullptr; o = rup(o + bytes, 256); return (void*)r; };
   s.send = (__nv_bfloat16*)take(2LL * world * m.B * Ks * 2);   // generator and discriminator staging
-  s.Ppart = (float*)take(Bg * m.RP * 4);
-  s.PBall = (float*)take(Bg * m.RP * 4);
-  s.PBHall = (__nv_bfloat16*)take(Bg * 2 * m.RP * 2);
+  for (int i = 0; i < 2; ++i) {
+    s.Ppart[i] = (float*)take(Bg * m.RP * 4);
+    s.PBall[i] = (float*)take(Bg * m.RP * 4);
+    s.PBHall[i] = (__nv_bfloat16*)take(Bg * 2 * m.RP * 2);
+  }
   s.bytes = o;
   return s;
 }
@@ -1019,7 +1029,8 @@ static int shard_ctx(const sgg_dims_t& d, int world, int rank, void* comm, const
             (long long)s.bytes);
   out->comm = comm; out->rank = rank; out->world = world; out->Ks = shard_ks(d, world);
   out->slab_g = (const __nv_bfloat16*)sh.slab_g; out->slab_d = (const __nv_bfloat16*)sh.slab_d;
-  out->send = s.send; out->Ppart = s.Ppart; out->PBall = s.PBall; out->PBHall = s.PBHall;
+  out->send = s.send;
+  for (int i = 0; i < 2; ++i) { out->Ppart[i] = s.Ppart[i]; out->PBall[i] = s.PBall[i]; out->PBHall[i] = s.PBHall[i]; }
   return 0;
 }
 extern "C" int64_t sgg_wa_shard_scratch_bytes(const sgg_dims_t* d, int32_t world) {

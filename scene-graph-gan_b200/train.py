@@ -4,7 +4,7 @@ Kept from the reference: the constructor signature (train.py:23-24), ``_Generato
 ``train`` method names, the CLI flag names (train.py:399-412), the step schedule (CRITIC_ITERS D steps then one G
 step on the same batch, train.py:185-187,362-368), the losses (train.py:245-253) and the two Adam optimisers
 (train.py:258-259).  Not reproduced (outside the hot path): the conv front-end, the tf.data JPEG
-pipeline, summaries, R@k evaluation.  Documented deviations: the reference passes batch_size / critic_iters to
+pipeline, summaries.  Documented deviations: the R@k ranking bug of train.py:320 (see ``test``); the reference passes batch_size / critic_iters to
 the constructor in swapped order (train.py:420-421 vs 23-24) -- here each flag reaches its own parameter; the
 constructor does not delete the contents of the checkpoint / summary directories (train.py:50-53).
 """
@@ -116,8 +116,47 @@ class SceneGraphGAN(object):
                 out.close()
         return n
 
-    def test(self, *args, **kwargs):
-        raise NotImplementedError("R@k evaluation (train.py:294-335) is outside the B200 hot path (SURVEY 8f-3)")
+    @staticmethod
+    def _recall(fake, real, N):
+        """train.py:294-295: |set(fake triples) & set(real triples)| / N."""
+        return float(len(set(map(tuple, fake)).intersection(set(map(tuple, real))))) / N
+
+    def test(self, batches: Iterable, multiplier: int = 10, out_path: Optional[str] = None):
+        """R@50 / R@100 evaluation of train.py:297-335 on the hot path: for every test batch, ``multiplier`` generator
+        passes with fresh noise (train.py:311: TEST_BATCH_MULTIPLIER) give fake triples ``argmax(logits)`` (train.py:270)
+        and discriminator scores ``mean_t D(logits, images)`` (train.py:272,314); the fakes are ranked by score and the
+        top 50 / 100 are intersected with the batch's real triples (train.py:326-327).  ``batches`` yields
+        (annotations_for_G, annotations_for_D, labels [B, n_steps]).
+        Documented deviation: the reference ranks with ``score_accumulator.argsort()`` on an [N,1] array, which sorts
+        each 1-element row and returns all zeros; here the fakes are sorted by descending critic score.
+        Returns (mean R@50, mean R@100) and, like the reference, writes them to ``recalls.txt``."""
+        e = self.trainer.eng
+        r50, r100 = [], []
+        for ag, ad, lb in batches:
+            dev = e.device
+            ag = ag.to(device=dev, dtype=torch.bfloat16).contiguous()
+            ad = ad.to(device=dev, dtype=torch.bfloat16).contiguous()
+            lb = lb.to(device=dev, dtype=torch.int64).contiguous()
+            e.set_batch(ag.view(e.B, e.R, 512), ad.view(e.B, e.R, 512), lb)
+            fakes, scores = [], []
+            for _ in range(multiplier):
+                e.sample_noise()
+                e._refresh = True
+                logits = e.gen_forward()                                   # self.fake_inputs (train.py:269)
+                fakes.append(logits.argmax(dim=-1))                        # self.fake_triples (train.py:270)
+                scores.append(e.disc_forward(logits).mean(dim=1))          # np.mean(disc_scores, axis=1) (train.py:314)
+            fake = torch.cat(fakes).cpu().numpy()
+            score = torch.cat(scores).cpu().numpy()
+            real = lb.cpu().numpy()
+            order = (-score).argsort(kind="stable")
+            r50.append(self._recall(fake[order[:50]], real, 50.0))
+            r100.append(self._recall(fake[order[:100]], real, 100.0))
+        m50 = float(sum(r50) / len(r50)) if r50 else 0.0
+        m100 = float(sum(r100) / len(r100)) if r100 else 0.0
+        path = out_path or "recalls.txt"
+        with open(path, "w") as f:                                         # train.py:333-335
+            f.write("{}\n{}".format(m50, m100))
+        return m50, m100
 
 
 def synthetic_batches(B, T, V, R, n, seed=1234):

@@ -98,3 +98,39 @@ def test_scene_graph_gan_trainer(tmp_path):
     for k, v in gan.g.variables.items():
         assert torch.equal(v, gan2.g.variables[k]), k
     assert int(gan2.trainer.eng.counters.item()) == 3
+
+
+def test_recall_at_k_evaluation(tmp_path):
+    """SceneGraphGAN.test (train.py:297-335): fakes ranked by critic score, R@50 / R@100 against the real triples.
+    Checked against a host restatement that uses the classes' own build_generator / build_discriminator outputs."""
+    from sgg_b200.train import SceneGraphGAN
+    V, B, mult = 6, 16, 8            # tiny vocabulary so that generated triples do hit real ones
+    gan = SceneGraphGAN(str(tmp_path / "ck"), str(tmp_path / "logs"), None, None, None, None, None,
+                        critic_iters=1, batch_size=B, lambda_=10, resume=False, vocab_size=V)
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(B, 196, 512, generator=g).bfloat16(), torch.randn(B, 196, 512, generator=g).bfloat16(),
+                torch.randint(0, V, (B, 3), generator=g)) for _ in range(2)]
+    out = str(tmp_path / "recalls.txt")
+    r50, r100 = gan.test(batches, multiplier=mult, out_path=out)
+    assert 0.0 <= r50 <= 1.0 and 0.0 <= r100 <= 1.0
+    assert open(out).read() == "{}\n{}".format(r50, r100)            # train.py:333-335
+    # the recall helper is the reference's set intersection (train.py:294-295)
+    assert SceneGraphGAN._recall([[1, 2, 3], [1, 2, 3], [4, 5, 0]], [[1, 2, 3], [9, 9, 9]], 50.0) == 1 / 50.0
+    # deterministic given the engine's RNG position: replay the same noise through the public classes
+    e = gan.trainer.eng
+    e._rng_off = 0
+    ag, ad, lb = batches[0]
+    fakes, scores = [], []
+    for _ in range(mult):
+        e.sample_noise()
+        e._refresh = True
+        e.set_batch(ag.cuda().contiguous(), ad.cuda().contiguous(), lb.cuda().contiguous())
+        lg = e.gen_forward().clone()
+        fakes.append(lg.argmax(-1).cpu())
+        scores.append(e.disc_forward(lg).mean(1).cpu())
+    fake, score = torch.cat(fakes).numpy(), torch.cat(scores).numpy()
+    order = (-score).argsort(kind="stable")
+    want50 = SceneGraphGAN._recall(fake[order[:50]], lb.numpy(), 50.0)
+    e._rng_off = 0
+    got50, _ = gan.test(batches[:1], multiplier=mult, out_path=out)
+    assert got50 == want50
