@@ -173,7 +173,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
 #pragma unroll 1
-   for (int mt = 0; mt < MT; ++mt) {
+   for (int mi = 0; mi < MT; ++mi) {
+    const int mt = (MT == 2 && gridDim.z > 1) ? (mi ^ (int)((blockIdx.z >> 3) & 1u)) : mi;   // see `rot` below
     const int row = m0 + mt * BM + q * 32 + (int)lane_id();
     const bool row_ok = row < p.M;
     long long orow = row;
@@ -190,10 +191,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     float best_v = -INFINITY;
     int best_c = 0;
+    // split-K: the CTAs that share an output tile finish together and would all reduce into the same addresses in the
+    // same order; each starts at its own column chunk so that same-address reductions are spread out in time
+    const int nch = min(BN / 32, (p.N - n0 + 31) / 32);
+    const int rot = gridDim.z > 1 ? (int)(blockIdx.z % (unsigned)nch) : 0;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int ci = 0; ci < nch; ++ci) {
+      const int c = ci + rot < nch ? ci + rot : ci + rot - nch;
       const int col0 = n0 + c * 32;
-      if (col0 >= p.N) break;
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c * 32), r);
       tmem_ld_wait();

@@ -1179,7 +1179,7 @@ struct SampleWs {
   long long bytes;
 };
 static int sample_chunk(const sgg_dims_t& d, int chunk) {
-  int c = chunk > 0 ? chunk : 1024;
+  int c = chunk > 0 ? chunk : 8192;   // measured (profiles/README.md): the whole-batch plan beats L2-sized chunks
   return c < d.B ? c : d.B;
 }
 static SampleWs sample_ws_layout(const sgg_dims_t& d, int chunk, void* base) {
