@@ -168,20 +168,24 @@ def synthetic_host_batches(n, B, T, V, R, seed):
     return out
 
 
-def _time_launches(fn, n, warm=3):
-    """Average device time of n back-to-back launches (CUDA events on the launching stream)."""
+def _time_launches(fn, n, warm=3, repeats=3):
+    """Average device time of n back-to-back launches (CUDA events on the launching stream), best of `repeats` trains."""
     import torch
     st = torch.cuda.current_stream()
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for i in range(n):
-        fn(warm + i)
-    e1.record(st)
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e-3 / n
+    best = None
+    for r in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for i in range(n):
+            fn(warm + r * n + i)
+        e1.record(st)
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / n
+        best = t if best is None or t < best else best
+    return best
 
 
 def kernel_rooflines(trainer, args, pk, dev_batches):

@@ -74,7 +74,8 @@ typedef struct sgg_gemm_desc {
   int32_t seg_b_k[SGG_GEMM_MAX_SEG], seg_b_mn[SGG_GEMM_MAX_SEG];
   int32_t seg_klen[SGG_GEMM_MAX_SEG]; /* k-blocks of 64; a ragged tail must fall outside both tensors */
   /* epilogue */
-  float* C; int64_t ldc; int32_t atomic;        /* fp32 output (optional); atomic => red.add */
+  float* C; int64_t ldc; int32_t atomic;        /* fp32 output (optional); 1 => red.add into the existing contents;
+                                                   2 => the output is known to be zero-filled (no clear needed) */
   void* Chl; int64_t ld_hl; int64_t lo_off;     /* bf16 hi/lo split output (optional) */
   const float* bias;                            /* [N] optional */
   const float* addm; int64_t ld_addm; int32_t add_mod; /* optional broadcast add */

@@ -53,6 +53,10 @@ struct AttnFwdParams {
   float* alpha_out; long long ldA;    // alpha (mode 0) or adot (mode 1)
   __nv_bfloat16* X; long long ldX; long long lo_off;  // z written at X[row, 0:C] (hi) and +lo_off (lo)
   int early_a;             // the annotations are not written by any kernel of this stream's PDL chain
+  int l2_keep;             // load the tile with the L2 evict_last policy (it is re-read by the next attention launches)
+  // optional: zero-fill the gate GEMM's output rows of this sample's streams (zero_cols floats at zero_p + row * zero_ld),
+  // so that the split-K GEMM behind this kernel needs no zero-fill launch of its own
+  float* zero_p; long long zero_ld; int zero_cols;
 };
 
 template <int MODE, int NV>
@@ -232,13 +236,15 @@ __global__ void __launch_bounds__(A2_THREADS) attn_fwd_mma_kernel(const __grid_c
     // ===================== TMA producer =====================
     if (elect_one()) {
       if (!p.early_a) pdl_wait();   // annotations that a preceding kernel may have written
+      const uint64_t pol = l2_policy_evict_last();
       for (int c = 0; c < nch; ++c) {
         const int st = c % A2_STAGES;
         mbar_wait(&sm.empty[st], ((c / A2_STAGES) & 1) ^ 1);
         mbar_expect_tx(&sm.full[st], A2_STAGE_BYTES);
 #pragma unroll
         for (int j = 0; j < AT_C / 64; ++j)
-          tma_load_3d(sm.stage[st] + j * (A2_ROWS * 128), &tmA, &sm.full[st], 64 * j, c * A2_ROWS, b);
+          if (p.l2_keep) tma_load_3d_hint(sm.stage[st] + j * (A2_ROWS * 128), &tmA, &sm.full[st], 64 * j, c * A2_ROWS, b, pol);
+          else tma_load_3d(sm.stage[st] + j * (A2_ROWS * 128), &tmA, &sm.full[st], 64 * j, c * A2_ROWS, b);
       }
     }
   } else if (warp == 1) {
@@ -327,6 +333,13 @@ __global__ void __launch_bounds__(A2_THREADS) attn_fwd_mma_kernel(const __grid_c
     }
     fence_proxy_async_smem();
     mbar_arrive(&sm.wready);
+    if (p.zero_p) {   // while the contraction runs: clear the gate pre-activation rows of this sample's streams
+      const int wt = threadIdx.x - 64;
+      for (int v = 0; v < p.nv; ++v) {
+        float4* d = reinterpret_cast<float4*>(p.zero_p + ((long long)p.row_blk[v] * p.B + b) * p.zero_ld);
+        for (int i = wt; i < (p.zero_cols >> 2); i += 128) d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     // ---- epilogue: TMEM lane = channel within the tile, column = stream
     const int q = warp & 3;
     mbar_wait(&sm.tmem_full, 0);
@@ -367,6 +380,7 @@ struct AttnRevParams {
   __nv_bfloat16* EB; long long ldEB; long long lo_off;  // e_bar hi/lo out (pad columns untouched)
   float* Pbar; long long ldP;             // [B,R] += sum over primal streams of e_bar (may be null)
   int early_a;                            // see AttnFwdParams
+  int l2_keep;
 };
 
 __global__ void __launch_bounds__(AT_THREADS) attn_rev_kernel(const AttnRevParams p) {
@@ -547,11 +561,13 @@ __global__ void __launch_bounds__(A2_THREADS) attn_rev_mma_kernel(const __grid_c
   if (warp == 0) {
     if (elect_one()) {
       if (!p.early_a) pdl_wait();
+      const uint64_t pol = l2_policy_evict_last();
       for (int c = 0; c < nch; ++c) {
         const int st = c % R2_STAGES;
         mbar_wait(&sm.empty[st], ((c / R2_STAGES) & 1) ^ 1);
         mbar_expect_tx(&sm.full[st], R2_STAGE_BYTES);
-        tma_load_3d(sm.stage[st], &tmA, &sm.full[st], 64 * (c & 7), 128 * (c >> 3), b);
+        if (p.l2_keep) tma_load_3d_hint(sm.stage[st], &tmA, &sm.full[st], 64 * (c & 7), 128 * (c >> 3), b, pol);
+        else tma_load_3d(sm.stage[st], &tmA, &sm.full[st], 64 * (c & 7), 128 * (c >> 3), b);
       }
     }
   } else if (warp == 1) {
@@ -700,7 +716,9 @@ static bool attn_use_simt() {   // SGG_ATTN_SIMT=1 selects the CUDA-core forward
   return v == 1;
 }
 
-int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
+int attn_fwd(const AttnFwdParams& p_in, int mode, cudaStream_t stream) {
+  AttnFwdParams p = p_in;
+  p.l2_keep = l2_policy_enabled() ? 1 : 0;
   SGG_CHECK(p.R > 0 && p.R <= AT_RMAX, "attn_fwd: R=%d out of range (1..%d)", p.R, AT_RMAX);
   SGG_CHECK(p.nv >= 1 && p.nv <= (mode == 0 ? AT_MAXV : 4), "attn_fwd: nv=%d out of range", p.nv);
   static bool configured = false;
@@ -721,6 +739,10 @@ int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
       SGG_LAUNCH(attn_fwd_mma_kernel<1>, p.B, A2_THREADS, attn2_smem_bytes(), stream, tm, p);
     return 0;
   }
+  if (p.zero_p) {   // the CUDA-core kernels do not carry the fused zero-fill
+    for (int v = 0; v < p.nv; ++v)
+      SGG_TRY(zero_2d(p.zero_p + (long long)p.row_blk[v] * p.B * p.zero_ld, p.zero_ld, p.zero_cols, p.B, stream));
+  }
   if (mode == 0 && p.nv > 4)
     SGG_LAUNCH((attn_fwd_kernel<0, 8>), p.B, AT_THREADS, attn_smem_bytes(), stream, p);
   else if (mode == 0)
@@ -730,7 +752,9 @@ int attn_fwd(const AttnFwdParams& p, int mode, cudaStream_t stream) {
   return 0;
 }
 
-int attn_rev(const AttnRevParams& p, cudaStream_t stream) {
+int attn_rev(const AttnRevParams& p_in, cudaStream_t stream) {
+  AttnRevParams p = p_in;
+  p.l2_keep = l2_policy_enabled() ? 1 : 0;
   SGG_CHECK(p.R > 0 && p.R <= AT_RMAX, "attn_rev: R=%d out of range (1..%d)", p.R, AT_RMAX);
   SGG_CHECK(p.nv >= 1 && p.nv <= AT_MAXV_REV, "attn_rev: nv=%d out of range", p.nv);
   static bool configured = false;

@@ -46,6 +46,7 @@ void note_launch();  // counts kernels launched by this library (sgg_launch_coun
 // (blocks until the preceding kernel has completed and flushed).  Launch latency, barrier / TMEM / descriptor
 // prologues then overlap the tail of the previous kernel.  SGG_PDL=0 in the environment turns the attribute off.
 bool pdl_enabled();
+bool l2_policy_enabled();   // SGG_L2_POLICY=1, see lib.cu
 // Optional per-launch event timing (SGG_TIMING=1; eager launches only, never during stream capture): warm,
 // in-sequence kernel durations without a profiler.  Read back with sgg_timing_report().
 bool timing_enabled();
@@ -183,6 +184,33 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// L2 eviction-priority policies (createpolicy) for TMA loads: the annotation tiles are re-read by every attention
+// launch of a step (evict_last keeps them resident), weight / optimiser streams are read once (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
       : "memory");
 }
 // Makes generic-proxy writes to shared memory visible to the async proxy (TMA / tcgen05.mma operand reads).

@@ -15,6 +15,50 @@ constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
+// Zero-fill as a KERNEL (not a memset node): it takes part in the programmatic-dependent-launch chain, so the launch
+// of the kernel behind it still overlaps, which a memset node in the middle of the chain prevents.  Up to 4 pitched
+// regions per launch; widths / pitches / pointers in multiples of 16 bytes.
+struct ZeroSegs { void* p[4]; long long pitch16[4], width16[4], rows[4]; long long start[5]; int n; };
+__global__ void __launch_bounds__(256) zero_kernel(const ZeroSegs z) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = z.start[z.n];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int s = 0;
+    while (s + 1 < z.n && i >= z.start[s + 1]) ++s;
+    const long long j = i - z.start[s];
+    const long long r = j / z.width16[s], c = j - r * z.width16[s];
+    reinterpret_cast<uint4*>(z.p[s])[r * z.pitch16[s] + c] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+struct ZeroList {
+  ZeroSegs z{};
+  // returns false when the region cannot be expressed in 16-byte units (caller falls back to cudaMemset*Async)
+  bool add(void* p, long long pitch_bytes, long long width_bytes, long long rows) {
+    if (z.n >= 4 || (reinterpret_cast<uintptr_t>(p) & 15) || (pitch_bytes & 15) || (width_bytes & 15)) return false;
+    z.p[z.n] = p; z.pitch16[z.n] = pitch_bytes / 16; z.width16[z.n] = width_bytes / 16; z.rows[z.n] = rows;
+    z.start[z.n + 1] = z.start[z.n] + rows * (width_bytes / 16);
+    ++z.n;
+    return true;
+  }
+  bool add(void* p, long long bytes) { return add(p, bytes, bytes, 1); }
+};
+int zero_fill(const ZeroList& l, cudaStream_t stream) {
+  const long long total = l.z.start[l.z.n];
+  if (l.z.n == 0 || total <= 0) return 0;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  SGG_LAUNCH(zero_kernel, grid, 256, 0, stream, l.z);
+  return 0;
+}
+// zero one pitched fp32 region, as a kernel when it can be (see zero_kernel), else as a memset node
+int zero_2d(float* p, long long ld, long long cols, long long rows, cudaStream_t stream) {
+  ZeroList l;
+  if (l.add(p, ld * 4, cols * 4, rows)) return zero_fill(l, stream);
+  SGG_CUDA(cudaMemset2DAsync(p, (size_t)ld * 4, 0, (size_t)cols * 4, (size_t)rows, stream));
+  return 0;
+}
+
 struct GemmKParams {
   int M, N;
   // Operand parts.  x ~= hi + lo operands are given as two parts of the same tensor (different k / mn offsets);
@@ -31,6 +75,7 @@ struct GemmKParams {
   int rm_d0, rm_d1; long long rm_s0, rm_s1;   // output row permutation (rm_d0 == 0: identity)
   // sampling epilogue (train:270 argmax / Gumbel-max): per output row the running maximum of v[n] (+ Gumbel noise) and
   // its column, packed as (orderable float bits << 32) | ~column and merged across n-tiles with a 64-bit atomicMax
+  int b_stream;   // B operand is a read-once weight stream (W_a): L2 evict_first; fp32 output stores stream too
   unsigned long long* amax; long long amax_stride;
   int gumbel; unsigned long long gseed, goff;
 };
@@ -93,6 +138,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_first = l2_policy_evict_first();
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * p.stage_bytes;
@@ -115,6 +161,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* sB = st + b_off + pb * B_PART_BYTES;
           if (!B_MN) {
             tma_load_2d(sB, &tmB, &full_bar[stage], p.b_k[pb] + kc, n0 + p.b_mn[pb]);
+          } else if (MT == 2 && p.b_stream) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d_hint(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + p.b_mn[pb] + 64 * j, p.b_k[pb] + kc, pol_first);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
@@ -350,6 +400,7 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   const bool wide_b = kp.nA == 1 && kp.nB == 2 && d.b_mn_major && d.M >= 2 * BM && d.N > 128 && d.N <= 256 &&
                       (d.block_n == 0 || d.block_n == 256);
   const int mt = wide_b ? 2 : 1;
+  kp.b_stream = (wide_b && !d.a_mn_major && l2_policy_enabled()) ? 1 : 0;   // K1: W_a is read once per pass
   if (wide_b) {
     bn = 256;
     if (d.splits <= 0) {
@@ -391,9 +442,11 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   if (splits > kp.total_kb) splits = kp.total_kb;
   SGG_CHECK(splits == 1 || can_split, "sgg_gemm: split-K needs the fp32 output only");
   SGG_CHECK(bn == 64 || bn == 128 || bn == 256, "sgg_gemm: block_n=%d unsupported", bn);
-  if (splits > 1 && !d.atomic) {   // overwrite semantics: clear the output, then accumulate
+  if (d.atomic == 2) {             // the caller guarantees a zero-filled output: accumulate or overwrite, whichever fits
+    kp.atomic = splits > 1 ? 1 : 0;
+  } else if (splits > 1 && !d.atomic) {   // overwrite semantics: clear the output, then accumulate
     SGG_CHECK(d.out_d0 == 0, "sgg_gemm: split-K with an output row permutation is not supported");
-    SGG_CUDA(cudaMemset2DAsync(d.C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, stream));
+    SGG_TRY(zero_2d(d.C, d.ldc, d.N, d.M, stream));
     kp.atomic = 1;
   }
   kp.stage_bytes = kp.nA * mt * A_STAGE_BYTES + kp.nB * bn * BK * 2;
@@ -456,7 +509,7 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
   }
   // ---- general segment lists: one accumulate-launch per segment
   SGG_CHECK(d.C && !d.Chl && d.out_d0 == 0 && !d.argmax_keys, "sgg_gemm: this segment pattern needs the plain fp32 output");
-  if (!d.atomic) SGG_CUDA(cudaMemset2DAsync(d.C, (size_t)d.ldc * 4, 0, (size_t)d.N * 4, (size_t)d.M, stream));
+  if (!d.atomic) SGG_TRY(zero_2d(d.C, d.ldc, d.N, d.M, stream));
   for (int s = 0; s < d.nseg; ++s) {
     sgg_gemm_desc_t e = d;
     e.atomic = 1;

@@ -36,6 +36,16 @@ bool pdl_enabled() {
   return on == 1;
 }
 
+// SGG_L2_POLICY=1: L2 eviction-priority hints (annotation tiles evict_last; weight / optimiser streams evict_first)
+bool l2_policy_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SGG_L2_POLICY");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 // ---- per-launch event timing (debug / profiling aid)
 struct TimedLaunch { cudaEvent_t e0, e1; const void* func; dim3 grid, block; };
 static std::vector<TimedLaunch> g_timed;

@@ -169,6 +169,15 @@ __device__ __forceinline__ void gate_fwd(int G, const float* q, const float* qd,
 }
 
 // shared memory: gate activations [4][512] (+ tangents [4][512]) + reduction scratch
+// Zero-fill of the NEXT split-K GEMM's output row that belongs to the row this CTA processes (the GEMM then accumulates
+// with reductions and needs no zero-fill launch of its own): `cols` floats (multiple of 4) at zp + row * ld.
+struct ZeroRow { float* p; long long ld; int cols; };
+__device__ __forceinline__ void zero_row(const ZeroRow& z, long long row) {
+  if (z.p == nullptr) return;
+  float4* d = reinterpret_cast<float4*>(z.p + row * z.ld);
+  for (int i = threadIdx.x; i < (z.cols >> 2); i += LS_THREADS) d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 struct LstmSmemFwd {
   float xa[4][LH];
   float xad[4][LH];
@@ -186,6 +195,7 @@ struct LstmFwdParams {
   __nv_bfloat16* Xn; long long ldX; long long x_lo; int hoff;  // h hi/lo into next step's x buffer
   const float* wdec; const float* bdec;   // optional D head (fp32 master weights)
   float* Y; long long ldY;                // Y[row*ldY]
+  ZeroRow zero;                           // optional: next step's scores rows
 };
 
 __global__ void __launch_bounds__(LS_THREADS) lstm_fwd_kernel(const LstmFwdParams p) {
@@ -196,6 +206,7 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_fwd_kernel(const LstmFwdParam
   int tog = 0;
   for (int row = blockIdx.x; row < p.nrows; row += gridDim.x) {
     prefetch_l1(p.Cin + (long long)row * LH + threadIdx.x * 4);   // state-phase operand: fetched under the gate phase
+    zero_row(p.zero, row);
     {
       V16 n, xd, nd, act, actd;
       float r;
@@ -248,6 +259,7 @@ struct LstmTanParams {
   float* Cout;               // tangent new c written at trow
   __nv_bfloat16* CH; long long ldCH; long long ch_lo;
   __nv_bfloat16* Xn; long long ldX; long long x_lo; int hoff;
+  ZeroRow zero;              // optional: next step's tangent-score rows (indexed by i, not by trow)
 };
 
 // State phase shared by the tangent and reverse kernels: from the gate activations in shared memory and c_in,
@@ -310,6 +322,7 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_tan_kernel(const LstmTanParam
     const long long prow = p.prow0 + i, trow = p.trow0 + i;
     prefetch_l1(p.C + prow * LH + threadIdx.x * 4);
     prefetch_l1(p.C + trow * LH + threadIdx.x * 4);
+    zero_row(p.zero, i);
     {
       V16 n, xd, nd, act, actd;
       float r;
@@ -363,6 +376,7 @@ struct LstmRevParams {
   float* CB;                                    // c_bar [rows,H]
   // parameter gradients (partials == nullptr => data path only)
   float* partials; int init_partials;
+  ZeroRow zero;                                 // optional: this step's x_bar rows (primal and tangent rows)
 };
 
 constexpr int LR_NVEC = 11;                 // dgamma[5], dbeta[5], dwdec
@@ -442,6 +456,8 @@ __device__ __forceinline__ void lstm_rev_row(const LstmRevParams& p, LstmSmemRev
   const int G = threadIdx.x >> 5;
   const float* q = p.Q + prow * p.ldQ;
   const float* qd = p.Q + trow * p.ldQ;
+  zero_row(p.zero, prow);
+  if (TAN) zero_row(p.zero, trow);
   {  // operands of the state phase: fetched into L1 under the gate phase (each is one 2 KB row, 16 B per thread)
     const int c4 = threadIdx.x * 4;
     prefetch_l1(p.C + prow * LH + c4);

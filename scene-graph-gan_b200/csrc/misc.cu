@@ -277,6 +277,7 @@ struct AdamParams {
   float lr_t, b1, b2, eps, gscale;
   // device-side step counter (graph replay): step = iter[0] * step_mul + step_add, lr_t recomputed in the kernel
   const long long* iter; long long step_mul, step_add; float lr;
+  int stream_l2;                                       // streaming (evict-first) accesses to the buckets
   int nseg; AdamSeg seg[ADAM_MAX_SEG];
   int blk_start[ADAM_MAX_SEG + 1];                     // CTA range of each segment (one flat 1-D grid)
 };
@@ -297,10 +298,17 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
     const long long i = base + u * 1024;
     const long long gi = sg.off + i;
     if (aligned && i + 4 <= sg.n) {
-      const float4 t4 = *reinterpret_cast<const float4*>(p.theta + gi);
       const float4 g4 = __ldcs(reinterpret_cast<const float4*>(p.grad + gi));   // gradients are dead after this read
-      const float4 m4 = *reinterpret_cast<const float4*>(p.m + gi);
-      const float4 v4 = *reinterpret_cast<const float4*>(p.v + gi);
+      float4 t4, m4, v4;
+      if (p.stream_l2) {   // the whole bucket is touched once per step: do not displace the annotation tiles in L2
+        t4 = __ldcs(reinterpret_cast<const float4*>(p.theta + gi));
+        m4 = __ldcs(reinterpret_cast<const float4*>(p.m + gi));
+        v4 = __ldcs(reinterpret_cast<const float4*>(p.v + gi));
+      } else {
+        t4 = *reinterpret_cast<const float4*>(p.theta + gi);
+        m4 = *reinterpret_cast<const float4*>(p.m + gi);
+        v4 = *reinterpret_cast<const float4*>(p.v + gi);
+      }
       th[u][0] = t4.x; th[u][1] = t4.y; th[u][2] = t4.z; th[u][3] = t4.w;
       g[u][0] = g4.x; g[u][1] = g4.y; g[u][2] = g4.z; g[u][3] = g4.w;
       m[u][0] = m4.x; m[u][1] = m4.y; m[u][2] = m4.z; m[u][3] = m4.w;
@@ -338,9 +346,15 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
     }
     const bool vec = aligned && i + 4 <= sg.n;
     if (vec) {
-      *reinterpret_cast<float4*>(p.theta + gi) = make_float4(th[u][0], th[u][1], th[u][2], th[u][3]);
-      *reinterpret_cast<float4*>(p.m + gi) = make_float4(m[u][0], m[u][1], m[u][2], m[u][3]);
-      *reinterpret_cast<float4*>(p.v + gi) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+      if (p.stream_l2) {
+        __stcs(reinterpret_cast<float4*>(p.theta + gi), make_float4(th[u][0], th[u][1], th[u][2], th[u][3]));
+        __stcs(reinterpret_cast<float4*>(p.m + gi), make_float4(m[u][0], m[u][1], m[u][2], m[u][3]));
+        __stcs(reinterpret_cast<float4*>(p.v + gi), make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+      } else {
+        *reinterpret_cast<float4*>(p.theta + gi) = make_float4(th[u][0], th[u][1], th[u][2], th[u][3]);
+        *reinterpret_cast<float4*>(p.m + gi) = make_float4(m[u][0], m[u][1], m[u][2], m[u][3]);
+        *reinterpret_cast<float4*>(p.v + gi) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+      }
     } else {
       for (int e = 0; e < 4; ++e)
         if (i + e < sg.n) { p.theta[gi + e] = th[u][e]; p.m[gi + e] = m[u][e]; p.v[gi + e] = v[u][e]; }
@@ -376,6 +390,7 @@ int adam(AdamParams p, cudaStream_t stream) {
   }
   p.blk_start[p.nseg] = nb;
   if (nb == 0) return 0;
+  p.stream_l2 = l2_policy_enabled() ? 1 : 0;
   SGG_LAUNCH(adam_kernel, nb, 256, 0, stream, p);
   return 0;
 }

@@ -331,7 +331,7 @@ static int net_init_state(const Net& n, int nblk) {
 }
 
 // e = P + b + c W_h for rows [row0, row0+nrows) of step t (tangent: edot = cdot W_h into ED).
-static int net_scores(const Net& n, int t, int row0, int nrows, bool tangent) {
+static int net_scores(const Net& n, int t, int row0, int nrows, bool tangent, bool prezeroed = false) {
   const Dm& m = n.m;
   sgg_gemm_desc_t g = gd_zero();
   g.A = n.w.CH + n.t2(t) * n.sCH() + (long long)row0 * 2 * m.H; g.a_rows = nrows; g.a_cols = 2 * m.H; g.a_ld = 2 * m.H;
@@ -345,11 +345,12 @@ static int net_scores(const Net& n, int t, int row0, int nrows, bool tangent) {
     g.bias = n.theta + n.L.batt;
     g.addm = n.w.P; g.ld_addm = m.RP; g.add_mod = m.B;   // row0 is a multiple of B
   }
+  if (prezeroed) g.atomic = 2;   // the preceding cell kernel cleared these rows (ZeroRow)
   return gemm(g, n.st);
 }
 
 // q = [z,u,h] K for rows [row0, row0+nrows) of step t.
-static int net_gates(const Net& n, int t, int row0, int nrows) {
+static int net_gates(const Net& n, int t, int row0, int nrows, bool prezeroed = false) {
   const Dm& m = n.m;
   sgg_gemm_desc_t g = gd_zero();
   g.A = n.w.X + n.t2(t) * n.sX() + (long long)row0 * 2 * n.KXP; g.a_rows = nrows; g.a_cols = 2 * n.KXP; g.a_ld = 2 * n.KXP;
@@ -357,6 +358,7 @@ static int net_gates(const Net& n, int t, int row0, int nrows) {
   g.M = nrows; g.N = 4 * m.H;
   segs_act_weight(g, 0, n.KXP, n.L.rK, true, n.KXP);
   g.C = n.w.Q + n.t1(t) * n.sQ() + (long long)row0 * 4 * m.H; g.ldc = 4 * m.H;
+  if (prezeroed) g.atomic = 2;   // the attention kernel in front cleared these rows
   return gemm(g, n.st);
 }
 
@@ -364,16 +366,18 @@ static int net_gates(const Net& n, int t, int row0, int nrows) {
 static int net_forward_step(const Net& n, int t, int nblk) {
   const Dm& m = n.m;
   const int rows = nblk * m.B;
-  SGG_TRY(net_scores(n, t, 0, rows, false));
+  SGG_TRY(net_scores(n, t, 0, rows, false, /*prezeroed=*/t > 0));
   AttnFwdParams ap{};
   ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk; ap.early_a = t_ann_static;
   for (int v = 0; v < nblk; ++v) { ap.row_blk[v] = v; ap.e_blk[v] = v; }
   ap.E = n.w.EA + n.t1(t) * n.sEA(); ap.ldE = m.RP;
   ap.alpha_out = n.w.EA + n.t1(t) * n.sEA(); ap.ldA = m.RP;
   ap.X = n.w.X + n.t2(t) * n.sX(); ap.ldX = 2 * n.KXP; ap.lo_off = n.KXP;
+  ap.zero_p = n.w.Q + n.t1(t) * n.sQ(); ap.zero_ld = 4 * m.H; ap.zero_cols = 4 * m.H;
   SGG_TRY(attn_fwd(ap, 0, n.st));
-  SGG_TRY(net_gates(n, t, 0, rows));
+  SGG_TRY(net_gates(n, t, 0, rows, true));
   LstmFwdParams lp{};
+  if (t + 1 < m.T) lp.zero = ZeroRow{n.w.EA + n.t1(t + 1) * n.sEA(), m.RP, m.RP};
   lp.nrows = rows;
   lp.Q = n.w.Q + n.t1(t) * n.sQ(); lp.ldQ = 4 * m.H;
   lp.Cin = n.w.Cf + n.t2(t) * n.sCf();
@@ -399,7 +403,7 @@ static int net_tangent(const Net& n, int pblk, int tblk) {
   const Dm& m = n.m;
   for (int t = 0; t < m.T; ++t) {
     if (t > 0) {  // cdot_0 = 0 => edot_0 = adot_0 = zdot_0 = 0 (z columns of X[0] tangent rows stay zero)
-      SGG_TRY(net_scores(n, t, tblk * m.B, m.B, true));
+      SGG_TRY(net_scores(n, t, tblk * m.B, m.B, true, true));   // cleared by lstm_tan of step t-1
       AttnFwdParams ap{};
       ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = 1; ap.early_a = t_ann_static;
       ap.row_blk[0] = tblk; ap.e_blk[0] = 0; ap.ain_blk = pblk;
@@ -407,10 +411,12 @@ static int net_tangent(const Net& n, int pblk, int tblk) {
       ap.alpha_in = n.w.EA + t * n.sEA();
       ap.alpha_out = n.w.EA + t * n.sEA(); ap.ldA = m.RP;
       ap.X = n.w.X + t * n.sX(); ap.ldX = 2 * n.KXP; ap.lo_off = n.KXP;
+      ap.zero_p = n.w.Q + t * n.sQ(); ap.zero_ld = 4 * m.H; ap.zero_cols = 4 * m.H;
       SGG_TRY(attn_fwd(ap, 1, n.st));
     }
-    SGG_TRY(net_gates(n, t, tblk * m.B, m.B));
+    SGG_TRY(net_gates(n, t, tblk * m.B, m.B, t > 0));
     LstmTanParams lp{};
+    if (t + 1 < m.T) lp.zero = ZeroRow{n.w.ED + (long long)(t + 1) * m.B * m.RP, m.RP, m.RP};
     lp.nrows = m.B; lp.prow0 = pblk * m.B; lp.trow0 = tblk * m.B;
     lp.Q = n.w.Q + t * n.sQ(); lp.ldQ = 4 * m.H;
     lp.C = n.w.Cf + t * n.sCf();
@@ -440,7 +446,7 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
   const int row0 = rc.blk0 * m.B;
   const int nrows_p = rc.nblk * m.B;                       // primal rows
   const int nrows_all = nrows_p + (tan ? m.B : 0);         // tangent block directly follows
-  if (rc.wgrad) SGG_CUDA(cudaMemsetAsync(n.w.PB, 0, (size_t)m.B * m.RP * 4, n.st));
+  if (rc.wgrad) SGG_TRY(zero_2d(n.w.PB, (long long)m.B * m.RP, (long long)m.B * m.RP, 1, n.st));
   for (int t = m.T - 1; t >= 0; --t) {
     const bool last = (t == m.T - 1);
     LstmRevParams lp{};
@@ -457,6 +463,7 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
     lp.QB = n.w.QB + t * n.sQB(); lp.ldQB = 8 * m.H; lp.qb_lo = 4 * m.H;
     lp.CB = n.w.CB + t * n.sCf();
     if (rc.wgrad) { lp.partials = n.lnp; lp.init_partials = last ? 1 : 0; }
+    lp.zero = ZeroRow{n.w.XB + t * n.sXB(), n.KXP, n.KXP};   // x_bar rows of this step: the GEMM below accumulates into them
     // first-order rows, then the (interp, tangent) pair, in one launch
     lp.n_plain = (tan ? (rc.tan_pblk - rc.blk0) : rc.nblk) * m.B; lp.prow0 = row0;
     lp.n_tan = tan ? m.B : 0; lp.tan_prow0 = tan ? rc.tan_pblk * m.B : 0; lp.trow0 = tan ? rc.tan_blk * m.B : 0;
@@ -468,7 +475,7 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
       g.B = n.sh + n.L.sK; g.b_rows = 2LL * n.L.rK; g.b_cols = 4 * m.H; g.b_ld = n.L.pK; g.b_mn_major = 0;
       g.M = nrows_all; g.N = n.L.KX;
       segs_act_weight(g, 0, 4 * m.H, n.L.rK, false, 4 * m.H);
-      g.C = n.w.XB + t * n.sXB() + (long long)row0 * n.KXP; g.ldc = n.KXP;
+      g.C = n.w.XB + t * n.sXB() + (long long)row0 * n.KXP; g.ldc = n.KXP; g.atomic = 2;
       SGG_TRY(gemm(g, n.st));
     }
     if (t == 0 && !rc.wgrad) break;  // data path: nothing upstream of the step-0 attention is needed
@@ -826,9 +833,14 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   const float invBT = 1.0f / ((float)B * a->world * T);
   {  // the dW_a block (first R*C*R floats of the bucket) is overwritten by its GEMM; everything else accumulates
     const long long skip = (long long)m.R * m.C * m.R;
-    SGG_CUDA(cudaMemsetAsync(a->d_grad + skip, 0, (size_t)(d.L.total - skip) * 4, st));
+    ZeroList zl;
+    if (zl.add(a->d_grad + skip, (d.L.total - skip) * 4) && zl.add(scalars, 16)) {
+      SGG_TRY(zero_fill(zl, st));
+    } else {
+      SGG_CUDA(cudaMemsetAsync(a->d_grad + skip, 0, (size_t)(d.L.total - skip) * 4, st));
+      SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
+    }
   }
-  SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
   // 2. embeddings of the three streams
   SGG_TRY(embed_dense(d, w, fake));
   EmbedMixParams em{};
@@ -855,10 +867,16 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   {
     // The tangent state at t = 0 is zero (c0/h0 do not depend on the triples); the generator step uses
     // the same workspace with another row count, so clear those rows explicitly.
-    SGG_CUDA(cudaMemsetAsync(d.w.X + 3LL * B * 2 * d.KXP, 0, (size_t)B * 2 * d.KXP * 2, st));
-    SGG_CUDA(cudaMemsetAsync(d.w.Cf + 3LL * B * m.H, 0, (size_t)B * m.H * 4, st));
-    SGG_CUDA(cudaMemsetAsync(d.w.CH + 3LL * B * 2 * m.H, 0, (size_t)B * 2 * m.H * 2, st));
-    SGG_CUDA(cudaMemsetAsync(d.w.ED, 0, (size_t)B * m.RP * 4, st));
+    ZeroList zl;
+    if (zl.add(d.w.X + 3LL * B * 2 * d.KXP, (long long)B * 2 * d.KXP * 2) && zl.add(d.w.Cf + 3LL * B * m.H, (long long)B * m.H * 4) &&
+        zl.add(d.w.CH + 3LL * B * 2 * m.H, (long long)B * 2 * m.H * 2) && zl.add(d.w.ED, (long long)B * m.RP * 4)) {
+      SGG_TRY(zero_fill(zl, st));
+    } else {
+      SGG_CUDA(cudaMemsetAsync(d.w.X + 3LL * B * 2 * d.KXP, 0, (size_t)B * 2 * d.KXP * 2, st));
+      SGG_CUDA(cudaMemsetAsync(d.w.Cf + 3LL * B * m.H, 0, (size_t)B * m.H * 4, st));
+      SGG_CUDA(cudaMemsetAsync(d.w.CH + 3LL * B * 2 * m.H, 0, (size_t)B * 2 * m.H * 2, st));
+      SGG_CUDA(cudaMemsetAsync(d.w.ED, 0, (size_t)B * m.RP * 4, st));
+    }
     PackParams pk{};
     pk.rows = T * B; pk.cols = m.V; pk.src = w.DFAKE; pk.ld = m.VP;
     pk.scale = w.coef; pk.smod = B;
@@ -938,9 +956,14 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   const float invBT = 1.0f / ((float)B * a->world * T);
   {
     const long long skip = (long long)m.R * m.C * m.R;   // dW_a is overwritten by its GEMM
-    SGG_CUDA(cudaMemsetAsync(a->g_grad + skip, 0, (size_t)(g.L.total - skip) * 4, st));
+    ZeroList zl;
+    if (zl.add(a->g_grad + skip, (g.L.total - skip) * 4) && zl.add(scalars, 16)) {
+      SGG_TRY(zero_fill(zl, st));
+    } else {
+      SGG_CUDA(cudaMemsetAsync(a->g_grad + skip, 0, (size_t)(g.L.total - skip) * 4, st));
+      SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
+    }
   }
-  SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
   SGG_TRY(gen_forward(g, w, noise, 1, 0, recompute_proj, a->logits_out));
   // D(fake), single stream
   SGG_TRY(embed_dense(d, w, fake_slot(w, m, 0)));
