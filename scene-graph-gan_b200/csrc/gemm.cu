@@ -16,9 +16,10 @@ constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 // Zero-fill as a KERNEL (not a memset node): it takes part in the programmatic-dependent-launch chain, so the launch
-// of the kernel behind it still overlaps, which a memset node in the middle of the chain prevents.  Up to 4 pitched
+// of the kernel behind it still overlaps, which a memset node in the middle of the chain prevents.  Up to 8 pitched
 // regions per launch; widths / pitches / pointers in multiples of 16 bytes.
-struct ZeroSegs { void* p[4]; long long pitch16[4], width16[4], rows[4]; long long start[5]; int n; };
+constexpr int ZERO_MAX_SEG = 8;
+struct ZeroSegs { void* p[ZERO_MAX_SEG]; long long pitch16[ZERO_MAX_SEG], width16[ZERO_MAX_SEG], rows[ZERO_MAX_SEG]; long long start[ZERO_MAX_SEG + 1]; int n; };
 __global__ void __launch_bounds__(256) zero_kernel(const ZeroSegs z) {
   pdl_trigger();
   pdl_wait();
@@ -35,7 +36,7 @@ struct ZeroList {
   ZeroSegs z{};
   // returns false when the region cannot be expressed in 16-byte units (caller falls back to cudaMemset*Async)
   bool add(void* p, long long pitch_bytes, long long width_bytes, long long rows) {
-    if (z.n >= 4 || (reinterpret_cast<uintptr_t>(p) & 15) || (pitch_bytes & 15) || (width_bytes & 15)) return false;
+    if (z.n >= ZERO_MAX_SEG || (reinterpret_cast<uintptr_t>(p) & 15) || (pitch_bytes & 15) || (width_bytes & 15)) return false;
     z.p[z.n] = p; z.pitch16[z.n] = pitch_bytes / 16; z.width16[z.n] = width_bytes / 16; z.rows[z.n] = rows;
     z.start[z.n + 1] = z.start[z.n] + rows * (width_bytes / 16);
     ++z.n;
@@ -414,6 +415,9 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
     // epilogue per output column, and a penalty for split-K (output memset node + fp32 reductions).
     double best = 1e30;
     int best_bn = 128, best_sp = 1;
+    static double split_penalty_env = -1.0;   // SGG_SPLIT_PENALTY (cycles) overrides the fitted constant (tuning aid)
+    if (split_penalty_env < 0.0) { const char* e = getenv("SGG_SPLIT_PENALTY"); split_penalty_env = e ? atof(e) : 0.0; }
+    const double split_penalty = split_penalty_env > 0.0 ? split_penalty_env : 6370.0;
     const int bn_lo = d.block_n ? d.block_n : 64, bn_hi = d.block_n ? d.block_n : 256;
     for (int b = bn_lo; b <= bn_hi; b *= 2) {
       if (b > 64 && d.N <= b / 2 && !d.block_n) continue;         // do not pad N by more than 2x
@@ -432,7 +436,7 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
         const double stage_b = (double)kp.nA * A_STAGE_BYTES + (double)kp.nB * b * BK * 2;
         const double kb_cyc = fmax(stage_b / feed, nprod * 1.93 * b);   // TMA-bound vs MMA-bound k-block
         const double epi = 3140.0 + 69.0 * b * (sp > 1 ? 0.2 : 1.0);
-        const double cost = waves * (8885.0 + kb_per * kb_cyc + epi) + (sp > 1 ? 6370.0 : 0.0);
+        const double cost = waves * (8885.0 + kb_per * kb_cyc + epi) + (sp > 1 ? split_penalty : 0.0);
         if (cost < best) { best = cost; best_bn = b; best_sp = sp; }
       }
     }

@@ -363,10 +363,10 @@ static int net_gates(const Net& n, int t, int row0, int nrows, bool prezeroed = 
 }
 
 // One primal forward step (scores, attention, gates, cell) for stream blocks [0, nblk).
-static int net_forward_step(const Net& n, int t, int nblk) {
+static int net_forward_step(const Net& n, int t, int nblk, bool ea0_prezeroed = false) {
   const Dm& m = n.m;
   const int rows = nblk * m.B;
-  SGG_TRY(net_scores(n, t, 0, rows, false, /*prezeroed=*/t > 0));
+  SGG_TRY(net_scores(n, t, 0, rows, false, /*prezeroed=*/t > 0 || ea0_prezeroed));
   AttnFwdParams ap{};
   ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk; ap.early_a = t_ann_static;
   for (int v = 0; v < nblk; ++v) { ap.row_blk[v] = v; ap.e_blk[v] = v; }
@@ -393,13 +393,13 @@ static int net_forward_step(const Net& n, int t, int nblk) {
 }
 
 // Primal forward over T steps for stream blocks [0, nblk).  Needs: X[t] u-columns filled, P, state 0.
-static int net_forward(const Net& n, int nblk) {
-  for (int t = 0; t < n.m.T; ++t) SGG_TRY(net_forward_step(n, t, nblk));
+static int net_forward(const Net& n, int nblk, bool ea0_prezeroed = false) {
+  for (int t = 0; t < n.m.T; ++t) SGG_TRY(net_forward_step(n, t, nblk, ea0_prezeroed));
   return 0;
 }
 
 // Tangent forward (D only): tangent rows are block `tblk`, their primal partner block `pblk`.
-static int net_tangent(const Net& n, int pblk, int tblk) {
+static int net_tangent(const Net& n, int pblk, int tblk, bool q0_prezeroed = false) {
   const Dm& m = n.m;
   for (int t = 0; t < m.T; ++t) {
     if (t > 0) {  // cdot_0 = 0 => edot_0 = adot_0 = zdot_0 = 0 (z columns of X[0] tangent rows stay zero)
@@ -414,7 +414,7 @@ static int net_tangent(const Net& n, int pblk, int tblk) {
       ap.zero_p = n.w.Q + t * n.sQ(); ap.zero_ld = 4 * m.H; ap.zero_cols = 4 * m.H;
       SGG_TRY(attn_fwd(ap, 1, n.st));
     }
-    SGG_TRY(net_gates(n, t, tblk * m.B, m.B, t > 0));
+    SGG_TRY(net_gates(n, t, tblk * m.B, m.B, t > 0 || q0_prezeroed));
     LstmTanParams lp{};
     if (t + 1 < m.T) lp.zero = ZeroRow{n.w.ED + (long long)(t + 1) * m.B * m.RP, m.RP, m.RP};
     lp.nrows = m.B; lp.prow0 = pblk * m.B; lp.trow0 = tblk * m.B;
@@ -619,7 +619,7 @@ static int gen_forward(const Net& g, const Ws& w, const float* noise, int ns, in
 }
 
 // u = x W_emb for a dense [T*B, 2*VP] hi/lo input; result fp32 in w.UF
-static int embed_dense(const Net& d, const Ws& w, const __nv_bfloat16* xhl) {
+static int embed_dense(const Net& d, const Ws& w, const __nv_bfloat16* xhl, bool prezeroed = false) {
   const Dm& m = d.m;
   sgg_gemm_desc_t g = gd_zero();
   g.A = xhl; g.a_rows = (long long)m.T * m.B; g.a_cols = 2 * m.VP; g.a_ld = 2 * m.VP;
@@ -627,6 +627,7 @@ static int embed_dense(const Net& d, const Ws& w, const __nv_bfloat16* xhl) {
   g.M = m.T * m.B; g.N = m.E;
   segs_act_weight(g, 0, m.VP, d.L.rWemb, true, m.VP);
   g.C = w.UF; g.ldc = m.EP;
+  if (prezeroed) g.atomic = 2;   // UF was cleared by the caller's zero-fill list
   return gemm(g, d.st);
 }
 
@@ -831,18 +832,23 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
   const float invBT = 1.0f / ((float)B * a->world * T);
+  bool pre_uf = false, pre_ea0 = false;
   {  // the dW_a block (first R*C*R floats of the bucket) is overwritten by its GEMM; everything else accumulates
     const long long skip = (long long)m.R * m.C * m.R;
+    // one zero-fill launch for everything this step accumulates into before its first reverse pass: the gradient
+    // bucket, the loss scalars, the embedding GEMM's output and the step-0 scores of the three streams
     ZeroList zl;
-    if (zl.add(a->d_grad + skip, (d.L.total - skip) * 4) && zl.add(scalars, 16)) {
+    if (zl.add(a->d_grad + skip, (d.L.total - skip) * 4) && zl.add(scalars, 16) &&
+        zl.add(w.UF, (long long)T * B * m.EP * 4) && zl.add(d.w.EA, 3LL * B * m.RP * 4)) {
       SGG_TRY(zero_fill(zl, st));
+      pre_uf = pre_ea0 = true;
     } else {
       SGG_CUDA(cudaMemsetAsync(a->d_grad + skip, 0, (size_t)(d.L.total - skip) * 4, st));
       SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
     }
   }
   // 2. embeddings of the three streams
-  SGG_TRY(embed_dense(d, w, fake));
+  SGG_TRY(embed_dense(d, w, fake, pre_uf));
   EmbedMixParams em{};
   em.B = B; em.T = T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
   em.labels = a->labels; em.Wemb = a->d_theta + d.L.Wemb; em.gp_alpha = gp_alpha;
@@ -853,7 +859,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   if (!(pre && pre->have_proj)) SGG_TRY(net_attn_proj(d));
   if (!(pre && pre->state_ready)) SGG_TRY(net_init_state(d, 3));
   if (pre && pre->have_proj && pre->proj_stream != st) SGG_TRY(side_join(st, pre->proj_stream));
-  SGG_TRY(net_forward(d, 3));
+  SGG_TRY(net_forward(d, 3, pre_ea0));
   LossParams lp{B, T, d.w.Y, 0, 1, invBT, scalars};
   SGG_TRY(losses(lp, st));
   // 4. g = d sum D(x_hat) / d x_hat : data-path reverse on the interp block
@@ -868,9 +874,12 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     // The tangent state at t = 0 is zero (c0/h0 do not depend on the triples); the generator step uses
     // the same workspace with another row count, so clear those rows explicitly.
     ZeroList zl;
+    bool pre_t = false;
     if (zl.add(d.w.X + 3LL * B * 2 * d.KXP, (long long)B * 2 * d.KXP * 2) && zl.add(d.w.Cf + 3LL * B * m.H, (long long)B * m.H * 4) &&
-        zl.add(d.w.CH + 3LL * B * 2 * m.H, (long long)B * 2 * m.H * 2) && zl.add(d.w.ED, (long long)B * m.RP * 4)) {
-      SGG_TRY(zero_fill(zl, st));
+        zl.add(d.w.CH + 3LL * B * 2 * m.H, (long long)B * 2 * m.H * 2) && zl.add(d.w.ED, (long long)B * m.RP * 4) &&
+        zl.add(w.UF, (long long)T * B * m.EP * 4) && zl.add(d.w.Q + 3LL * B * 4 * m.H, (long long)B * 4 * m.H * 4)) {
+      SGG_TRY(zero_fill(zl, st));   // also: the tangent embedding GEMM's output and the step-0 gate rows of the tangent block
+      pre_t = true;
     } else {
       SGG_CUDA(cudaMemsetAsync(d.w.X + 3LL * B * 2 * d.KXP, 0, (size_t)B * 2 * d.KXP * 2, st));
       SGG_CUDA(cudaMemsetAsync(d.w.Cf + 3LL * B * m.H, 0, (size_t)B * m.H * 4, st));
@@ -882,13 +891,13 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     pk.scale = w.coef; pk.smod = B;
     pk.dst = w.VHL; pk.ldd = 2 * m.VP; pk.lo_off = m.VP;
     SGG_TRY(pack_hl(pk, st));
-    SGG_TRY(embed_dense(d, w, w.VHL));
+    SGG_TRY(embed_dense(d, w, w.VHL, pre_t));
     EmbedMixParams et{};
     et.B = B; et.T = T; et.E = m.E; et.Uf = w.UF; et.ldUf = m.EP;
     et.blk_fake = 3; et.blk_real = -1; et.blk_int = -1;
     et.X = d.w.X; et.ldX = 2 * d.KXP; et.x_lo = d.KXP; et.strideT = d.sX(); et.uoff = d.uoff;
     SGG_TRY(embed_mix(et, st));
-    SGG_TRY(net_tangent(d, 2, 3));
+    SGG_TRY(net_tangent(d, 2, 3, pre_t));
   }
   // 6. one reverse pass over the three primal streams and the tangent
   RevCfg rv{};
