@@ -367,7 +367,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     configured = true;
   }
   dim3 grid((kp.M + BM * MT - 1) / (BM * MT), (kp.N + BN - 1) / BN, splits);
-  const int smem = kp.stages * kp.stage_bytes + 1024 + 256;
+  int smem = kp.stages * kp.stage_bytes + 1024 + 256;
+  {  // A single-wave grid runs faster with one CTA per SM (measured: two co-resident small-tile CTAs share the SM's
+     // operand feed while other SMs idle; scores GEMM 14.2 -> 9.7 us): pad the shared-memory request past half an SM.
+     // SGG_GEMM_MIN_SMEM (bytes) overrides the padding (0 disables it).
+    static int min_smem = -1;
+    if (min_smem < 0) { const char* e = getenv("SGG_GEMM_MIN_SMEM"); min_smem = e ? atoi(e) : 118000; }
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    if (ctas <= 148 && smem < min_smem) smem = min_smem < gemm_smem_bytes() ? min_smem : gemm_smem_bytes();
+  }
   SGG_LAUNCH(kern, grid, GEMM_THREADS, smem, stream, tmA, tmB, kp);
   return 0;
 }
@@ -398,7 +406,9 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   int bn = d.block_n, splits = d.splits > 1 ? d.splits : 1;
   // B-heavy contractions (single A part, hi/lo B, N <= 256: the two W_a GEMMs): 256-row CTAs with two accumulators, so
   // the wide B tile enters shared memory once per 256 output rows.
-  const bool wide_b = kp.nA == 1 && kp.nB == 2 && d.b_mn_major && d.M >= 2 * BM && d.N > 128 && d.N <= 256 &&
+  static int no_wide = -1;   // SGG_NO_WIDE_B=1: tuning aid
+  if (no_wide < 0) { const char* e = getenv("SGG_NO_WIDE_B"); no_wide = (e && e[0] == '1') ? 1 : 0; }
+  const bool wide_b = !no_wide && kp.nA == 1 && kp.nB == 2 && d.b_mn_major && d.M >= 2 * BM && d.N > 128 && d.N <= 256 &&
                       (d.block_n == 0 || d.block_n == 256);
   const int mt = wide_b ? 2 : 1;
   kp.b_stream = (wide_b && !d.a_mn_major && l2_policy_enabled()) ? 1 : 0;   // K1: W_a is read once per pass
@@ -456,6 +466,11 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   kp.stage_bytes = kp.nA * mt * A_STAGE_BYTES + kp.nB * bn * BK * 2;
   kp.stages = GEMM_SMEM_BUDGET / kp.stage_bytes;
   if (kp.stages > GEMM_MAX_STAGES) kp.stages = GEMM_MAX_STAGES;
+  {
+    static int cap = -1;   // SGG_GEMM_MAX_STAGES: tuning aid
+    if (cap < 0) { const char* e = getenv("SGG_GEMM_MAX_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && kp.stages > cap) kp.stages = cap;
+  }
   const int kb_per = (kp.total_kb + splits - 1) / splits;
   if (kp.stages > kb_per) kp.stages = kb_per < 1 ? 1 : kb_per;
   CUtensorMap tmA, tmB;

@@ -295,6 +295,8 @@ static void segs_act_weight(sgg_gemm_desc_t& g, int a0, int a_lo, int b_lo, bool
 
 static sgg_gemm_desc_t gd_zero() { sgg_gemm_desc_t g; memset(&g, 0, sizeof(g)); g.alpha = 1.0f; return g; }
 int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream);
+struct AdamProjParams;
+int adam_proj(const AdamProjParams& p, const void* ann, cudaStream_t stream);
 
 // K1: P = flat(a) W_a  (bias is added where P is consumed); hoisted out of the time loop (gen:14-15).
 // lane: communicator lane (= stream) of the sharded variant's reduce-scatter.
@@ -1151,17 +1153,35 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
   // right behind the W_a update on the side stream, where it overlaps the main stream's weight-gradient GEMMs; the
   // side stream is then joined by the next pass just before its first scores GEMM instead of here.
   auto optimise = [&](int net, float* theta, float* grad, float* mm, float* vv, void* shadow, long long step_mul,
-                      long long step_add, cudaStream_t s1, bool next_proj, cudaStream_t* pending) -> int {
+                      long long step_add, cudaStream_t s1, bool next_proj, cudaStream_t* pending, bool last_critic) -> int {
     const ParamLayout L = param_layout(net == 0, dd);
     const long long n_wa = (long long)m.R * m.C * m.R;
     if (s1 != st && !side_ok) { SGG_TRY(side_join(st, s1)); s1 = st; }
-    if (shard) {   // this rank's rows of dW_a are already sums over the global batch: no exchange, 1/world of the update
+    static int fuse_env = -1;   // SGG_FUSED_ADAM_PROJ=0 keeps the Adam update of W_a and the next projection as two kernels
+    if (fuse_env < 0) { const char* e = getenv("SGG_FUSED_ADAM_PROJ"); fuse_env = (e && e[0] == '0') ? 0 : 1; }
+    bool fused = false;
+    if (fuse_env && next_proj && net == 1 && !shard && !it->comm && m.B <= 256 && (m.R & 3) == 0 &&
+        ((long long)m.R * m.C) % 64 == 0) {
+      // Adam on W_a and the next pass's P = flat(a_d) W_a in one kernel (adamproj.cu): the updated weights go from
+      // registers into the MMA operand; the hi/lo shadow is only written for the pass that will see new annotations
+      AdamProjParams ap{};
+      ap.theta = theta + L.Watt; ap.grad = grad + L.Watt; ap.m = mm + L.Watt; ap.v = vv + L.Watt;
+      ap.shadow = (__nv_bfloat16*)shadow + L.sWa; ap.pitch = L.pAtt; ap.lo_off = (long long)L.rWa * L.pAtt;
+      ap.write_shadow = last_critic ? 1 : 0;
+      ap.lr = hp.lr; ap.b1 = hp.b1; ap.b2 = hp.b2; ap.eps = hp.eps;
+      ap.iter = iter; ap.step_mul = step_mul; ap.step_add = step_add;
+      ap.R = m.R; ap.total_kb = (int)((long long)m.R * m.C / 64); ap.M = m.B;
+      ap.P = w.d.P; ap.ldP = m.RP;
+      SGG_TRY(zero_2d(w.d.P, m.RP, m.R, m.B, s1));
+      SGG_TRY(adam_proj(ap, a->ann_d, s1));
+      fused = true;
+    } else if (shard) {   // this rank's rows of dW_a are already sums over the global batch: no exchange, 1/world of the update
       SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1, sc.rank * sc.Ks, sc.Ks));
     } else {
       if (it->comm) SGG_TRY(comm_allreduce(it->comm, grad, n_wa, s1, s1 != st ? 1 : 0));
       SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1));
     }
-    if (next_proj) {
+    if (next_proj && !fused) {
       const Net dn = make_net(false, dd, a->d_theta, a->d_shadow, nullptr, a->ann_d, w.d, m.B, s1);
       SGG_TRY(net_attn_proj(dn, s1 != st ? 1 : 0));
     }
@@ -1184,7 +1204,7 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
                            use_side ? &s1 : nullptr, &pre));
     cudaStream_t pending = st;
     SGG_TRY(optimise(1, const_cast<float*>(a->d_theta), a->d_grad, it->d_m, it->d_v, const_cast<void*>(a->d_shadow), nc, i + 1, s1,
-                     prefetch_proj != 0, &pending));
+                     prefetch_proj != 0, &pending, i == nc - 1));
     pre.have_proj = prefetch_proj != 0; pre.proj_stream = pending;
     pre.state_ready = true;                  // same batch, same row layout: c0 = h0 stay valid for the next critic step
   }
@@ -1194,7 +1214,7 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
     SGG_TRY(gen_step_core(a, w, it->noise_all + (long long)nc * m.B * m.C, fresh, it->scalars_all + 4 * nc, st,
                           use_side ? &s1 : nullptr, &pre));
     SGG_TRY(optimise(0, const_cast<float*>(a->g_theta), a->g_grad, it->g_m, it->g_v, const_cast<void*>(a->g_shadow), 1, 1, s1,
-                     false, nullptr));
+                     false, nullptr, false));
   }
   return bump_counter(reinterpret_cast<long long*>(it->counters), st);
 }

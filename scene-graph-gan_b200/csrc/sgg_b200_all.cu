@@ -4,5 +4,6 @@
 #include "attn.cu"
 #include "lstm.cu"
 #include "misc.cu"
+#include "adamproj.cu"
 #include "plan.cu"
 #include "comm.cu"

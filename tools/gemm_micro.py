@@ -16,7 +16,7 @@ def main():
     dev = "cuda"
     torch.manual_seed(0)
 
-    def run(tag, M, N, K, a_mn, b_mn, nprod, splits, block_n, atomic=False, addm=False, hl=False, reps=40):
+    def run(tag, M, N, K, a_mn, b_mn, nprod, splits, block_n, atomic=False, addm=False, hl=False, reps=40, bparts=False):
         KP = (K + 63) // 64 * 64
         # operands as hi/lo pairs laid out like the plan does: A [M, 2*KP] (or [2*KP... for mn-major [K, 2*MP])
         if not a_mn:
@@ -35,7 +35,9 @@ def main():
             Bm = torch.randn(2 * KP, NP8, device=dev).bfloat16()
             b_seg = [(0, 0), (KP, 0)]
         segs = [(a_seg[0][0], a_seg[0][1], b_seg[0][0], b_seg[0][1], K)]
-        if nprod >= 2:
+        if bparts:      # single A part, hi/lo B (the W_a contractions)
+            segs.append((a_seg[0][0], a_seg[0][1], b_seg[1][0], b_seg[1][1], K))
+        elif nprod >= 2:
             segs.append((a_seg[1][0], a_seg[1][1], b_seg[0][0], b_seg[0][1], K))
         if nprod >= 3:
             segs.append((a_seg[0][0], a_seg[0][1], b_seg[1][0], b_seg[1][1], K))
@@ -71,30 +73,37 @@ def main():
         os.environ["SGG_PDL"] = pdl   # read once per process: only the first value is effective
         break
     print("PDL", os.environ.get("SGG_PDL"))
-    # fixed-cost probe: tiny K, growing K
-    for K in (64, 128, 256, 512, 1024, 2048):
-        run("probe 1 tile-row", 128, 64, K, False, True, 1, 1, 64)
-    for K in (64, 512, 2048):
-        run("probe 3 products", 128, 64, K, False, True, 3, 1, 64)
-    # scores: e = P + c W_h  (M=3B, N=196, K=512)
-    for sp, bn in ((0, 0), (1, 64), (1, 128), (1, 256), (2, 64), (4, 64)):
-        run("scores (auto=0/0)", 768, 196, 512, False, True, 3, sp, bn, addm=True)
-    # gates: q = x K (M=3B, N=2048, K=1344)
-    for sp, bn in ((0, 0), (1, 256), (1, 128), (2, 256), (3, 256), (2, 128)):
-        run("gates M=768", 768, 2048, 1344, False, True, 3, sp, bn)
-    for sp, bn in ((0, 0), (1, 256), (1, 128), (4, 256), (7, 256), (2, 128), (4, 128)):
-        run("gates M=256 (tangent)", 256, 2048, 1344, False, True, 3, sp, bn)
-    # x_bar = q_bar K^T (M=4B, N=1324, K=2048), weight K-major
-    for sp, bn in ((0, 0), (1, 256), (1, 128), (2, 256), (2, 128), (3, 128)):
-        run("x_bar M=1024", 1024, 1324, 2048, False, False, 3, sp, bn)
-    for sp, bn in ((0, 0), (1, 128), (2, 128), (4, 128), (4, 256), (8, 256)):
-        run("x_bar M=256", 256, 1324, 2048, False, False, 3, sp, bn)
-    # dK = X^T QB (M=1324, N=2048, K=3072) mn/mn
-    for sp, bn in ((0, 0), (1, 256), (2, 256), (3, 256), (5, 256), (3, 128)):
-        run("dK", 1324, 2048, 3072, True, True, 3, sp, bn, atomic=True)
-    # logits h W_dec for 5 streams (M=3840, N=2000, K=512) hi/lo out
-    for sp, bn in ((0, 0), (1, 256), (1, 128)):
-        run("logits", 3840, 2000, 512, False, True, 3, sp, bn, hl=True)
+    # sweep (splits, block_n) for the shapes of the time loop; atomic=2 = output cleared by the producer kernel (no zero-fill launch)
+    sweeps = [
+        ("scores M=768", 768, 196, 512, False, True, dict(addm=True, atomic=2)),
+        ("scores M=256", 256, 196, 512, False, True, dict(addm=True, atomic=2)),
+        ("gates M=768", 768, 2048, 1344, False, True, dict(atomic=2)),
+        ("gates M=256", 256, 2048, 1344, False, True, dict(atomic=2)),
+        ("gates G M=1280", 1280, 2048, 1536, False, True, dict(atomic=2)),
+        ("x_bar M=1024", 1024, 1324, 2048, False, False, dict(atomic=2)),
+        ("x_bar M=256", 256, 1324, 2048, False, False, dict(atomic=2)),
+        ("c_bar M=1024", 1024, 512, 256, False, False, dict(atomic=1)),
+        ("c_bar M=256", 256, 512, 256, False, False, dict(atomic=1)),
+        ("dK", 1324, 2048, 3072, True, True, dict(atomic=1)),
+        ("dW_h", 512, 196, 3072, True, True, dict(atomic=1)),
+    ]
+    if os.environ.get("GEMM_MICRO_ONLY") == "dWa":
+        for sp, bn in ((0, 0), (1, 256), (1, 128), (1, 64)):
+            run("dW_a", 100352, 196, 256, True, True, 2, sp, bn, bparts=True, reps=10)
+        return
+    if os.environ.get("GEMM_MICRO_ONLY"):
+        sweeps = [x for x in sweeps if x[0].startswith(os.environ["GEMM_MICRO_ONLY"])]
+    for tag, M, N, K, amn, bmn, kw in sweeps:
+        run(tag + " auto", M, N, K, amn, bmn, 3, 0, 0, **kw)
+        for bn in (64, 128, 256):
+            if bn > 64 and N <= bn // 2:
+                continue
+            for sp in (1, 2, 3, 4, 6, 8):
+                tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+                if tiles * sp > 3 * 148 or sp > (K + 63) // 64:
+                    continue
+                run(tag, M, N, K, amn, bmn, 3, sp, bn, **kw)
+    return
 
 
 if __name__ == "__main__":
