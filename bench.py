@@ -266,6 +266,27 @@ def kernel_rooflines(trainer, args, pk, dev_batches):
     out.append(entry("gemm_kernel_K1 : P = flat(a) W_a (M=B, N=196, K=100352, hi/lo weight)", t, nbytes,
                      "12 back-to-back launches, rotating annotation tensors; W_a hi/lo (79 MB) + annotations (51 MB) per launch"))
 
+    # ---- optimiser-fused projection: Adam on W_a + next P = flat(a) W_a in one pass (adamproj.cu)
+    bucket_d = trainer.eng.d
+    nW = R * 512 * R
+    thf, grf, mf, vf = (torch.zeros(bucket_d.theta.numel(), device=dev) for _ in range(4))
+    thf.copy_(bucket_d.theta)
+    grf.normal_(std=1e-3)
+    shf = torch.empty_like(bucket_d.shadow)
+    Pf = torch.empty(B, 256, dtype=torch.float32, device=dev)
+
+    def adam_proj(i):
+        a = anns[i % len(anns)]
+        check(L.sgg_adam_project(C.c_int(1), C.byref(trainer.eng.dims), C.c_void_p(thf.data_ptr()), C.c_void_p(grf.data_ptr()),
+                                 C.c_void_p(mf.data_ptr()), C.c_void_p(vf.data_ptr()), C.c_void_p(shf.data_ptr()), C.c_int64(i + 1),
+                                 C.c_float(1e-4), C.c_float(0.5), C.c_float(0.9), C.c_float(1e-8), C.c_void_p(a.data_ptr()),
+                                 C.c_void_p(Pf.data_ptr()), C.c_int32(0), stream_ptr()), "sgg_adam_project")
+    if B <= 256:
+        t = _time_launches(adam_proj, 10)
+        nbytes = 28 * nW + B * R * 512 * 2 + 4 * B * R
+        out.append(entry("adam_proj_kernel (Adam on W_a fused with the next P = flat(a) W_a; incl. its zero-fill launch)", t, nbytes,
+                         "10 back-to-back launches; 28 B/param over W_a (551 MB) + one annotation tensor (51 MB) per launch"))
+
     # ---- Adam over the discriminator bucket (+ hi/lo shadow rewrite)
     n = bucket.theta.numel()
     th, gr, mm, vv = (torch.zeros(n, device=dev) for _ in range(4))

@@ -154,6 +154,16 @@ int sgg_adam_step(int net, const sgg_dims_t* d, float* theta, const float* grad,
                   void* shadow, int64_t step, float lr, float beta1, float beta2, float eps,
                   float grad_scale, sgg_stream_t stream);
 
+/* Optimiser-fused attention projection (single GPU, B <= 256, R % 4 == 0): the Adam update of the annotation rows
+ * W_a = attention_perceptron/kernel[0 : R*C, :] (same rule as sgg_adam_step) and, from the updated weights while they
+ * are still on the SM, the hoisted projection  P[b, :] = flat(a)[b, :] W_a  (gen:14-15) of the NEXT pass, by split-K
+ * reduction into P [B, rup(R,64)] fp32 (cleared by the call).  The bf16 hi/lo shadow of W_a is rewritten only when
+ * write_shadow != 0 (a later pass with other annotations needs it).  theta / grad / m / v / shadow are the bucket bases
+ * of network `net`; every other tensor of the bucket is left to sgg_adam_step. */
+int sgg_adam_project(int net, const sgg_dims_t* d, float* theta, const float* grad, float* m, float* v, void* shadow,
+                     int64_t step, float lr, float beta1, float beta2, float eps, const void* ann, float* P,
+                     int32_t write_shadow, sgg_stream_t stream);
+
 /* Philox4x32-10 counter RNG: tf.random_normal (gen:81) / tfgan's random_uniform alpha. */
 int sgg_rng_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream);
 int sgg_rng_fill_uniform(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream);

@@ -119,7 +119,7 @@ SAMPLE_GREEDY, SAMPLE_GUMBEL = 0, 1
 
 # every symbol include/sgg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "sgg_last_error", "sgg_version", "sgg_launch_count", "sgg_timing_report", "sgg_gemm", "sgg_attn_forward", "sgg_attn_reverse", "sgg_param_table", "sgg_refresh_shadow", "sgg_adam_step",
+    "sgg_last_error", "sgg_version", "sgg_launch_count", "sgg_timing_report", "sgg_gemm", "sgg_attn_forward", "sgg_attn_reverse", "sgg_param_table", "sgg_refresh_shadow", "sgg_adam_step", "sgg_adam_project",
     "sgg_rng_fill_normal", "sgg_rng_fill_uniform", "sgg_workspace_bytes", "sgg_gen_forward",
     "sgg_disc_forward", "sgg_disc_step", "sgg_gen_step", "sgg_ws_lookup", "sgg_train_iteration",
     "sgg_comm_unique_id", "sgg_comm_init", "sgg_comm_destroy", "sgg_comm_allreduce_sum",

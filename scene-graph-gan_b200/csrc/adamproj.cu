@@ -21,6 +21,7 @@ struct AdamProjParams {
   float* theta; const float* grad; float* m; float* v;   // the W_a block: [K, R] row-major fp32
   __nv_bfloat16* shadow; int pitch; long long lo_off; int write_shadow;
   float lr, b1, b2, eps;
+  float lr_t;                                            // used when iter == nullptr (host-side step number)
   const long long* iter; long long step_mul, step_add;
   int R, total_kb, M;
   float* P; long long ldP;                               // [M, ldP] fp32, zero-filled by the caller
@@ -120,8 +121,12 @@ adam_proj_kernel(const __grid_constant__ CUtensorMap tmA, const AdamProjParams p
     const int t = threadIdx.x - 64;
     pdl_wait();   // the gradient comes from the preceding kernels
     if (t == 0) {
-      const double step = (double)(p.iter[0] * p.step_mul + p.step_add);
-      *s_lr = (float)((double)p.lr * sqrt(1.0 - pow((double)p.b2, step)) / (1.0 - pow((double)p.b1, step)));
+      float lr_t = p.lr_t;
+      if (p.iter) {
+        const double step = (double)(p.iter[0] * p.step_mul + p.step_add);
+        lr_t = (float)((double)p.lr * sqrt(1.0 - pow((double)p.b2, step)) / (1.0 - pow((double)p.b1, step)));
+      }
+      *s_lr = lr_t;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const float lr_t = *s_lr;

@@ -758,6 +758,28 @@ extern "C" int sgg_adam_step(int net, const sgg_dims_t* d, float* theta, const f
   return adam(p, (cudaStream_t)stream);
 }
 
+// Op-level entry point of the optimiser-fused projection (adamproj.cu), see include/sgg_b200.h.
+extern "C" int sgg_adam_project(int net, const sgg_dims_t* d, float* theta, const float* grad, float* m, float* v, void* shadow,
+                                int64_t step, float lr, float beta1, float beta2, float eps, const void* ann, float* P,
+                                int32_t write_shadow, sgg_stream_t stream) {
+  SGG_CHECK(d && theta && grad && m && v && shadow && ann && P, "sgg_adam_project: null argument");
+  SGG_CHECK(step >= 1, "sgg_adam_project: step must be >= 1");
+  SGG_TRY(check_dims(*d));
+  const ParamLayout L = param_layout(net == 0, *d);
+  const Dm dm = derive(*d);
+  SGG_CHECK(d->B <= 256 && (d->R & 3) == 0, "sgg_adam_project: needs B <= 256 and R %% 4 == 0 (got B=%d R=%d)", d->B, d->R);
+  AdamProjParams ap{};
+  ap.theta = theta + L.Watt; ap.grad = grad + L.Watt; ap.m = m + L.Watt; ap.v = v + L.Watt;
+  ap.shadow = (__nv_bfloat16*)shadow + L.sWa; ap.pitch = L.pAtt; ap.lo_off = (long long)L.rWa * L.pAtt;
+  ap.write_shadow = write_shadow ? 1 : 0;
+  ap.lr = lr; ap.b1 = beta1; ap.b2 = beta2; ap.eps = eps;
+  ap.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
+  ap.R = d->R; ap.total_kb = (int)((long long)d->R * d->C / 64); ap.M = d->B;
+  ap.P = P; ap.ldP = dm.RP;
+  SGG_TRY(zero_2d(P, dm.RP, d->R, d->B, (cudaStream_t)stream));
+  return adam_proj(ap, ann, (cudaStream_t)stream);
+}
+
 extern "C" int sgg_rng_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, sgg_stream_t stream) {
   SGG_CHECK(out || n == 0, "sgg_rng_fill_normal: null output");
   return rng_fill(out, n, seed, offset, 1, (cudaStream_t)stream);

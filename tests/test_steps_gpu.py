@@ -203,6 +203,57 @@ def test_adam_matches_tf_update_rule():
             assert torch.equal(lo, (th - hi.float()).to(torch.bfloat16)), name
 
 
+@pytest.mark.parametrize("B,R", [(5, 24), (130, 196), (256, 60)])
+def test_fused_adam_projection_matches_adam_then_projection(B, R):
+    """sgg_adam_project == sgg_adam_step restricted to W_a followed by P = flat(a) W_a with the UPDATED weights
+    (TF Adam rule train:258-259; projection gen:14-15 in its split form)."""
+    import ctypes as C
+    from sgg_b200._lib import check, lib, stream_ptr
+    from sgg_b200.params import DISC, ParamBucket, make_dims
+    dims = make_dims(B, 3, 50, R)
+    g = torch.Generator().manual_seed(B + R)
+    bk = ParamBucket(DISC, dims)
+    bk.init_reference(3)
+    name, off, rows, cols, soff, pitch = next(e for e in bk.entries if e[0].endswith("attention_perceptron/kernel"))
+    n_wa = R * 512 * R
+    bk.grad[off:off + n_wa] = (torch.randn(n_wa, generator=g) * 1e-3).cuda()
+    bk.m[off:off + n_wa] = (torch.randn(n_wa, generator=g) * 1e-3).cuda()
+    bk.v[off:off + n_wa] = (torch.rand(n_wa, generator=g) * 1e-6).cuda()
+    ann = torch.randn(B, R * 512, generator=g).bfloat16().cuda()
+    th0, m0, v0, gr = (x[off:off + n_wa].double().cpu() for x in (bk.theta, bk.m, bk.v, bk.grad))
+    step, lr, b1, b2, eps = 7, 1e-4, 0.5, 0.9, 1e-8
+    P = torch.full((B, 256), 7.0, device="cuda")                      # must be cleared by the call
+    shadow_before = bk.shadow.clone()
+    check(lib().sgg_adam_project(C.c_int(DISC), C.byref(dims), C.c_void_p(bk.theta.data_ptr()), C.c_void_p(bk.grad.data_ptr()),
+                                 C.c_void_p(bk.m.data_ptr()), C.c_void_p(bk.v.data_ptr()), C.c_void_p(bk.shadow.data_ptr()),
+                                 C.c_int64(step), C.c_float(lr), C.c_float(b1), C.c_float(b2), C.c_float(eps),
+                                 C.c_void_p(ann.data_ptr()), C.c_void_p(P.data_ptr()), C.c_int32(0), stream_ptr()), "adam_project")
+    torch.cuda.synchronize()
+    m1 = b1 * m0 + (1 - b1) * gr
+    v1 = b2 * v0 + (1 - b2) * gr * gr
+    lr_t = lr * math.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+    th1 = th0 - lr_t * m1 / (v1.sqrt() + eps)
+    assert torch.allclose(bk.theta[off:off + n_wa].double().cpu(), th1, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(bk.m[off:off + n_wa].double().cpu(), m1, rtol=1e-5, atol=1e-12)
+    assert torch.allclose(bk.v[off:off + n_wa].double().cpu(), v1, rtol=1e-5, atol=1e-15)
+    ref_P = ann.double().cpu() @ th1.view(R * 512, R)
+    got_P = P[:, :R].double().cpu()
+    assert ((got_P - ref_P).norm() / ref_P.norm()).item() < 1e-4
+    assert torch.equal(bk.shadow, shadow_before)                      # write_shadow = 0 leaves the shadow alone
+    # write_shadow = 1: the hi/lo pair reproduces the updated weights to 2^-17
+    bk.grad[off:off + n_wa].zero_()
+    check(lib().sgg_adam_project(C.c_int(DISC), C.byref(dims), C.c_void_p(bk.theta.data_ptr()), C.c_void_p(bk.grad.data_ptr()),
+                                 C.c_void_p(bk.m.data_ptr()), C.c_void_p(bk.v.data_ptr()), C.c_void_p(bk.shadow.data_ptr()),
+                                 C.c_int64(step + 1), C.c_float(lr), C.c_float(b1), C.c_float(b2), C.c_float(eps),
+                                 C.c_void_p(ann.data_ptr()), C.c_void_p(P.data_ptr()), C.c_int32(1), stream_ptr()), "adam_project")
+    torch.cuda.synchronize()
+    srows = bk.shadow_rows[name]
+    sh = bk.shadow[soff:soff + 2 * srows * pitch].view(2 * srows, pitch)
+    rec = sh[:R * 512, :R].double().cpu() + sh[srows:srows + R * 512, :R].double().cpu()
+    th2 = bk.theta[off:off + n_wa].double().cpu().view(R * 512, R)
+    assert ((rec - th2).abs().max() / th2.abs().max()).item() < 2e-5
+
+
 def test_rng_streams():
     """Philox fills (gen:81 noise, tfgan alpha): moments, range, determinism, offset continuity."""
     import ctypes as C
