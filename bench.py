@@ -487,7 +487,7 @@ def run_sample_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 tensor-core operands (hi/lo split), fp32 accumulate", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[4]: generator-only {args.mode} decoding, batch {B}/GPU, {T // 3} triples (T={T}), "
-                                   f"vocab {V}, chunk {smp.chunk or min(B, 8192)}", "global_batch": B * world, "parallelism": f"dp{world}",
+                                   f"vocab {V}, chunk {smp.chunk or (B // 2 if B >= 2048 else B)}", "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "two alternating 1.6 GB annotation tensors (>> 126 MB L2)"},
             "clocks": clocks, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "whole call (annotation re-reads dominate)", "achieved": ann_bytes * args.steps / secs / 1e9,

@@ -218,7 +218,8 @@ typedef struct sgg_sample_args {
   const void* ann_g;          /* [B,R,C] bf16 annotations */
   const float* noise;         /* [B,C] N(0,1) (gen:81), or NULL: drawn on the device from (seed, offset) */
   int32_t mode;               /* SGG_SAMPLE_GREEDY | SGG_SAMPLE_GUMBEL */
-  int32_t chunk;              /* images per pass (0 = default: min(B, 8192)) */
+  int32_t chunk;              /* images per chunk (0 = default: B/2 when B >= 2048, else B); consecutive chunks
+                                 alternate between `stream` and a library-owned second stream */
   uint64_t seed, offset;      /* Philox key / position of the noise and Gumbel draws */
   void* workspace; int64_t workspace_bytes;   /* sgg_sample_workspace_bytes(dims, chunk) */
   int32_t* tokens_out;        /* [B,T] token ids */

@@ -1249,11 +1249,14 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
 // n-tile to a (max, column) key.
 struct SampleWs {
   float* P; float* noise; unsigned long long* keys;
-  NetWs g;
+  NetWs g[2];      // two chunk workspaces: consecutive chunks alternate between the caller's stream and the side stream
   long long bytes;
 };
+// Default: two chunks per call (B >= 2048), so that the HBM-bound attention steps of one half overlap the tensor-bound
+// GEMMs of the other half on the second stream; small batches run as one chunk.
 static int sample_chunk(const sgg_dims_t& d, int chunk) {
-  int c = chunk > 0 ? chunk : 8192;   // measured (profiles/README.md): the whole-batch plan beats L2-sized chunks
+  int c = chunk > 0 ? chunk : (d.B >= 2048 ? (d.B + 1) / 2 : d.B);
+  if (c > 8192) c = 8192;
   return c < d.B ? c : d.B;
 }
 static SampleWs sample_ws_layout(const sgg_dims_t& d, int chunk, void* base) {
@@ -1266,12 +1269,14 @@ static SampleWs sample_ws_layout(const sgg_dims_t& d, int chunk, void* base) {
   w.P = (float*)take((long long)m.B * m.RP * 4);
   w.noise = (float*)take((long long)m.B * m.C * 4);
   w.keys = (unsigned long long*)take((long long)m.B * m.T * 8);
-  w.g.NRmax = Bc;
-  w.g.X = (__nv_bfloat16*)take(2LL * Bc * 2 * m.KXG * 2);
-  w.g.Cf = (float*)take(2LL * Bc * m.H * 4);
-  w.g.CH = (__nv_bfloat16*)take(2LL * Bc * 2 * m.H * 2);
-  w.g.EA = (float*)take((long long)Bc * m.RP * 4);
-  w.g.Q = (float*)take((long long)Bc * 4 * m.H * 4);
+  for (int i = 0; i < (Bc < m.B ? 2 : 1); ++i) {
+    w.g[i].NRmax = Bc;
+    w.g[i].X = (__nv_bfloat16*)take(2LL * Bc * 2 * m.KXG * 2);
+    w.g[i].Cf = (float*)take(2LL * Bc * m.H * 4);
+    w.g[i].CH = (__nv_bfloat16*)take(2LL * Bc * 2 * m.H * 2);
+    w.g[i].EA = (float*)take((long long)Bc * m.RP * 4);
+    w.g[i].Q = (float*)take((long long)Bc * 4 * m.H * 4);
+  }
   w.bytes = o;
   return w;
 }
@@ -1303,18 +1308,24 @@ extern "C" int sgg_gen_sample(const sgg_sample_args_t* a, sgg_stream_t stream) {
   }
   SGG_CUDA(cudaMemsetAsync(w.keys, 0, (size_t)m.B * m.T * 8, st));
   {  // K1 for the whole batch: W_a streams through the SMs once (tensor-bound at large B)
-    NetWs wa = w.g; wa.P = w.P;
+    NetWs wa = w.g[0]; wa.P = w.P;
     const Net g = make_net(true, dd, a->g_theta, a->g_shadow, nullptr, a->ann_g, wa, m.B, st);
     SGG_TRY(net_attn_proj(g));
   }
-  for (int c0 = 0; c0 < m.B; c0 += Bc) {
+  static int two_streams = -1;   // SGG_SAMPLE_STREAMS=1: every chunk on the caller's stream
+  if (two_streams < 0) { const char* e = getenv("SGG_SAMPLE_STREAMS"); two_streams = (e && e[0] == '1') ? 0 : 1; }
+  cudaStream_t s2 = st;
+  if (two_streams && Bc < m.B) SGG_TRY(side_fork(st, &s2));
+  int ci = 0;
+  for (int c0 = 0; c0 < m.B; c0 += Bc, ++ci) {
+    cudaStream_t sc = (ci & 1) ? s2 : st;
     sgg_dims_t dc = dd;
     dc.B = m.B - c0 < Bc ? m.B - c0 : Bc;
     dc.S = 1;
-    NetWs wc = w.g;
+    NetWs wc = w.g[(Bc < m.B) ? (ci & 1) : 0];
     wc.P = w.P + (long long)c0 * m.RP;
     Net g = make_net(true, dc, a->g_theta, a->g_shadow, nullptr,
-                     (const __nv_bfloat16*)a->ann_g + (long long)c0 * m.R * m.C, wc, dc.B, st);
+                     (const __nv_bfloat16*)a->ann_g + (long long)c0 * m.R * m.C, wc, dc.B, sc);
     g.roll = true;
     SGG_TRY(net_init_state(g, 1));
     {
@@ -1322,7 +1333,7 @@ extern "C" int sgg_gen_sample(const sgg_sample_args_t* a, sgg_stream_t stream) {
       pk.rows = dc.B; pk.cols = m.C; pk.src = noise + (long long)c0 * m.C; pk.ld = m.C;
       pk.dst = g.w.X + g.uoff; pk.ldd = 2 * g.KXP; pk.lo_off = g.KXP;
       pk.reps = 2; pk.rep_stride = g.sX();
-      SGG_TRY(pack_hl(pk, st));
+      SGG_TRY(pack_hl(pk, sc));
     }
     for (int t = 0; t < m.T; ++t) {
       SGG_TRY(net_forward_step(g, t, 1));
@@ -1338,9 +1349,10 @@ extern "C" int sgg_gen_sample(const sgg_sample_args_t* a, sgg_stream_t stream) {
       q.gumbel = a->mode == SGG_SAMPLE_GUMBEL; q.gumbel_seed = a->seed ^ 0x5851F42D4C957F2DULL;
       q.gumbel_offset = a->offset + (unsigned long long)c0 + (unsigned long long)t * (unsigned long long)m.B;
       if (a->logits_out) { q.C = a->logits_out + ((long long)c0 * m.T + t) * m.V; q.ldc = (long long)m.T * m.V; }
-      SGG_TRY(gemm(q, st));
+      SGG_TRY(gemm(q, sc));
     }
   }
+  SGG_TRY(side_join(st, s2));
   return decode_keys(w.keys, a->tokens_out, (long long)m.B * m.T, st);
 }
 

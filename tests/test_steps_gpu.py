@@ -222,7 +222,7 @@ def test_fused_adam_projection_matches_adam_then_projection(B, R):
     ann = torch.randn(B, R * 512, generator=g).bfloat16().cuda()
     th0, m0, v0, gr = (x[off:off + n_wa].double().cpu() for x in (bk.theta, bk.m, bk.v, bk.grad))
     step, lr, b1, b2, eps = 7, 1e-4, 0.5, 0.9, 1e-8
-    P = torch.full((B, 256), 7.0, device="cuda")                      # must be cleared by the call
+    P = torch.full((B, (R + 63) // 64 * 64), 7.0, device="cuda")      # [B, rup(R,64)]; must be cleared by the call
     shadow_before = bk.shadow.clone()
     check(lib().sgg_adam_project(C.c_int(DISC), C.byref(dims), C.c_void_p(bk.theta.data_ptr()), C.c_void_p(bk.grad.data_ptr()),
                                  C.c_void_p(bk.m.data_ptr()), C.c_void_p(bk.v.data_ptr()), C.c_void_p(bk.shadow.data_ptr()),
