@@ -132,6 +132,7 @@ adam_proj_kernel(const __grid_constant__ CUtensorMap tmA, const AdamProjParams p
     const float lr_t = *s_lr;
     const unsigned R = (unsigned)p.R;
     const int n_f4 = 64 * p.R / 4;                 // float4 per k-block (R % 4 == 0: a float4 never straddles a row)
+    const long long range_end = (long long)kb_end * 64 * p.R;
     for (int i = 0; i < nkb; ++i) {
       const int st = i & 1;
       mbar_wait(&b_free[st], ((i >> 1) & 1) ^ 1);
@@ -146,6 +147,12 @@ adam_proj_kernel(const __grid_constant__ CUtensorMap tmA, const AdamProjParams p
           const int f = f0 + u * AP_WORKERS;
           if (f < n_f4) {
             const long long gi = base + 4LL * f;
+            // the CTA's rows are one contiguous run: pull the lines two passes ahead into L2 (more bytes in flight than
+            // the registers of 256 threads can hold)
+            const long long gp = gi + 2LL * 4 * 4 * AP_WORKERS;
+            if (gp < range_end && (gi & 31) == 0) {   // one request per 128-byte line
+              prefetch_l2(p.theta + gp); prefetch_l2(p.grad + gp); prefetch_l2(p.m + gp); prefetch_l2(p.v + gp);
+            }
             th[u] = *reinterpret_cast<const float4*>(p.theta + gi);
             g[u] = __ldcs(reinterpret_cast<const float4*>(p.grad + gi));
             mm[u] = *reinterpret_cast<const float4*>(p.m + gi);

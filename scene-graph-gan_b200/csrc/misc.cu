@@ -75,11 +75,15 @@ struct PackParams {
   const float* scale; int smod;        // optional per-row scale
   __nv_bfloat16* dst; long long ldd; long long lo_off;
   int reps; long long rep_stride;      // the result is written `reps` times, rep_stride elements apart (0/1 = once)
+  float4* zero_p; long long zero_n4;   // optional: also clear zero_n4 float4 at zero_p (a later kernel accumulates there)
 };
 __global__ void pack_hl_kernel(const PackParams p) {
   pdl_trigger();
   pdl_wait();
   const long long n = (long long)p.rows * p.cols;
+  if (p.zero_p)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.zero_n4; i += (long long)gridDim.x * blockDim.x)
+      p.zero_p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / p.cols), c = (int)(i % p.cols);
     const int grp = p.rpg > 0 ? r / p.rpg : 0, idx = p.rpg > 0 ? r % p.rpg : r;

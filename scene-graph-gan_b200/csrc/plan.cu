@@ -438,6 +438,7 @@ struct RevCfg {
   float ydot_bar;        // D head tangent upstream (lambda)
   const float* HB;       // G: [T*B, H] h_bar contributions from the logits (row t*B+b), or null
   bool wgrad;            // accumulate parameter gradients
+  bool clear_P;          // the W_a chain's hi/lo packing kernel also clears P (the fused Adam + projection accumulates into it)
 };
 
 // Reverse pass over T steps.  With wgrad: LN / head gradients inside lstm_rev, P_bar in attn_rev, and
@@ -541,6 +542,7 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
     } else {
       pk.rows = m.B; pk.cols = m.R; pk.src = n.w.PB; pk.ld = m.RP;
       pk.dst = n.w.PBH; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
+      if (rc.clear_P) { pk.zero_p = reinterpret_cast<float4*>(n.w.P); pk.zero_n4 = (long long)m.B * m.RP / 4; }
       SGG_TRY(pack_hl(pk, s1));
       g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 1;
       g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
@@ -848,7 +850,7 @@ extern "C" int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, 
 // pre: what the caller has already enqueued for this step's discriminator pass (sgg_train_iteration only):
 //   proj_stream != null : P = flat(a_d) W_a is being computed on that stream (join it before the first scores GEMM)
 //   state_ready         : c0 = h0 of the stream blocks is still in the workspace from the previous critic step
-struct StepPre { cudaStream_t proj_stream; bool have_proj; bool state_ready; };
+struct StepPre { cudaStream_t proj_stream; bool have_proj; bool state_ready; bool clear_P; };
 static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bfloat16* fake, const float* gp_alpha,
                           float* scalars, cudaStream_t st, cudaStream_t* side_out = nullptr, const StepPre* pre = nullptr) {
   const sgg_dims_t& dd = a->dims;
@@ -928,6 +930,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   rv.blk0 = 0; rv.nblk = 3; rv.tan_pblk = 2; rv.tan_blk = 3;
   rv.ybar_blk[0] = invBT; rv.ybar_blk[1] = -invBT; rv.ybar_blk[2] = 0.f; rv.ydot_bar = a->lam;
   rv.wgrad = true;
+  rv.clear_P = pre && pre->clear_P;
   cudaStream_t s1 = st;
   SGG_TRY(net_reverse(d, rv, &s1));
   // 7. embedding gradient: fake^T (ub_f + al ub_i) + scatter(labels, ub_r + (1-al) ub_i) + v^T udot_bar
@@ -1174,16 +1177,17 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
   // `next_proj`: the discriminator's projection for the NEXT pass (P = flat(a_d) W_a with the updated W_a) is enqueued
   // right behind the W_a update on the side stream, where it overlaps the main stream's weight-gradient GEMMs; the
   // side stream is then joined by the next pass just before its first scores GEMM instead of here.
+  static int fuse_env = -1;   // SGG_FUSED_ADAM_PROJ=0 keeps the Adam update of W_a and the next projection as two kernels
+  if (fuse_env < 0) { const char* e = getenv("SGG_FUSED_ADAM_PROJ"); fuse_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool will_fuse = fuse_env && prefetch_proj != 0 && !shard && !it->comm && m.B <= 256 && (m.R & 3) == 0 &&
+                         ((long long)m.R * m.C) % 64 == 0;
   auto optimise = [&](int net, float* theta, float* grad, float* mm, float* vv, void* shadow, long long step_mul,
                       long long step_add, cudaStream_t s1, bool next_proj, cudaStream_t* pending, bool last_critic) -> int {
     const ParamLayout L = param_layout(net == 0, dd);
     const long long n_wa = (long long)m.R * m.C * m.R;
     if (s1 != st && !side_ok) { SGG_TRY(side_join(st, s1)); s1 = st; }
-    static int fuse_env = -1;   // SGG_FUSED_ADAM_PROJ=0 keeps the Adam update of W_a and the next projection as two kernels
-    if (fuse_env < 0) { const char* e = getenv("SGG_FUSED_ADAM_PROJ"); fuse_env = (e && e[0] == '0') ? 0 : 1; }
     bool fused = false;
-    if (fuse_env && next_proj && net == 1 && !shard && !it->comm && m.B <= 256 && (m.R & 3) == 0 &&
-        ((long long)m.R * m.C) % 64 == 0) {
+    if (will_fuse && next_proj && net == 1) {
       // Adam on W_a and the next pass's P = flat(a_d) W_a in one kernel (adamproj.cu): the updated weights go from
       // registers into the MMA operand; the hi/lo shadow is only written for the pass that will see new annotations
       AdamProjParams ap{};
@@ -1194,8 +1198,7 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
       ap.iter = iter; ap.step_mul = step_mul; ap.step_add = step_add;
       ap.R = m.R; ap.total_kb = (int)((long long)m.R * m.C / 64); ap.M = m.B;
       ap.P = w.d.P; ap.ldP = m.RP;
-      SGG_TRY(zero_2d(w.d.P, m.RP, m.R, m.B, s1));
-      SGG_TRY(adam_proj(ap, a->ann_d, s1));
+      SGG_TRY(adam_proj(ap, a->ann_d, s1));   // P was cleared by the W_a chain's packing kernel (RevCfg::clear_P)
       fused = true;
     } else if (shard) {   // this rank's rows of dW_a are already sums over the global batch: no exchange, 1/world of the update
       SGG_TRY(adam_dev(net, dd, theta, grad, mm, vv, shadow, hp, iter, step_mul, step_add, s1, 1, sc.rank * sc.Ks, sc.Ks));
@@ -1212,7 +1215,7 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
     if (next_proj && pending) { *pending = s1; return 0; }
     return side_join(st, s1);
   };
-  StepPre pre{st, false, false};
+  StepPre pre{st, false, false, will_fuse};
   if (prefetch_proj != 0 && nc > 0 && use_side && side_stream() != nullptr) {
     // the first critic step's projection and initial state do not depend on the generator: they were enqueued on the
     // side stream (behind the discriminator's slab exchange when sharded) and ran beside the generator forwards
