@@ -106,3 +106,41 @@ def test_product_never_imports_the_oracle():
                     src = f.read()
                 assert not re.search(r"^\s*(import|from)\s+oracle|import_module\(.oracle|oracle/_ref", src, flags=re.M), \
                     f"{fn} reaches into oracle/"
+
+
+def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
+    """The Python side mirrors the public structs of include/sgg_b200.h with ctypes; a drifted field order or type
+    would silently corrupt arguments.  Compile a probe with gcc that prints sizeof / offsetof and compare."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from sgg_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {
+        "sgg_dims_t": (_lib.Dims, ["B", "S"]),
+        "sgg_gemm_desc_t": (_lib.GemmDesc, ["A", "seg_klen", "C", "Chl", "bias", "alpha", "splits", "out_s1", "argmax_keys",
+                                            "gumbel_offset"]),
+        "sgg_param_entry_t": (_lib.ParamEntry, ["name", "offset", "shadow_rows"]),
+        "sgg_step_args_t": (_lib.StepArgs, ["dims", "lam", "g_theta", "labels", "workspace_bytes", "flags"]),
+        "sgg_wa_shard_t": (_lib.WaShard, ["enabled", "slab_g", "scratch_bytes"]),
+        "sgg_iter_args_t": (_lib.IterArgs, ["step", "critic_iters", "lr", "seed", "scalars_all", "comm", "shard"]),
+        "sgg_sample_args_t": (_lib.SampleArgs, ["dims", "noise", "mode", "seed", "workspace_bytes", "logits_out"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "sgg_b200.h")}"',
+             "int main(void) {"]
+    for cname, (_, fields) in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(l.rsplit(" ", 1) for l in out.strip().splitlines())
+    for cname, (ctype, fields) in pairs.items():
+        assert int(got[cname]) == C.sizeof(ctype), (cname, got[cname], C.sizeof(ctype))
+        for f in fields:
+            assert int(got[f"{cname}.{f}"]) == getattr(ctype, f).offset, (cname, f)
