@@ -293,6 +293,25 @@ def train_iteration(gp, dp, adam_g: TFAdam, adam_d: TFAdam, ann_g, ann_d, real,
 # --------------------------------------------------------------------------------------
 # Synthetic inputs
 # --------------------------------------------------------------------------------------
+def greedy_triples(p: Dict[str, Tensor], annotations: Tensor, noise: Tensor, n_steps: int = 3) -> Tensor:
+    """train:269-270: ``fake_triples = tf.argmax(self._Generator(images), axis=-1)`` -> [B, n_steps] token ids
+    (tf.argmax returns the lowest index among equal maxima, as torch.argmax does)."""
+    return generator_forward(p, annotations, noise, n_steps).argmax(dim=-1)
+
+
+def recall(fake, real, N: float) -> float:
+    """train:294-295 ``_recall``: |set(fake triples) & set(real triples)| / N."""
+    return float(len(set(map(tuple, fake)).intersection(set(map(tuple, real))))) / N
+
+
+def recall_at_k(fake: Tensor, scores: Tensor, real: Tensor, k: int) -> float:
+    """train:320-327 with the ranking the comments there describe ("Sort by discriminator score"): the k fakes with
+    the highest mean critic score against the real triples.  (The reference's ``score_accumulator.argsort()`` acts on
+    an [N,1] array, i.e. sorts each 1-element row and yields zeros: a bug that is documented, not reproduced.)"""
+    order = torch.argsort(-scores.reshape(-1), stable=True)[:k]
+    return recall(fake[order].tolist(), real.tolist(), float(k))
+
+
 def synthetic_batch(B: int, V: int, T: int = 3, R: int = 196, C: int = 512, seed: int = 1234,
                     dtype=torch.float32, bf16_exact: bool = False):
     """ann_g, ann_d ~ N(0,1) [B,R,C]; labels uniform ints -> one-hot [B,T,V] (train:173)."""

@@ -253,3 +253,21 @@ def test_oracle_reproduces_committed_golden_vectors():
         for k, rec in gold[net].items():
             assert abs(fresh[net][k]["norm"] - rec["norm"]) <= 1e-10 * max(rec["norm"], 1e-30), k
             np.testing.assert_allclose(np.array(fresh[net][k]["samples"]), np.array(rec["samples"]), rtol=1e-8, atol=1e-14)
+
+
+def test_greedy_triples_and_recall_known_answers():
+    """train:269-270 argmax decoding (lowest index wins ties) and train:294-295 / 320-327 recall."""
+    from oracle import sgg_oracle as O
+    gp = O.init_generator_params(11, seed=5, R=6, dtype=torch.float64)
+    ann, _, _, _ = O.synthetic_batch(3, 11, 2, 6, 512, seed=9, dtype=torch.float64)
+    noise = torch.randn(3, 512, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    tok = O.greedy_triples(gp, ann, noise, 2)
+    assert tok.shape == (3, 2) and tok.dtype == torch.int64
+    assert torch.equal(tok, O.generator_forward(gp, ann, noise, 2).argmax(-1))
+    assert torch.argmax(torch.tensor([1.0, 3.0, 3.0])).item() == 1            # tie -> lowest index, like tf.argmax
+    assert O.recall([[1, 2, 3], [1, 2, 3], [4, 5, 0]], [[1, 2, 3], [9, 9, 9]], 50.0) == 1 / 50.0
+    fake = torch.tensor([[1, 2, 3], [4, 5, 6], [7, 8, 9], [1, 1, 1]])
+    scores = torch.tensor([0.1, 0.9, 0.5, 0.7])
+    real = torch.tensor([[4, 5, 6], [1, 2, 3]])
+    assert O.recall_at_k(fake, scores, real, 2) == 1 / 2                        # top-2 by score: rows 1, 3 -> one hit
+    assert O.recall_at_k(fake, scores, real, 4) == 2 / 4

@@ -108,3 +108,28 @@ def test_generator_class_sample_method():
     tokens = gen.sample(ann, noise=noise)
     torch.cuda.synchronize()
     assert torch.equal(tokens.long(), logits.argmax(dim=2))
+
+
+def test_greedy_tokens_match_the_committed_golden_logits():
+    """tests/golden/step_B4_T3_V64_R12.json holds the oracle's generator logits for a seeded problem: the decoded
+    tokens must be their argmax wherever the top-2 gap is resolvable at the tolerance."""
+    import json
+    import os
+    from sgg_b200.params import GEN, ParamBucket, make_dims
+    from sgg_b200.sampling import GeneratorSampler
+    from tests.util import make_problem
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_B4_T3_V64_R12.json")) as f:
+        gold = json.load(f)
+    c = gold["config"]
+    B, T, V, R = c["B"], c["T"], c["V"], c["R"]
+    prob = make_problem(B, T, V, R=R, seed=c["seed"], dtype=torch.float64)
+    bucket = ParamBucket(GEN, make_dims(B, T, V, R))
+    bucket.load_state_dict({k: v.float() for k, v in prob["gp"].items()})
+    smp = GeneratorSampler(bucket, B, T, R)
+    tokens = smp.sample(prob["ann_g"].to(torch.bfloat16).cuda().contiguous(), "greedy",
+                        noise=prob["noise"].float().cuda().contiguous()).cpu().long()
+    ref = torch.tensor(gold["logits"], dtype=torch.float64).view(B, T, V)
+    top2 = ref.topk(2, dim=2).values
+    clear = (top2[..., 0] - top2[..., 1]) > 2e-3 * ref.abs().amax(dim=2)
+    assert clear.any()
+    assert torch.equal(tokens[clear], ref.argmax(dim=2)[clear])
