@@ -11,8 +11,8 @@
 
 namespace sgg {
 
-constexpr int AP_THREADS = 320;                  // warp 0: TMA, warp 1: MMA, warps 2..9: Adam + epilogue
-constexpr int AP_WORKERS = 256;
+constexpr int AP_THREADS = 448;                  // warp 0: TMA, warp 1: MMA, warps 2..13: Adam (2..9 also the epilogue)
+constexpr int AP_WORKERS = 384;
 constexpr int AP_A_STAGE = 2 * 128 * 64 * 2;     // two 128-row m-tiles x 64 k, bf16: 32 KB
 constexpr int AP_B_PART = 256 * 64 * 2;          // 64 k x 256 n (4 chunks of 64 n), bf16: 32 KB
 constexpr int AP_SMEM = 2 * AP_A_STAGE + 2 * 2 * AP_B_PART + 1024 + 256;
@@ -128,7 +128,7 @@ adam_proj_kernel(const __grid_constant__ CUtensorMap tmA, const AdamProjParams p
       }
       *s_lr = lr_t;
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(AP_WORKERS) : "memory");
     const float lr_t = *s_lr;
     const unsigned R = (unsigned)p.R;
     const int n_f4 = 64 * p.R / 4;                 // float4 per k-block (R % 4 == 0: a float4 never straddles a row)
@@ -198,7 +198,7 @@ adam_proj_kernel(const __grid_constant__ CUtensorMap tmA, const AdamProjParams p
       mbar_arrive(&b_ready[st]);
     }
     // ===================== epilogue: split-K reduction of the two accumulators into P =====================
-    if (nkb > 0) {
+    if (nkb > 0 && warp < 10) {
       const int mt = (warp - 2) >> 2, q = warp & 3;
       const int row = mt * 128 + q * 32 + (int)lane_id();
       mbar_wait(tmem_full, 0);
