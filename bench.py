@@ -409,7 +409,8 @@ def run_gpu_arm(args):
             "e2e": None if e2e_secs is None else {
                 "value": images / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": tr.h2d_bytes_per_batch,
                 "d2h_bytes_per_step": tr.d2h_bytes_per_iteration,
-                "api": "HotPathTrainer.fit(pinned host batches): double-buffered H2D on a copy stream + 16 B loss read per iteration"},
+                "api": "HotPathTrainer.fit(pinned host batches): double-buffered H2D on a copy stream + a 96 B loss read per iteration "
+                       "(enqueued behind the iteration, consumed by the host one iteration later)"},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "cuda_graph": tr.use_graph,
             "roofline": roofs[0] if roofs else None, "roofline_more": roofs[1:] if roofs else None, "cpu_baseline": cpu,

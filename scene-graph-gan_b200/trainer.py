@@ -137,12 +137,7 @@ class HotPathTrainer:
         these are this rank's shard of the global means (sum over ranks = the global value)."""
         self._loss_host.copy_(self.eng.scalars_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        nc = self.critic_iters
-        out = {"gen_cost": float(self._loss_host[nc, 3])}
-        if nc > 0:
-            w, gp = float(self._loss_host[nc - 1, 1]), float(self._loss_host[nc - 1, 2])
-            out.update({"w_disc": w, "gp": gp, "disc_cost": w + self.lam * gp})
-        return out
+        return self._losses_from(self._loss_host)
 
     # ------------------------------------------------------------------ host-buffer path (end to end)
     def _alloc_slot(self):
@@ -172,14 +167,28 @@ class HotPathTrainer:
         self._cur = slot
         self.eng.set_batch(*self._slots[slot])
 
+    def _losses_from(self, host: torch.Tensor) -> Dict[str, float]:
+        nc = self.critic_iters
+        out = {"gen_cost": float(host[nc, 3])}
+        if nc > 0:
+            w, gp = float(host[nc - 1, 1]), float(host[nc - 1, 2])
+            out.update({"w_disc": w, "gp": gp, "disc_cost": w + self.lam * gp})
+        return out
+
     def fit(self, host_batches: Iterable[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]):
-        """Trains one iteration per host batch; the upload of batch i+1 overlaps the compute of batch i.
-        Yields the losses of every iteration (a small D2H read per iteration)."""
+        """Trains one iteration per host batch and yields the losses of every iteration, in order.  Software pipeline:
+        the upload of batch i+1 (copy stream) overlaps the compute of batch i, and the 96-byte loss read of iteration
+        i is enqueued behind it on the compute stream into one of two pinned buffers and only waited for after
+        iteration i+1 has been launched, so the host never idles the GPU between iterations."""
         it = iter(host_batches)
         try:
             nxt = self.upload(*next(it))
         except StopIteration:
             return
+        if not hasattr(self, "_loss_ring"):
+            self._loss_ring = [torch.zeros_like(self._loss_host).pin_memory() for _ in range(2)]
+        pending = None      # (event, pinned buffer) of the previous iteration
+        k = 0
         while nxt is not None:
             self.use_slot(nxt)
             try:
@@ -187,4 +196,15 @@ class HotPathTrainer:
             except StopIteration:
                 nxt = None
             self.iteration()
-            yield self.losses()
+            buf = self._loss_ring[k & 1]
+            buf.copy_(self.eng.scalars_all, non_blocking=True)      # stream-ordered before the next iteration overwrites it
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            if pending is not None:
+                pending[0].synchronize()
+                yield self._losses_from(pending[1])
+            pending = (ev, buf)
+            k += 1
+        if pending is not None:
+            pending[0].synchronize()
+            yield self._losses_from(pending[1])
