@@ -2,11 +2,10 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
-
-import os
 
 from ._lib import FLAG_REFRESH_GEN_PROJ, Dims, IterArgs, StepArgs, check, lib, stream_ptr
 from .params import DISC, GEN, ParamBucket, make_dims
