@@ -3,7 +3,7 @@
 This file is a literal PyTorch-CPU restatement of the reference arithmetic.  It is
 NOT part of the product: only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
-path (``scene-graph-gan_b200``) never imports anything from ``oracle/`` and fails loudly
+path (``sgg_b200``) never imports anything from ``oracle/`` and fails loudly
 when its CUDA library is missing.
 
 PARITY UNPINNED: the reference (/root/reference, Python 2 + TensorFlow 1.x ``tf.contrib``)

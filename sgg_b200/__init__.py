@@ -1,8 +1,2 @@
-"""Importable alias of the ``scene-graph-gan_b200/`` package directory (its name is not a
-valid Python identifier)."""
-import os as _os
-
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "scene-graph-gan_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+"""sgg_b200: B200-native (sm_100a) implementation of the Scene-Graph-GAN training hot path."""
+__version__ = "0.1.0"

@@ -10,7 +10,7 @@ attention projection ``P = flat(a) W_a + b``, batches the discriminator's passes
 
 so the double backward becomes: forward, input-gradient pass, tangent (JVP) forward, and
 ONE reverse pass over the primal+tangent program.  Every function below corresponds to
-one CUDA kernel (or one fused kernel family) in ``scene-graph-gan_b200/csrc``; the unit
+one CUDA kernel (or one fused kernel family) in ``sgg_b200/csrc``; the unit
 tests check each formula here against autograd on the oracle in fp64, and the GPU tests
 check each kernel against the matching function here.
 

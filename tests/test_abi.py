@@ -98,7 +98,7 @@ def test_null_arguments_are_rejected_not_crashed(lib):
 
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under the package may reference it."""
-    pkg = os.path.join(ROOT, "scene-graph-gan_b200")
+    pkg = os.path.join(ROOT, "sgg_b200")
     for dirpath, _, files in os.walk(pkg):
         for fn in files:
             if fn.endswith((".py", ".cu", ".cuh", ".h")):

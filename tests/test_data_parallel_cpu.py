@@ -1,7 +1,7 @@
 """World-size-2 gloo test (CPU) of the data-parallel scheme: batch shards, losses normalised by the
 GLOBAL batch, one sum-allreduce of the gradient bucket per optimiser step == the single-process step on the
 concatenated batch.  The per-rank arithmetic is the oracle's (the CUDA kernels normalise the same way through
-sgg_step_args_t.world); the host plumbing under test is scene-graph-gan_b200/dp.py."""
+sgg_step_args_t.world); the host plumbing under test is sgg_b200/dp.py."""
 import os
 import socket
 
