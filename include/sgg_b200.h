@@ -34,6 +34,9 @@ int sgg_version(void);
 /* Number of CUDA kernels this library has launched (or recorded into a stream capture) in this
  * process so far.  Lets a caller report how much of a timed region ran in these kernels. */
 int64_t sgg_launch_count(void);
+/* Launches per kernel entry point so far, as "demangled kernel name;launches" lines (NUL-terminated, truncated to cap;
+ * returns the size needed).  reset != 0 clears the counters.  Lets a test assert WHICH kernel variants a call ran. */
+int64_t sgg_kernel_counts(char* buf, int64_t cap, int32_t reset);
 /* Profiling aid: with SGG_TIMING=1 in the environment every eager (non-captured) kernel launch is bracketed by CUDA
  * events.  This call synchronises the device, writes one "kernel;grid;block;launches;total_us" line per distinct
  * launch shape timed since the previous call into buf (NUL-terminated, truncated to cap) and returns the size needed. */

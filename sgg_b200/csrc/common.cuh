@@ -12,6 +12,7 @@ namespace sgg {
 // ---------------------------------------------------------------- error plumbing (host)
 void set_error(const char* fmt, ...);
 void note_launch();  // counts kernels launched by this library (sgg_launch_count)
+void note_kernel(const void* func);   // ... per kernel entry point (sgg_kernel_counts)
 #define SGG_CHECK(cond, ...)                      \
   do {                                            \
     if (!(cond)) {                                \
@@ -70,6 +71,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  note_kernel(reinterpret_cast<const void*>(kern));
   if (timing_enabled()) {
     timing_begin(stream);
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
@@ -314,7 +316,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+// 23 random bits + 1/2: every value k + 0.5 (k < 2^23) is exact in fp32, so the result lies strictly inside (0,1)
+// (with 24 bits, (2^24 - 1) + 0.5 rounds up to 2^24 and the result would be exactly 1.0 once in 2^24 draws, which
+// -log(-log(u)) in the Gumbel epilogue turns into +inf).
+__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 #endif  // __CUDACC__
 

@@ -5,9 +5,11 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cudaTypedefs.h>
+#include <cxxabi.h>
 
 #include "common.cuh"
 #include "../../include/sgg_b200.h"
@@ -26,6 +28,25 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// demangled name of a kernel entry point ("void sgg::gemm_kernel<256, false, true, 2>(...)")
+static std::string kernel_name(const void* func) {
+  const char* name = nullptr;
+  if (cudaFuncGetName(&name, func) != cudaSuccess || !name) return "?";
+  int status = 0;
+  char* dm = abi::__cxa_demangle(name, nullptr, nullptr, &status);
+  std::string out = (status == 0 && dm) ? dm : name;
+  free(dm);
+  return out;
+}
+
+// launches per kernel entry point (always on; a map update per launch): lets a caller prove which kernels ran
+static std::mutex g_kern_mu;
+static std::map<const void*, long long> g_kern_counts;
+void note_kernel(const void* func) {
+  std::lock_guard<std::mutex> lk(g_kern_mu);
+  g_kern_counts[func] += 1;
+}
 
 bool pdl_enabled() {
   static int on = -1;
@@ -133,6 +154,26 @@ extern "C" const char* sgg_last_error(void) { return sgg::g_err; }
 extern "C" int sgg_version(void) { return 100; }
 extern "C" int64_t sgg_launch_count(void) { return (int64_t)sgg::launch_count(); }
 
+// "kernel name;launches" lines for every kernel of this library launched (or captured) so far; reset != 0 clears the
+// counters afterwards.  Returns the number of bytes needed.
+extern "C" int64_t sgg_kernel_counts(char* buf, int64_t cap, int32_t reset) {
+  using namespace sgg;
+  std::string out;
+  {
+    std::lock_guard<std::mutex> lk(g_kern_mu);
+    for (auto& kv : g_kern_counts) {
+      out += kernel_name(kv.first) + ";" + std::to_string(kv.second) + "\n";
+    }
+    if (reset) g_kern_counts.clear();
+  }
+  if (buf && cap > 0) {
+    const size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
+
 // Synchronises the device and writes "kernel;grid;block;launches;total_us" lines for every launch timed since the
 // last report (SGG_TIMING=1) into buf; returns the number of bytes needed.
 extern "C" int64_t sgg_timing_report(char* buf, int64_t cap) {
@@ -144,10 +185,8 @@ extern "C" int64_t sgg_timing_report(char* buf, int64_t cap) {
   for (auto& t : g_timed) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, t.e0, t.e1);
-    const char* name = nullptr;
-    if (cudaFuncGetName(&name, t.func) != cudaSuccess || !name) name = "?";
-    char key[512];
-    snprintf(key, sizeof(key), "%s;%ux%ux%u;%u", name, t.grid.x, t.grid.y, t.grid.z, t.block.x);
+    char key[768];
+    snprintf(key, sizeof(key), "%s;%ux%ux%u;%u", kernel_name(t.func).c_str(), t.grid.x, t.grid.y, t.grid.z, t.block.x);
     auto it = agg.find(key);
     if (it == agg.end()) { order.push_back(key); it = agg.emplace(key, Agg{}).first; }
     it->second.n += 1;
@@ -158,7 +197,7 @@ extern "C" int64_t sgg_timing_report(char* buf, int64_t cap) {
   g_timed.clear();
   std::string out;
   for (auto& k : order) {
-    char line[640];
+    char line[896];
     snprintf(line, sizeof(line), "%s;%lld;%.2f\n", k.c_str(), agg[k].n, agg[k].us);
     out += line;
   }

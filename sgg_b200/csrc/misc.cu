@@ -113,6 +113,7 @@ int pack_hl(const PackParams& p, cudaStream_t stream) {
 // tfgan's interpolates).  Written hi/lo into the x buffers' u columns of the stream row blocks.
 struct EmbedMixParams {
   int B, T, E;
+  int V;                                // label ids are clamped to [0, V): a bad id cannot read outside W_emb (the host validates)
   const float* Uf; long long ldUf;      // [T*B, E] or null (no fake stream)
   const int64_t* labels;                // [B, T] or null (no real stream)
   const float* Wemb;                    // [V, E] fp32 master
@@ -129,7 +130,12 @@ __global__ void embed_mix_kernel(const EmbedMixParams p) {
     const long long tb = i / p.E;
     const int b = (int)(tb % p.B), t = (int)(tb / p.B);
     const float uf = p.Uf ? p.Uf[tb * p.ldUf + e] : 0.f;
-    const float ur = p.labels ? p.Wemb[p.labels[(long long)b * p.T + t] * p.E + e] : 0.f;
+    float ur = 0.f;
+    if (p.labels) {
+      long long id = p.labels[(long long)b * p.T + t];
+      id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+      ur = p.Wemb[id * p.E + e];
+    }
     __nv_bfloat16* xt = p.X + (long long)t * p.strideT + p.uoff + e;
     __nv_bfloat16 h, l;
     if (p.blk_fake >= 0) {
@@ -159,6 +165,7 @@ int embed_mix(const EmbedMixParams& p, cudaStream_t stream) {
 // dW_emb[label[b,t], :] += u_bar_real + (1 - alpha_b) u_bar_int   (one-hot rows of x^T u_bar)
 struct EmbedScatterParams {
   int B, T, E;
+  int V;                                // ids clamped like embed_mix
   const int64_t* labels; const float* gp_alpha;
   const float* XB; long long ldXB; long long strideT; int uoff;   // u_bar = XB[t][row, uoff:uoff+E]
   int blk_real, blk_int;
@@ -175,7 +182,9 @@ __global__ void embed_scatter_kernel(const EmbedScatterParams p) {
     const float* xb = p.XB + (long long)t * p.strideT + p.uoff + e;
     float v = xb[((long long)p.blk_real * p.B + b) * p.ldXB];
     if (p.blk_int >= 0) v += (1.0f - p.gp_alpha[b]) * xb[((long long)p.blk_int * p.B + b) * p.ldXB];
-    atomicAdd(p.dWemb + p.labels[(long long)b * p.T + t] * p.E + e, v);
+    long long id = p.labels[(long long)b * p.T + t];
+    id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+    atomicAdd(p.dWemb + id * p.E + e, v);
   }
 }
 int embed_scatter(const EmbedScatterParams& p, cudaStream_t stream) {

@@ -831,7 +831,7 @@ extern "C" int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, 
   }
   SGG_TRY(embed_dense(d, w, w.TRIH));
   EmbedMixParams em{};
-  em.B = m.B; em.T = m.T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
+  em.B = m.B; em.T = m.T; em.E = m.E; em.V = m.V; em.Uf = w.UF; em.ldUf = m.EP;
   em.blk_fake = 0; em.blk_real = -1; em.blk_int = -1;
   em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
   SGG_TRY(embed_mix(em, st));
@@ -876,7 +876,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   // 2. embeddings of the three streams
   SGG_TRY(embed_dense(d, w, fake, pre_uf));
   EmbedMixParams em{};
-  em.B = B; em.T = T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
+  em.B = B; em.T = T; em.E = m.E; em.V = m.V; em.Uf = w.UF; em.ldUf = m.EP;
   em.labels = a->labels; em.Wemb = a->d_theta + d.L.Wemb; em.gp_alpha = gp_alpha;
   em.blk_fake = 0; em.blk_real = 1; em.blk_int = 2;
   em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
@@ -919,7 +919,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     SGG_TRY(pack_hl(pk, st));
     SGG_TRY(embed_dense(d, w, w.VHL, pre_t));
     EmbedMixParams et{};
-    et.B = B; et.T = T; et.E = m.E; et.Uf = w.UF; et.ldUf = m.EP;
+    et.B = B; et.T = T; et.E = m.E; et.V = m.V; et.Uf = w.UF; et.ldUf = m.EP;
     et.blk_fake = 3; et.blk_real = -1; et.blk_int = -1;
     et.X = d.w.X; et.ldX = 2 * d.KXP; et.x_lo = d.KXP; et.strideT = d.sX(); et.uoff = d.uoff;
     SGG_TRY(embed_mix(et, st));
@@ -958,7 +958,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
       SGG_TRY(gemm(q, st));
     }
     EmbedScatterParams es{};
-    es.B = B; es.T = T; es.E = m.E; es.labels = a->labels; es.gp_alpha = gp_alpha;
+    es.B = B; es.T = T; es.E = m.E; es.V = m.V; es.labels = a->labels; es.gp_alpha = gp_alpha;
     es.XB = d.w.XB; es.ldXB = d.KXP; es.strideT = d.sXB(); es.uoff = d.uoff;
     es.blk_real = 1; es.blk_int = 2; es.dWemb = a->d_grad + d.L.Wemb;
     SGG_TRY(embed_scatter(es, st));
@@ -1004,7 +1004,7 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   // D(fake), single stream
   SGG_TRY(embed_dense(d, w, fake_slot(w, m, 0)));
   EmbedMixParams em{};
-  em.B = B; em.T = T; em.E = m.E; em.Uf = w.UF; em.ldUf = m.EP;
+  em.B = B; em.T = T; em.E = m.E; em.V = m.V; em.Uf = w.UF; em.ldUf = m.EP;
   em.blk_fake = 0; em.blk_real = -1; em.blk_int = -1;
   em.X = d.w.X; em.ldX = 2 * d.KXP; em.x_lo = d.KXP; em.strideT = d.sX(); em.uoff = d.uoff;
   SGG_TRY(embed_mix(em, st));

@@ -40,6 +40,8 @@ class Engine:
         self.logits = torch.zeros(B, T, V, dtype=torch.float32, device=device)
         self.ann_g = self.ann_d = self.labels = None
         self._refresh = True
+        self._g_version = -1            # generator bucket version the cached projection P / c0 was computed from
+        self._checked_labels = {}       # (data_ptr, tensor version) of label tensors already range-checked
         self.seed, self._rng_off = seed, 0
         # sgg_train_iteration state: device-side iteration counter, per-step randomness and losses
         nc = max(1, self.critic_iters)
@@ -64,15 +66,27 @@ class Engine:
             self.shard_scratch = torch.zeros(n_scr, dtype=torch.uint8, device=device)
 
     # ------------------------------------------------------------------ inputs
-    def set_batch(self, ann_g: torch.Tensor, ann_d: torch.Tensor, labels: Optional[torch.Tensor]) -> None:
+    def set_batch(self, ann_g: torch.Tensor, ann_d: torch.Tensor, labels: Optional[torch.Tensor],
+                  validate: bool = True) -> None:
         """Annotations [B,R,512] (or [B,14,14,512]) bf16 on device; labels [B,T] int64.  The same batch
-        serves the n_critic + 1 steps of an iteration (train.py:185-187)."""
+        serves the n_critic + 1 steps of an iteration (train.py:185-187).  Labels index rows of Discriminator/W
+        (one-hot of train.py:173): ids outside [0, V) raise here (one device min/max per distinct label tensor; the
+        kernels additionally clamp, so a skipped check cannot corrupt memory).  validate=False skips the check for
+        callers that validated the host copy (HotPathTrainer.upload)."""
         for a in (ann_g, ann_d):
             assert a.dtype == torch.bfloat16 and a.is_cuda and a.is_contiguous()
             assert a.numel() == self.B * self.R * 512, "annotation shape mismatch"
         self.ann_g, self.ann_d = ann_g, ann_d
         if labels is not None:
             assert labels.dtype == torch.int64 and labels.shape == (self.B, self.T) and labels.is_contiguous()
+            key = (labels.data_ptr(), labels._version)
+            if validate and self._checked_labels.get(labels.data_ptr()) != key:
+                lo, hi = int(labels.min()), int(labels.max())
+                if lo < 0 or hi >= self.V:
+                    raise ValueError(f"label ids must lie in [0, {self.V}); got [{lo}, {hi}]")
+                if len(self._checked_labels) > 64:
+                    self._checked_labels.clear()
+                self._checked_labels[labels.data_ptr()] = key
         self.labels = labels
         self._refresh = True
 
@@ -97,14 +111,20 @@ class Engine:
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
         a.scalars = self.scalars.data_ptr()
         a.logits_out = self.logits.data_ptr() if want_logits else None
-        a.flags = FLAG_REFRESH_GEN_PROJ if self._refresh else 0
+        # the hoisted projection P = flat(a_g) W_a and c0 are cached in the workspace: recompute them for a new batch
+        # and whenever the generator's weights may have changed since (Adam step, load_state_dict, refresh_shadow)
+        a.flags = FLAG_REFRESH_GEN_PROJ if (self._refresh or self._g_version != self.g.version) else 0
         return a
+
+    def _proj_cached(self) -> None:
+        self._refresh = False
+        self._g_version = self.g.version
 
     # ------------------------------------------------------------------ steps
     def gen_forward(self, stream=None) -> torch.Tensor:
         a = self._args(want_logits=True)
         check(lib().sgg_gen_forward(C.byref(a), stream_ptr(stream)), "sgg_gen_forward")
-        self._refresh = False
+        self._proj_cached()
         return self.logits
 
     def disc_forward(self, triples: torch.Tensor, stream=None) -> torch.Tensor:
@@ -119,13 +139,13 @@ class Engine:
         """Gradients of disc_cost into self.d.grad; scalars[1] = w_disc, scalars[2] = gp."""
         a = self._args()
         check(lib().sgg_disc_step(C.byref(a), stream_ptr(stream)), "sgg_disc_step")
-        self._refresh = False
+        self._proj_cached()
 
     def gen_step(self, stream=None) -> None:
         """Gradients of gen_cost into self.g.grad; scalars[3] = gen_cost."""
         a = self._args()
         check(lib().sgg_gen_step(C.byref(a), stream_ptr(stream)), "sgg_gen_step")
-        self._refresh = False
+        self._proj_cached()
 
     def train_iteration(self, critic_iters: Optional[int] = None, comm=None, lr=1e-4, beta1=0.5, beta2=0.9,
                         eps=1e-8, stream=None) -> None:
@@ -149,7 +169,9 @@ class Engine:
             it.shard.slab_g, it.shard.slab_d = self.slab_g.data_ptr(), self.slab_d.data_ptr()
             it.shard.scratch, it.shard.scratch_bytes = self.shard_scratch.data_ptr(), self.shard_scratch.numel()
         check(lib().sgg_train_iteration(C.byref(it), stream_ptr(stream)), "sgg_train_iteration")
-        self._refresh = True   # the generator was updated
+        self._refresh = True   # the generator was updated inside the library
+        self.g.version += 1
+        self.d.version += 1
 
     def wa_rows(self, rank: int):
         """Rows of attention_perceptron/kernel rank `rank` maintains under the row-sharded projection."""

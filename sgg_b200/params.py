@@ -39,6 +39,9 @@ class ParamBucket:
         self.v = torch.zeros_like(self.theta)
         self.shadow = torch.zeros(self.n_shadow, dtype=torch.bfloat16, device=device)
         self.step = 0
+        # bumped whenever theta may have changed through this object (Adam, load, shadow refresh after an in-place
+        # edit of a view): consumers that cache products of the weights (Engine: the hoisted projection P) compare it
+        self.version = 0
 
     # ---- named views in the reference's (TF) shapes
     def _views(self, flat: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
@@ -67,6 +70,7 @@ class ParamBucket:
         return OrderedDict((k, v.detach().clone()) for k, v in self.views().items())
 
     def refresh_shadow(self, stream=None) -> None:
+        self.version += 1
         check(lib().sgg_refresh_shadow(self.net, C.byref(self.dims), C.c_void_p(self.theta.data_ptr()),
                                        C.c_void_p(self.shadow.data_ptr()), stream_ptr(stream)), "sgg_refresh_shadow")
 
@@ -91,6 +95,7 @@ class ParamBucket:
     def adam_step(self, lr=1e-4, beta1=0.5, beta2=0.9, eps=1e-8, grad_scale=1.0, stream=None) -> None:
         """tf.train.AdamOptimizer(1e-4, beta1=0.5, beta2=0.9) of train.py:258-259."""
         self.step += 1
+        self.version += 1
         check(lib().sgg_adam_step(self.net, C.byref(self.dims), C.c_void_p(self.theta.data_ptr()),
                                   C.c_void_p(self.grad.data_ptr()), C.c_void_p(self.m.data_ptr()),
                                   C.c_void_p(self.v.data_ptr()), C.c_void_p(self.shadow.data_ptr()),

@@ -25,12 +25,13 @@ from .trainer import HotPathTrainer
 class SceneGraphGAN(object):
     def __init__(self, checkpoints_dir, summaries_dir, path_to_ims_to_triples, path_to_vocab, path_to_word_embeddings,
                  path_to_image_means, path_to_image_stds, critic_iters, batch_size, lambda_, resume,
-                 vocab_size: Optional[int] = None, n_triples: int = 1, seed: int = 0):
+                 vocab_size: Optional[int] = None, n_triples: int = 1, seed: int = 0, allow_synthetic: bool = True):
         # Hyperparameters (train.py:27-32)
         self.CRITIC_ITERS = int(critic_iters)
         self.BATCH_SIZE = int(batch_size)
         self.LAMBDA = float(lambda_)
         self.resume = bool(resume)
+        self.allow_synthetic = bool(allow_synthetic)
         self.checkpoints_dir, self.summaries_dir = checkpoints_dir, summaries_dir
         for d in (checkpoints_dir, summaries_dir):
             if d and not os.path.exists(d):
@@ -78,10 +79,18 @@ class SceneGraphGAN(object):
         return os.path.join(self.checkpoints_dir, "model.ckpt.pt")
 
     def _saveModel(self, itr=None):
-        e = self.trainer.eng
-        torch.save({"generator": e.g.state_dict(), "discriminator": e.d.state_dict(),
-                    "adam": {"g": (e.g.m.cpu(), e.g.v.cpu(), e.g.step), "d": (e.d.m.cpu(), e.d.v.cpu(), e.d.step)},
-                    "iterations": int(e.counters.item())}, self._ckpt())
+        """Collective under data parallelism: every rank calls it.  With the row-sharded attention projection each
+        rank only maintains its own rows of attention_perceptron/kernel, so the rows are all-gathered first; rank 0
+        alone writes the file, then all ranks meet at a barrier."""
+        tr = self.trainer
+        tr.gather_sharded()
+        e = tr.eng
+        if tr.rank == 0:
+            torch.save({"generator": e.g.state_dict(), "discriminator": e.d.state_dict(),
+                        "adam": {"g": (e.g.m.cpu(), e.g.v.cpu(), e.g.step), "d": (e.d.m.cpu(), e.d.v.cpu(), e.d.step)},
+                        "iterations": int(e.counters.item())}, self._ckpt())
+        if tr.dist is not None:
+            tr.dist.barrier(group=tr.pg)
 
     def _loadModel(self):
         ck = torch.load(self._ckpt(), map_location="cpu")
@@ -100,8 +109,13 @@ class SceneGraphGAN(object):
         the configured shape are generated."""
         tr = self.trainer
         if batches is None:
-            batches = synthetic_batches(tr.B, tr.T, tr.V, tr.R, max_iterations or 100)
-        log_path = os.path.join(self.summaries_dir, "train_log.jsonl") if self.summaries_dir else None
+            if self.ims_to_triples is not None and not self.allow_synthetic:
+                raise RuntimeError(
+                    "SceneGraphGAN.train(): an ims_to_triples file was loaded but no annotation batches were given. The "
+                    "hot path starts at the annotation grid (gen:68); the JPEG -> conv front-end that produces it is "
+                    "outside this build (SURVEY 8f-1/f4). Pass `batches`, or --synthetic to train on synthetic inputs.")
+            batches = synthetic_batches(tr.B, tr.T, tr.V, tr.R, max_iterations or 100, seed=1234 + tr.rank)
+        log_path = os.path.join(self.summaries_dir, "train_log.jsonl") if (self.summaries_dir and tr.rank == 0) else None
         t0, n = time.time(), 0
         out = open(log_path, "a") if log_path else None
         try:
@@ -121,7 +135,9 @@ class SceneGraphGAN(object):
         """train.py:294-295: |set(fake triples) & set(real triples)| / N."""
         return float(len(set(map(tuple, fake)).intersection(set(map(tuple, real))))) / N
 
-    def test(self, batches: Iterable, multiplier: int = 10, out_path: Optional[str] = None):
+    TEST_BATCH_MULTIPLIER = 8                                                  # train.py:31
+
+    def test(self, batches: Iterable, multiplier: Optional[int] = None, out_path: Optional[str] = None):
         """R@50 / R@100 evaluation of train.py:297-335 on the hot path: for every test batch, ``multiplier`` generator
         passes with fresh noise (train.py:311: TEST_BATCH_MULTIPLIER) give fake triples ``argmax(logits)`` (train.py:270)
         and discriminator scores ``mean_t D(logits, images)`` (train.py:272,314); the fakes are ranked by score and the
@@ -130,6 +146,9 @@ class SceneGraphGAN(object):
         Documented deviation: the reference ranks with ``score_accumulator.argsort()`` on an [N,1] array, which sorts
         each 1-element row and returns all zeros; here the fakes are sorted by descending critic score.
         Returns (mean R@50, mean R@100) and, like the reference, writes them to ``recalls.txt``."""
+        if multiplier is None:
+            multiplier = self.TEST_BATCH_MULTIPLIER
+        self.trainer.gather_sharded()      # evaluation reads the full attention kernel (collective when world > 1)
         e = self.trainer.eng
         r50, r100 = [], []
         for ag, ad, lb in batches:
@@ -141,7 +160,6 @@ class SceneGraphGAN(object):
             fakes, scores = [], []
             for _ in range(multiplier):
                 e.sample_noise()
-                e._refresh = True
                 logits = e.gen_forward()                                   # self.fake_inputs (train.py:269)
                 fakes.append(logits.argmax(dim=-1))                        # self.fake_triples (train.py:270)
                 scores.append(e.disc_forward(logits).mean(dim=1))          # np.mean(disc_scores, axis=1) (train.py:314)
@@ -154,8 +172,9 @@ class SceneGraphGAN(object):
         m50 = float(sum(r50) / len(r50)) if r50 else 0.0
         m100 = float(sum(r100) / len(r100)) if r100 else 0.0
         path = out_path or "recalls.txt"
-        with open(path, "w") as f:                                         # train.py:333-335
-            f.write("{}\n{}".format(m50, m100))
+        if self.trainer.rank == 0:
+            with open(path, "w") as f:                                     # train.py:333-335
+                f.write("{}\n{}".format(m50, m100))
         return m50, m100
 
 
@@ -190,16 +209,36 @@ def main(argv=None):
     p.add_argument("--vocab_size", type=int, default=None, help="synthetic vocabulary size when no vocab.json exists")
     p.add_argument("--n_triples", type=int, default=1)
     p.add_argument("--iterations", type=int, default=100)
+    p.add_argument("--synthetic", action="store_true",
+                   help="train on synthetic annotation batches even when dataset files are present")
     a = p.parse_args(argv)
-    if "LOCAL_RANK" not in os.environ:
+    distributed = "LOCAL_RANK" in os.environ
+    if distributed:   # torchrun: one process per GPU over NCCL (the reference is single-GPU, train.py:417-418)
+        import torch.distributed as dist
+        local = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
         os.environ.setdefault("CUDA_VISIBLE_DEVICES", a.GPU)          # train.py:417-418
     gan = SceneGraphGAN(a.checkpoints_dir, a.summaries_dir, a.path_to_ims_to_triples, a.path_to_vocab,
                         a.path_to_word_embeddings, a.path_to_image_means, a.path_to_image_stds,
                         critic_iters=a.critic_iters, batch_size=a.batch_size, lambda_=a.lambda_, resume=a.resume,
-                        vocab_size=a.vocab_size, n_triples=a.n_triples)
+                        vocab_size=a.vocab_size, n_triples=a.n_triples, allow_synthetic=a.synthetic)
+    if gan.ims_to_triples is None and not a.synthetic:
+        print("train.py: no dataset files found; training on synthetic annotation batches", flush=True)
+        gan.allow_synthetic = True
     n = gan.train(max_iterations=a.iterations)
-    gan._saveModel()
-    print(json.dumps({"iterations": n, **gan.trainer.losses()}))
+    gan._saveModel()                                                   # collective; rank 0 writes
+    if gan.trainer.rank == 0:
+        print(json.dumps({"iterations": n, **gan.trainer.losses()}))
+    else:
+        gan.trainer.losses()
+    gan.trainer.close()
+    if distributed:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

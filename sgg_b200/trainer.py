@@ -149,6 +149,8 @@ class HotPathTrainer:
     def upload(self, ann_g_host: torch.Tensor, ann_d_host: torch.Tensor, labels_host: torch.Tensor) -> int:
         """Asynchronous H2D of one batch (pinned bf16 annotations [B,R,512] / [B,14,14,512], int64 labels
         [B,T]) into the staging slot that is NOT in use; returns the slot id."""
+        if labels_host.numel() and (int(labels_host.min()) < 0 or int(labels_host.max()) >= self.V):
+            raise ValueError(f"label ids must lie in [0, {self.V}); got [{int(labels_host.min())}, {int(labels_host.max())}]")
         slot = 1 - self._cur
         if self._slots[slot] is None:
             self._slots[slot] = self._alloc_slot()
@@ -165,7 +167,7 @@ class HotPathTrainer:
     def use_slot(self, slot: int) -> None:
         torch.cuda.current_stream().wait_event(self._slot_ready[slot])
         self._cur = slot
-        self.eng.set_batch(*self._slots[slot])
+        self.eng.set_batch(*self._slots[slot], validate=False)   # the host copy was range-checked in upload()
 
     def _losses_from(self, host: torch.Tensor) -> Dict[str, float]:
         nc = self.critic_iters

@@ -123,7 +123,6 @@ def test_recall_at_k_evaluation(tmp_path):
     fakes, scores = [], []
     for _ in range(mult):
         e.sample_noise()
-        e._refresh = True
         e.set_batch(ag.cuda().contiguous(), ad.cuda().contiguous(), lb.cuda().contiguous())
         lg = e.gen_forward().clone()
         fakes.append(lg.argmax(-1).cpu())

@@ -271,3 +271,22 @@ def test_greedy_triples_and_recall_known_answers():
     real = torch.tensor([[4, 5, 6], [1, 2, 3]])
     assert O.recall_at_k(fake, scores, real, 2) == 1 / 2                        # top-2 by score: rows 1, 3 -> one hit
     assert O.recall_at_k(fake, scores, real, 4) == 2 / 4
+
+
+def test_u01_restatement_stays_inside_the_open_interval():
+    """csrc/common.cuh u01(): ((x >> 9) + 0.5f) * 2^-23 in fp32.  Known answers for the extreme counter values: the
+    largest draw must stay below 1 (the previous 24-bit form rounded (2^24 - 1) + 0.5 up to 2^24 and returned exactly
+    1.0, which the Gumbel epilogue's -log(-log u) turned into +inf)."""
+    import numpy as np
+
+    def u01(x):
+        return np.float32(np.float32(np.uint32(x) >> np.uint32(9)) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+
+    def u01_old(x):
+        return np.float32(np.float32(np.uint32(x) >> np.uint32(8)) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+
+    assert u01(0xFFFFFFFF) == np.float32(1.0) - np.float32(2.0 ** -24) and u01(0xFFFFFFFF) < 1.0
+    assert u01(0) == np.float32(2.0 ** -24) and u01(0) > 0.0
+    assert u01_old(0xFFFFFFFF) == 1.0                        # the defect this form replaces
+    g = -np.log(-np.log(np.float64(u01(0xFFFFFFFF))))
+    assert np.isfinite(g)
