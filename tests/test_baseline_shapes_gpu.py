@@ -161,11 +161,13 @@ def test_fused_adam_projection_at_config2_shape():
 
 def test_cost_of_the_bf16_annotation_format():
     """The reference's annotations (self.downsampled, gen:68) are fp32; the CUDA path takes them as bf16 (INTEGRATION.md
-    section 4).  Here the oracle sees fp32 N(0,1) annotations and the CUDA path their bf16 cast, at configs[0] shape.
-    A K = 100,352-long dot product of bf16-rounded inputs carries ~2^-9 / sqrt(3) relative noise per term, i.e. the
-    scores move by ~1e-3 of their spread, and every downstream tensor inherits that: the format change costs up to
-    ~5e-3 per tensor against fp32 inputs -- 5x the 1e-3 parity tolerance, which therefore only holds for
-    bf16-representable annotations (every other parity test).  The measured errors are written next to the test logs."""
+    section 4).  Here the oracle sees general fp32 N(0,1) annotations and the CUDA path their bf16 cast, at configs[0]
+    shape.  Every annotation element then carries a relative rounding error of up to 2^-9, which a correct kernel
+    cannot undo.  Measured on B200 (round 2, gpurun_out/fp32_annotation_cost.json, copied to profiles/): losses within
+    1e-3, slopes 7e-4, generator gradients 4e-4 .. 3.8e-3, discriminator gradients 3e-3 .. 1.9e-2 (this problem has an
+    active penalty of ~80, whose second-order terms amplify the input perturbation).  So the 1e-3 parity tolerance of
+    north_star holds for bf16-representable annotations (every other parity test) and NOT for arbitrary fp32
+    annotations: against those the input format costs up to 2e-2 per gradient tensor.  Asserted here: 5e-2."""
     err, terr, _, _ = _d_and_g_step(32, 3, 2000, 196, seed=4, ann_bf16=False)
     worst = max(terr.items(), key=lambda kv: kv[1])
     out = {"scalars": {k: {"got": g, "ref": r} for k, (g, r) in err.items()}, "per_tensor_rel_l2": terr,
@@ -176,7 +178,7 @@ def test_cost_of_the_bf16_annotation_format():
     for k, (got, ref) in err.items():
         assert _scalar_close(got, ref, tol=1e-2), (k, got, ref)
     for k, e in terr.items():
-        assert e < 1e-2, (k, e)
+        assert e < 5e-2, (k, e)
 
 
 def test_label_ids_are_validated():
