@@ -132,11 +132,35 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// Branch-free transcendental pieces.  IEEE division / __frcp_rn / __expf compile to a MUFU plus a range check with a
+// slow-path CALL per element; the check is a real branch (BSSY / BSYNC), so the elements of an unrolled loop are
+// processed one dependency chain at a time (measured in the LSTM cell epilogues: ~200 cycles per element).  The
+// approximate forms below are a single MUFU each (relative error ~2^-22), which is far inside the 1e-3 parity budget.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_exp(float x) {   // e^x
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return fast_rcp(1.0f + fast_exp(-x)); }
 __device__ __forceinline__ float tanhf_(float x) {
   // tanh via exp keeps ~1e-7 relative accuracy; tanh.approx is only ~1e-3.
-  float e = __expf(-2.0f * fabsf(x));
-  float t = (1.0f - e) / (1.0f + e);
+  float e = fast_exp(-2.0f * fabsf(x));
+  float t = (1.0f - e) * fast_rcp(1.0f + e);
   return copysignf(t, x);
 }
 

@@ -29,11 +29,17 @@ namespace sgg {
 constexpr int GF_THREADS = 320;
 constexpr int GF_EPI = 256;
 constexpr int GF_SMEM_BUDGET = 196 * 1024;
+constexpr int GF_NSTAT = 12;                    // exchange rows per CTA: 8 gate partials, 2 state partials, head partial, pad
 
 // column of gate g, hidden unit u in the interleaved weight shadow Kp (groups of 32 units: [i | j | f | o] x 32)
 __host__ __device__ __forceinline__ int perm_gate_col(int g, int u) { return (u >> 5) * 128 + g * 32 + (u & 31); }
 
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// .aligned: every thread of the warp executes the instruction together -> reconverge first (the elected producer /
+// issuer lanes and the row-guarded epilogue code leave the warps diverged)
+__device__ __forceinline__ void cluster_arrive_release() {
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 struct GatesParams {
@@ -48,7 +54,8 @@ struct GatesParams {
   __nv_bfloat16* Xn; long long ldX; long long x_lo; int hoff;
   const float* wdec; const float* bdec; float* Y; long long ldY;   // optional D head: Y[row * ldY] += partial dots (zero-filled)
   ZeroRow zero;               // optional: next step's scores rows
-  float* scratch;             // [m-tiles][cluster][128][10] fp32 exchange buffer
+  float* scratch;             // [m-tiles][cluster][GF_NSTAT][128] fp32 exchange buffer
+  int debug;
 };
 
 template <int NPC>
@@ -62,10 +69,10 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int STAGE = 2 * A_PART + 2 * B_PART;
   constexpr int STAGES = GF_SMEM_BUDGET / STAGE;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_part = reinterpret_cast<float*>(smem + STAGES * STAGE);          // [128][8]  half-1 partials (gates)
-  float* s_part2 = s_part + 128 * 8;                                        // [128][2]  half-1 partials (state)
-  float* s_ln = s_part2 + 128 * 2;                                          // [10][NPC] gamma[5], beta[5] of this CTA's units
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared state space
+  float* s_part = reinterpret_cast<float*>(smem + STAGES * STAGE);          // [NPC/16][128][8] chunk partials (gates)
+  float* s_part2 = s_part + (NPC / 16) * 128 * 8;                           // [NPC/16][128][2] chunk partials (state)
+  float* s_ln = s_part2 + (NPC / 16) * 128 * 2;                             // [10][NPC] gamma[5], beta[5] of this CTA's units
   float* s_wd = s_ln + 10 * NPC;                                            // [NPC] D head weights
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_wd + NPC);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -94,6 +101,10 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();
+  unsigned long long tq[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool dbg = p.debug && threadIdx.x == 64 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == 5);
+#define SGG_TS(i) if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[i]))
+  SGG_TS(0);
 
   // per-row statistics produced by the epilogue (registers of the epilogue threads)
   if (warp == 0) {
@@ -142,6 +153,14 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 
   // ===================== epilogue (warps 2..9); warps 0 / 1 only take part in the cluster barriers =====================
+  // Thread = (row of the m-tile = TMEM lane, half of the CTA's units); a thread walks its units in chunks of 16.
+  //  * Everything a thread produces for its row is staged in shared memory (the operand ring is free once the last MMA
+  //    has retired) and leaves the SM through cooperative stores in which a warp writes whole 128-byte lines: a
+  //    row-per-thread store pattern touches 32 partial sectors per instruction (measured: 20 us of epilogue).
+  //  * The gate loop and the chunk loop are run-time loops over ONE copy of the cell code: fully unrolled, the epilogue
+  //    was instruction-fetch bound (measured: 28 us for 32 units per thread against 7 us for 16).
+  //  * The cross-CTA partials are pulled from the L2 scratch by cooperative, fully coalesced float4 loads (one L2
+  //    round trip) into shared memory; per-thread scalar pulls serialised ~16 round trips.
   const bool epi = warp >= 2;
   const int q = warp & 3;                        // TMEM lane quadrant of this warp
   const int half = epi ? ((warp - 2) >> 2) : 0;  // which half of the CTA's units of the row
@@ -149,11 +168,38 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const long long row = (long long)m0 + rt;
   const bool row_ok = epi && row < p.nrows;
   const int et = threadIdx.x - 64;               // 0..255 among the epilogue threads
-  // TMEM column of (gate g, this thread's unit k): NPC = 32: g*32 + half*16 + k ; NPC = 64: half*128 + g*32 + k
-  const uint32_t tcol0 = (NPC == 32) ? (uint32_t)(half * 16) : (uint32_t)(half * 128);
-  const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tcol0;
-  const int ut0 = u0 + half * UPT;               // first hidden unit of this thread
-  float* scr = p.scratch + ((long long)blockIdx.y * CS) * 128 * 10;   // this m-tile's exchange block: [CS][128][10]
+  const int ew = warp - 2;                       // 0..7
+  constexpr int NCH = UPT / 16;                  // 16-unit chunks per thread
+  constexpr int NSLOT = NPC / 16;                // 16-unit chunks per row in this CTA
+  // local unit index of (half, chunk c, k): lu = half * UPT + c * 16 + k ; its TMEM column for gate g:
+  //   NPC = 32: g * 32 + lu ;  NPC = 64: (lu >> 5) * 128 + g * 32 + (lu & 31)
+  const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+  // exchange block of this m-tile: [CS][12][128] fp32 (row fastest: coalesced), stat rows 0-7 gates, 8-9 state, 10 head
+  float* scr = p.scratch + ((long long)blockIdx.y * CS) * GF_NSTAT * 128;
+  constexpr int QS = N + 4;                      // staging pitches (floats): (pitch mod 32) = 4 keeps float4 accesses of
+  constexpr int CSP = NPC + 4;                   // a quarter-warp of rows on distinct banks
+  float* sQ = reinterpret_cast<float*>(smem);    // [128][QS]   pre-activations (staging for the Q store)
+  float* sST = reinterpret_cast<float*>(smem + ((128 * QS * 4 + 1023) & ~1023));   // [CS][8][128] pulled partials
+  // NPC = 32: the ring has room for separate c' / sigmoid(o) tiles, so the 64 KB Q store can be issued late (between the
+  // arrive and the wait of the SECOND cluster barrier): arrive.release waits for the thread's outstanding global stores,
+  // and only the few scratch stores should be in front of it.  NPC = 64: the tiles alias sQ, the Q store stays early.
+  constexpr bool kLateQ = (NPC == 32);
+  float* sCN = kLateQ ? sST + CS * 8 * 128 : sQ; // [128][CSP]  c' then c_new
+  float* sH = sCN + 128 * CSP;                   // [128][CSP]  sigmoid(o) then h
+  auto store_q = [&]() {
+    // warp = rows ew, ew + 8, ...; a lane covers one float4 of the row's N staged values; NPC consecutive floats belong
+    // to one gate (global column gate * 512 + u0 + u)
+    for (int r = ew; r < 128; r += 8) {
+      if (m0 + r >= p.nrows) break;
+      float* qrow = p.Q + (long long)(m0 + r) * p.ldQ + u0;
+#pragma unroll
+      for (int c = lane * 4; c < N; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(sQ + r * QS + c);
+        const int g = c / NPC, u = c - g * NPC;
+        *reinterpret_cast<float4*>(qrow + g * 512 + u) = v;
+      }
+    }
+  };
 
   float gmean[4], grstd[4];
   if (epi) {
@@ -172,200 +218,263 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c = lo4 + (et & 7); c < hi4; c += 8) d[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    if (row_ok) prefetch_l1(p.Cin + row * 512 + ut0);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    // ---- pass 1: pre-activations out (for the reverse pass), local (mean, M2) per gate over this thread's units
-    float part[8];
+    SGG_TS(1);
+    // ---- pass 1: (mean, M2) per gate and 16-unit chunk; pre-activations into the staging tile
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int lu = half * UPT + c * 16;
+      const uint32_t tcol = (NPC == 32) ? (uint32_t)lu : (uint32_t)((lu >> 5) * 128 + (lu & 31));
+      float* slot = s_part + ((half * NCH + c) * 128 + rt) * 8;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[16];
+        tmem_ld_32x16(tlane + tcol + g * 32, r);
+        tmem_ld_wait();
+        float x[16];
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { x[k] = __uint_as_float(r[k]); sum += x[k]; }
+        const float mu = sum * (1.0f / 16.0f);
+        float m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const float d = x[k] - mu; m2 = fmaf(d, d, m2); }
+        *reinterpret_cast<float2*>(slot + 2 * g) = make_float2(mu, m2);
+        float4* dst = reinterpret_cast<float4*>(sQ + rt * QS + g * NPC + lu);   // staging column = gate * NPC + unit
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) dst[k >> 2] = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // combine the row's NSLOT chunk partials (Chan, equal group sizes) and publish them: thread = (row, gate pair)
+    {
+      float* dst = scr + (long long)j * GF_NSTAT * 128 + rt;
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = half * 2 + gg;
+        float pm[NSLOT], mu = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl) {
+          const float2 v = *reinterpret_cast<const float2*>(s_part + (sl * 128 + rt) * 8 + 2 * g);
+          pm[sl] = v.x; mu += v.x; m2 += v.y;
+        }
+        mu *= (1.0f / NSLOT);
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl) { const float d = pm[sl] - mu; m2 = fmaf(16.0f * d, d, m2); }
+        dst[(2 * g) * 128] = mu;
+        dst[(2 * g + 1) * 128] = m2;
+      }
+    }
+  }
+  SGG_TS(2);
+  cluster_arrive_release();
+  float cin_pref[4] = {0.f, 0.f, 0.f, 0.f};
+  if (epi) {
+    if (!kLateQ) store_q();   // while the cluster gathers at the barrier
+    if (row_ok) {   // first quad of c_in: its L2 round trip overlaps the barrier (the rest of the row's line follows it into L1)
+      const float4 t = *reinterpret_cast<const float4*>(p.Cin + row * 512 + u0 + half * UPT);
+      cin_pref[0] = t.x; cin_pref[1] = t.y; cin_pref[2] = t.z; cin_pref[3] = t.w;
+    }
+  }
+  cluster_wait_acquire();
+  SGG_TS(3);
+  if (epi) {
+    // ---- pass 2: pull the CS x 8 gate partials of the m-tile (coalesced float4, one round trip), then per-row statistics
+    {
+      const float4* src = reinterpret_cast<const float4*>(scr);
+      float4* dst = reinterpret_cast<float4*>(sST);
+#pragma unroll
+      for (int i = et; i < CS * 8 * 32; i += GF_EPI) {
+        const int sblk = i >> 8, rem = i & 255;                       // 8 stat rows x 32 float4 per CTA block
+        dst[i] = __ldcg(src + sblk * (GF_NSTAT * 32) + rem);
+      }
+    }
+    SGG_TS(6);
+    asm volatile("bar.sync 1, 256;" ::: "memory");                    // also: every warp has finished its Q-store rows
+    SGG_TS(7);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      float x[UPT];
-      if (UPT == 16) {
-        uint32_t r[16];
-        tmem_ld_32x16(taddr + g * 32, r);
-        tmem_ld_wait();
+      float pm[CS], mu = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = __uint_as_float(r[k]);
-      } else {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + g * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < UPT; ++k) x[k] = __uint_as_float(r[k]);
+      for (int s2 = 0; s2 < CS; ++s2) {
+        pm[s2] = sST[(s2 * 8 + 2 * g) * 128 + rt];
+        mu += pm[s2];
+        m2 += sST[(s2 * 8 + 2 * g + 1) * 128 + rt];
       }
-      float s = 0.f;
+      mu *= (1.0f / CS);
+      float dd = 0.f;
 #pragma unroll
-      for (int k = 0; k < UPT; ++k) s += x[k];
-      const float mu = s * (1.0f / UPT);
+      for (int s2 = 0; s2 < CS; ++s2) { const float d = pm[s2] - mu; dd = fmaf(d, d, dd); }
+      gmean[g] = mu;
+      grstd[g] = fast_rsqrt((m2 + dd * NPC) * (1.0f / 512.0f) + 1e-12f);
+    }
+    SGG_TS(8);
+    // ---- pass 3: gate activations and the cell update, chunk by chunk; c' and sigmoid(o) go to the staging tiles
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int lu = half * UPT + c * 16;
+      const uint32_t tcol = (NPC == 32) ? (uint32_t)lu : (uint32_t)((lu >> 5) * 128 + (lu & 31));
+      float cin[16];
+      if (row_ok) {
+        const float4* src = reinterpret_cast<const float4*>(p.Cin + row * 512 + u0 + lu);
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) { const float4 t = src[k >> 2]; cin[k] = t.x; cin[k + 1] = t.y; cin[k + 2] = t.z; cin[k + 3] = t.w; }
+        if (c == 0) { cin[0] = cin_pref[0]; cin[1] = cin_pref[1]; cin[2] = cin_pref[2]; cin[3] = cin_pref[3]; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cin[k] = 0.f;
+      }
+      if (dbg) { float acc = 0.f; for (int k = 0; k < 16; ++k) acc += cin[k]; if (acc == 12345.678f) printf("x"); }
+      SGG_TS(10);
+      float cp[16], so[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) cp[k] = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[16];
+        tmem_ld_32x16(tlane + tcol + g * 32, r);
+        tmem_ld_wait();
+        const float fb = (g == 2) ? 1.0f : 0.f;
+        const float kk = (g == 1) ? -2.0f : -1.0f;
+        const float mean = g == 0 ? gmean[0] : (g == 1 ? gmean[1] : (g == 2 ? gmean[2] : gmean[3]));
+        const float rstd = g == 0 ? grstd[0] : (g == 1 ? grstd[1] : (g == 2 ? grstd[2] : grstd[3]));
+        const float* gam = s_ln + g * NPC + lu;
+        const float* bet = s_ln + (5 + g) * NPC + lu;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float a = fmaf((__uint_as_float(r[k]) - mean) * rstd, gam[k], bet[k]) + fb;
+          const float e = fast_exp(kk * fabsf(a));
+          const float rr = fast_rcp(1.0f + e);
+          const float y = (g == 1) ? copysignf((1.0f - e) * rr, a) : (a >= 0.f ? rr : e * rr);
+          // g = 0: cp = sigmoid(i); g = 1: cp *= tanh(j); g = 2: cp += c * sigmoid(f + 1); g = 3: so = sigmoid(o)
+          cp[k] = g == 0 ? y : (g == 1 ? cp[k] * y : (g == 2 ? fmaf(cin[k], y, cp[k]) : cp[k]));
+          so[k] = y;
+        }
+      }
+      if (dbg) { float acc = 0.f; for (int k = 0; k < 16; ++k) acc += cp[k] + so[k]; if (acc == 12345.678f) printf("x"); }
+      SGG_TS(11);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sum += cp[k];
+      const float mu = sum * (1.0f / 16.0f);
       float m2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < UPT; ++k) { const float d = x[k] - mu; m2 = fmaf(d, d, m2); }
-      part[2 * g] = mu; part[2 * g + 1] = m2;
-      if (row_ok) {
-        float4* dst = reinterpret_cast<float4*>(p.Q + row * p.ldQ + g * 512 + ut0);
+      for (int k = 0; k < 16; ++k) { const float d = cp[k] - mu; m2 = fmaf(d, d, m2); }
+      *reinterpret_cast<float2*>(s_part2 + ((half * NCH + c) * 128 + rt) * 2) = make_float2(mu, m2);
 #pragma unroll
-        for (int k = 0; k < UPT; k += 4) dst[k >> 2] = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
+      for (int k = 0; k < 16; k += 4) {
+        *reinterpret_cast<float4*>(sCN + rt * CSP + lu + k) = make_float4(cp[k], cp[k + 1], cp[k + 2], cp[k + 3]);
+        *reinterpret_cast<float4*>(sH + rt * CSP + lu + k) = make_float4(so[k], so[k + 1], so[k + 2], so[k + 3]);
       }
     }
-    // combine the two halves of the row (Chan), publish this CTA's partial for the row
-    if (half == 1) {
-      *reinterpret_cast<float4*>(s_part + rt * 8) = make_float4(part[0], part[1], part[2], part[3]);
-      *reinterpret_cast<float4*>(s_part + rt * 8 + 4) = make_float4(part[4], part[5], part[6], part[7]);
-    }
+    SGG_TS(9);
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (half == 0) {
-      const float4 o0 = *reinterpret_cast<const float4*>(s_part + rt * 8), o1 = *reinterpret_cast<const float4*>(s_part + rt * 8 + 4);
-      const float om[4] = {o0.x, o0.z, o1.x, o1.z}, o2[4] = {o0.y, o0.w, o1.y, o1.w};
-      float c[8];
+    if (half == 0) {   // row partial of the state LayerNorm
+      float pm[NSLOT], mu = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float d = om[g] - part[2 * g];
-        c[2 * g] = 0.5f * (om[g] + part[2 * g]);
-        c[2 * g + 1] = part[2 * g + 1] + o2[g] + d * d * (0.5f * UPT);
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const float2 v = *reinterpret_cast<const float2*>(s_part2 + (sl * 128 + rt) * 2);
+        pm[sl] = v.x; mu += v.x; m2 += v.y;
       }
-      float* dst = scr + ((long long)j * 128 + rt) * 10;
-      *reinterpret_cast<float2*>(dst) = make_float2(c[0], c[1]);
-      *reinterpret_cast<float2*>(dst + 2) = make_float2(c[2], c[3]);
-      *reinterpret_cast<float2*>(dst + 4) = make_float2(c[4], c[5]);
-      *reinterpret_cast<float2*>(dst + 6) = make_float2(c[6], c[7]);
+      mu *= (1.0f / NSLOT);
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) { const float d = pm[sl] - mu; m2 = fmaf(16.0f * d, d, m2); }
+      float* dst = scr + (long long)j * GF_NSTAT * 128 + rt;
+      dst[8 * 128] = mu;
+      dst[9 * 128] = m2;
     }
   }
+  SGG_TS(4);
   cluster_arrive_release();
+  if (epi && kLateQ) store_q();
   cluster_wait_acquire();
-  float cp[UPT], so[UPT];
+  SGG_TS(5);
   if (epi) {
-    // ---- pass 2: full-row statistics of the four gates from the CS partials (NPC units each)
+    float rc, cmean;
     {
-      float mu[4] = {0.f, 0.f, 0.f, 0.f}, pm[4][CS], m2[4] = {0.f, 0.f, 0.f, 0.f};
+      float pm[CS], mu = 0.f, m2 = 0.f;
 #pragma unroll
-      for (int s = 0; s < CS; ++s) {
-        const float* src = scr + ((long long)s * 128 + rt) * 10;
-        const float2 a0 = __ldcg(reinterpret_cast<const float2*>(src)), a1 = __ldcg(reinterpret_cast<const float2*>(src + 2));
-        const float2 a2 = __ldcg(reinterpret_cast<const float2*>(src + 4)), a3 = __ldcg(reinterpret_cast<const float2*>(src + 6));
-        pm[0][s] = a0.x; pm[1][s] = a1.x; pm[2][s] = a2.x; pm[3][s] = a3.x;
-        m2[0] += a0.y; m2[1] += a1.y; m2[2] += a2.y; m2[3] += a3.y;
-        mu[0] += a0.x; mu[1] += a1.x; mu[2] += a2.x; mu[3] += a3.x;
+      for (int s2 = 0; s2 < CS; ++s2) {
+        const float* src = scr + (long long)s2 * GF_NSTAT * 128 + rt;
+        pm[s2] = __ldcg(src + 8 * 128);
+        m2 += __ldcg(src + 9 * 128);
+        mu += pm[s2];
       }
+      mu *= (1.0f / CS);
+      float dd = 0.f;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        mu[g] *= (1.0f / CS);
-        float dd = 0.f;
-#pragma unroll
-        for (int s = 0; s < CS; ++s) { const float d = pm[g][s] - mu[g]; dd = fmaf(d, d, dd); }
-        const float var = (m2[g] + dd * NPC) * (1.0f / 512.0f);
-        gmean[g] = mu[g];
-        grstd[g] = 1.0f / sqrtf(var + 1e-12f);
-      }
+      for (int s2 = 0; s2 < CS; ++s2) { const float d = pm[s2] - mu; dd = fmaf(d, d, dd); }
+      cmean = mu;
+      rc = fast_rsqrt((m2 + dd * NPC) * (1.0f / 512.0f) + 1e-12f);
     }
-    // ---- pass 3: gate activations and the cell update for this thread's units
-    const float* lg = s_ln + half * UPT;          // gamma[v][u] at lg[v * NPC + u], beta at lg[(5 + v) * NPC + u]
-    float cin[UPT];
-    if (row_ok) {
-      const float4* src = reinterpret_cast<const float4*>(p.Cin + row * 512 + ut0);
+    // new cell state and hidden state of this thread's units, in place in the staging tiles
+    float sy = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int lu = half * UPT + c * 16;
+      const float* gam = s_ln + 4 * NPC + lu;
+      const float* bet = s_ln + 9 * NPC + lu;
 #pragma unroll
-      for (int k = 0; k < UPT; k += 4) { const float4 t = src[k >> 2]; cin[k] = t.x; cin[k + 1] = t.y; cin[k + 2] = t.z; cin[k + 3] = t.w; }
-    } else {
-#pragma unroll
-      for (int k = 0; k < UPT; ++k) cin[k] = 0.f;
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float x[UPT];
-      if (UPT == 16) {
-        uint32_t r[16];
-        tmem_ld_32x16(taddr + g * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = __uint_as_float(r[k]);
-      } else {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + g * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < UPT; ++k) x[k] = __uint_as_float(r[k]);
-      }
-      const float fb = (g == 2) ? 1.0f : 0.f;
-      const float kk = (g == 1) ? -2.0f : -1.0f;
-#pragma unroll
-      for (int k = 0; k < UPT; ++k) {
-        const float a = fmaf((x[k] - gmean[g]) * grstd[g], lg[g * NPC + k], lg[(5 + g) * NPC + k]) + fb;
-        const float e = __expf(kk * fabsf(a));
-        const float rr = 1.0f / (1.0f + e);
-        const float y = (g == 1) ? copysignf((1.0f - e) * rr, a) : (a >= 0.f ? rr : e * rr);
-        // g = 0: cp holds sigmoid(i); g = 1: cp = si * tanh(j); g = 2: cp += c * sigmoid(f + 1); g = 3: so = sigmoid(o)
-        if (g == 0) cp[k] = y;
-        else if (g == 1) cp[k] *= y;
-        else if (g == 2) cp[k] = fmaf(cin[k], y, cp[k]);
-        else so[k] = y;
-      }
-    }
-    // local (mean, M2) of c' and the second exchange
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < UPT; ++k) s += cp[k];
-    const float mu = s * (1.0f / UPT);
-    float m2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < UPT; ++k) { const float d = cp[k] - mu; m2 = fmaf(d, d, m2); }
-    if (half == 1) *reinterpret_cast<float2*>(s_part2 + rt * 2) = make_float2(mu, m2);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (half == 0) {
-      const float2 o = *reinterpret_cast<const float2*>(s_part2 + rt * 2);
-      const float d = o.x - mu;
-      *reinterpret_cast<float2*>(scr + ((long long)j * 128 + rt) * 10 + 8) = make_float2(0.5f * (o.x + mu), m2 + o.y + d * d * (0.5f * UPT));
-    }
-  }
-  cluster_arrive_release();
-  cluster_wait_acquire();
-  if (epi) {
-    float mu = 0.f, m2 = 0.f, pm[CS];
-#pragma unroll
-    for (int s = 0; s < CS; ++s) {
-      const float2 a = __ldcg(reinterpret_cast<const float2*>(scr + ((long long)s * 128 + rt) * 10 + 8));
-      pm[s] = a.x; mu += a.x; m2 += a.y;
-    }
-    mu *= (1.0f / CS);
-    float dd = 0.f;
-#pragma unroll
-    for (int s = 0; s < CS; ++s) { const float d = pm[s] - mu; dd = fmaf(d, d, dd); }
-    const float rc = 1.0f / sqrtf((m2 + dd * NPC) * (1.0f / 512.0f) + 1e-12f);
-    if (row_ok) {
-      const float* lg = s_ln + half * UPT;
-      float cn[UPT], h[UPT];
-      float sy = 0.f;
-#pragma unroll
-      for (int k = 0; k < UPT; ++k) {
-        cn[k] = fmaf((cp[k] - mu) * rc, lg[4 * NPC + k], lg[9 * NPC + k]);
-        h[k] = tanhf_(cn[k]) * so[k];
-        if (p.Y) sy = fmaf(h[k], s_wd[half * UPT + k], sy);
-      }
-      float4* co = reinterpret_cast<float4*>(p.Cout + row * 512 + ut0);
-#pragma unroll
-      for (int k = 0; k < UPT; k += 4) co[k >> 2] = make_float4(cn[k], cn[k + 1], cn[k + 2], cn[k + 3]);
-#pragma unroll
-      for (int k = 0; k < UPT; k += 8) {
-        uint32_t ch[4], cl[4], hh[4], hl[4];
+      for (int k = 0; k < 16; k += 4) {
+        const float4 cpv = *reinterpret_cast<const float4*>(sCN + rt * CSP + lu + k), sov = *reinterpret_cast<const float4*>(sH + rt * CSP + lu + k);
+        const float cpa[4] = {cpv.x, cpv.y, cpv.z, cpv.w}, soa[4] = {sov.x, sov.y, sov.z, sov.w};
+        float cn[4], h[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 a0, b0, a1, b1;
-          split_bf16(cn[k + 2 * e], a0, b0); split_bf16(cn[k + 2 * e + 1], a1, b1);
-          ch[e] = pack_bf16x2(a0, a1); cl[e] = pack_bf16x2(b0, b1);
-          split_bf16(h[k + 2 * e], a0, b0); split_bf16(h[k + 2 * e + 1], a1, b1);
-          hh[e] = pack_bf16x2(a0, a1); hl[e] = pack_bf16x2(b0, b1);
+          cn[e] = fmaf((cpa[e] - cmean) * rc, gam[k + e], bet[k + e]);
+          h[e] = tanhf_(cn[e]) * soa[e];
+          if (p.Y) sy = fmaf(h[e], s_wd[lu + k + e], sy);
         }
+        *reinterpret_cast<float4*>(sCN + rt * CSP + lu + k) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(sH + rt * CSP + lu + k) = make_float4(h[0], h[1], h[2], h[3]);
+      }
+    }
+    if (p.Y && half == 1) s_part2[rt] = sy;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (p.Y && half == 0) scr[((long long)j * GF_NSTAT + 10) * 128 + rt] = sy + s_part2[rt];   // head partial of this CTA
+    // ---- cooperative stores: 8 lanes cover one row's NPC floats (4 floats each for NPC = 32, 8 for NPC = 64)
+    constexpr int FPL = NPC / 8;                   // floats per lane: 4 or 8
+    for (int r = ew * 4 + (lane >> 3); r < 128; r += 32) {
+      const long long grow = (long long)m0 + r;
+      if (grow >= p.nrows) continue;
+      const int c0 = (lane & 7) * FPL;
+#pragma unroll
+      for (int k = 0; k < FPL; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(sCN + r * CSP + c0 + k), b4 = *reinterpret_cast<const float4*>(sH + r * CSP + c0 + k);
+        const float cn[4] = {a4.x, a4.y, a4.z, a4.w}, h[4] = {b4.x, b4.y, b4.z, b4.w};
+        *reinterpret_cast<float4*>(p.Cout + grow * 512 + u0 + c0 + k) = a4;
+        __nv_bfloat16 a[4], b[4], cc[4], d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { split_bf16(cn[e], a[e], b[e]); split_bf16(h[e], cc[e], d[e]); }
         if (p.CH) {
-          __nv_bfloat16* d = p.CH + row * p.ldCH + ut0 + k;
-          *reinterpret_cast<uint4*>(d) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-          *reinterpret_cast<uint4*>(d + p.ch_lo) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+          __nv_bfloat16* dst = p.CH + grow * p.ldCH + u0 + c0 + k;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]));
+          *reinterpret_cast<uint2*>(dst + p.ch_lo) = make_uint2(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]));
         }
-        if (p.Xn) {
-          __nv_bfloat16* d = p.Xn + row * p.ldX + p.hoff + ut0 + k;
-          *reinterpret_cast<uint4*>(d) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<uint4*>(d + p.x_lo) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+        if (p.Xn) {   // the h columns start at C + U (812 for the discriminator): 8-byte aligned only
+          __nv_bfloat16* dst = p.Xn + grow * p.ldX + p.hoff + u0 + c0 + k;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(cc[0], cc[1]), pack_bf16x2(cc[2], cc[3]));
+          *reinterpret_cast<uint2*>(dst + p.x_lo) = make_uint2(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]));
         }
       }
-      if (p.Y) atomicAdd(p.Y + row * p.ldY, sy + ((j == 0 && half == 0) ? p.bdec[0] : 0.f));
     }
+  }
+  if (p.Y) {   // the discriminator's head (disc:90): CTA 0 of the cluster sums the per-CTA partial dot products (no atomics)
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    if (j == 0 && epi && half == 0 && row_ok) {
+      float y = p.bdec[0];
+#pragma unroll
+      for (int s2 = 0; s2 < CS; ++s2) y += __ldcg(scr + ((long long)s2 * GF_NSTAT + 10) * 128 + rt);
+      p.Y[row * p.ldY] = y;
+    }
+  }
+  if (dbg) {
+    unsigned long long t6;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t6));
+    printf("gates<%d> cta %d rows %d kb %d: mainloop %llu  pass1 %llu  bar1 %llu  pass23 %llu [pull %llu bar %llu stats %llu cell %llu (cin %llu gates %llu) rest %llu]  bar2 %llu  tail %llu ns\n", NPC, (int)blockIdx.x,
+           p.nrows, p.kb, tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[6] - tq[3], tq[7] - tq[6], tq[8] - tq[7], tq[9] - tq[8], tq[10] - tq[8], tq[11] - tq[10], tq[4] - tq[9], tq[5] - tq[4], t6 - tq[5]);
   }
   tc_fence_before();
   __syncthreads();
@@ -377,7 +486,7 @@ static int gates_smem_bytes() {
   constexpr int N = 4 * NPC;
   constexpr int STAGE = 2 * 128 * 64 * 2 + 2 * N * 64 * 2;
   constexpr int STAGES = GF_SMEM_BUDGET / STAGE;
-  return STAGES * STAGE + (128 * 8 + 128 * 2 + 10 * NPC + NPC) * 4 + (2 * STAGES + 1) * 8 + 16 + 1024;
+  return STAGES * STAGE + ((NPC / 16) * 128 * 10 + 10 * NPC + NPC) * 4 + (2 * STAGES + 1) * 8 + 16 + 1024;
 }
 
 template <int NPC>
@@ -436,7 +545,7 @@ static int gates_max_clusters(int npc) {
   return n;
 }
 
-constexpr int GATES_SCRATCH_FLOATS_PER_MTILE = 16 * 128 * 10;
+constexpr int GATES_SCRATCH_FLOATS_PER_MTILE = 16 * GF_NSTAT * 128;
 long long gates_scratch_floats(long long max_rows) { return (max_rows + 127) / 128 * GATES_SCRATCH_FLOATS_PER_MTILE; }
 
 // SGG_FUSED_GATES=0 keeps the gate GEMM and the cell as two kernels (A/B measurements); =16 / =8 force a cluster shape.
@@ -455,6 +564,7 @@ int gates_fused(const __nv_bfloat16* X, long long ldx, int KXP, const __nv_bfloa
   if (p.nrows <= 0) return 0;
   SGG_CHECK(KXP % 64 == 0, "gates_fused: KXP=%d must be a multiple of 64", KXP);
   p.kb = KXP / 64; p.a_lo = KXP; p.b_lo = rK;
+  { static int d = -1; if (d < 0) { const char* e = getenv("SGG_GATES_DEBUG"); d = (e && e[0] == '1') ? 1 : 0; } p.debug = d; }
   const int mt = (p.nrows + 127) / 128;
   const int c16 = gates_max_clusters(32), c8 = gates_max_clusters(64);
   int npc;

@@ -79,7 +79,7 @@ __device__ __forceinline__ void ln_norm(const V16& x, V16& n, float& r) {
     s = fmaf(n[j], n[j], s);
   }
   const float var = warp_sum(s) * INV_LH;
-  r = 1.0f / sqrtf(var + LN_EPS_F);
+  r = fast_rsqrt(var + LN_EPS_F);
 #pragma unroll
   for (int j = 0; j < 16; ++j) n[j] *= r;
 }
@@ -160,8 +160,8 @@ __device__ __forceinline__ void gate_fwd(int G, const float* q, const float* qd,
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float a = fmaf(n[j], g[j], bt[j]) + fb;
-    const float e = __expf(k * fabsf(a));
-    const float rr = 1.0f / (1.0f + e);
+    const float e = fast_exp(k * fabsf(a));
+    const float rr = fast_rcp(1.0f + e);
     const float y = is_tanh ? copysignf((1.0f - e) * rr, a) : (a >= 0.f ? rr : e * rr);
     act[j] = y;
     if (TAN) actd[j] = (is_tanh ? (1.f - y * y) : y * (1.f - y)) * nd[j] * g[j];
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(LS_THREADS) lstm_fwd_kernel(const LstmFwdParam
 #pragma unroll
     for (int e = 0; e < 4; ++e) { cp.v[e] -= mean; s2[0] = fmaf(cp.v[e], cp.v[e], s2[0]); }
     block_sum(s2, sm.red, tog);
-    const float rc = 1.0f / sqrtf(s2[0] * INV_LH + LN_EPS_F);
+    const float rc = fast_rsqrt(s2[0] * INV_LH + LN_EPS_F);
     F4 cn, h;
     float sy[1] = {0.f};
     const F4 wd = p.Y ? ld4(p.wdec) : F4{{0.f, 0.f, 0.f, 0.f}};
@@ -297,7 +297,7 @@ __device__ __forceinline__ void state_fwd(const LstmSmemFwd& sm, const float* c_
 #pragma unroll
   for (int e = 0; e < 4; ++e) { cp.v[e] -= mean; s2[0] = fmaf(cp.v[e], cp.v[e], s2[0]); }
   block_sum(s2, red, tog);
-  s.rc = 1.0f / sqrtf(s2[0] * INV_LH + LN_EPS_F);
+  s.rc = fast_rsqrt(s2[0] * INV_LH + LN_EPS_F);
 #pragma unroll
   for (int e = 0; e < 4; ++e) s.nc.v[e] = cp.v[e] * s.rc;
   if (TAN) {

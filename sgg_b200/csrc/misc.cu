@@ -281,7 +281,10 @@ int colsum(const float* src, long long ld, int rows, int cols, float* out, cudaS
 // theta -= lr_t * m / (sqrt(v) + eps).  Flat fp32 buckets; also refreshes the bf16 shadow of
 // each tensor (the GEMM B operands), whose rows are padded to a 16-byte pitch.
 namespace sgg {
-struct AdamSeg { long long off; long long sh_off; int cols; int pitch; long long n; long long lo_off; };
+// sh2_off >= 0: a second shadow copy with the columns in the fused gate kernel's interleaved order (gates.cu
+// perm_gate_col: groups of 32 hidden units, [i | j | f | o] inside a group); same pitch and lo offset.
+struct AdamSeg { long long off; long long sh_off; int cols; int pitch; long long n; long long lo_off; long long sh2_off; };
+__host__ __device__ __forceinline__ unsigned perm_gate_col4(unsigned c) { return ((c & 511u) >> 5) * 128u + (c >> 9) * 32u + (c & 31u); }
 constexpr int ADAM_MAX_SEG = 24;
 constexpr int ADAM_UNROLL = 4;                         // float4 quadruples in flight per thread and array
 constexpr int ADAM_TILE = 256 * 4 * ADAM_UNROLL;       // floats per CTA
@@ -382,12 +385,22 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
         __nv_bfloat16* dst = p.shadow + sg.sh_off + (long long)r * sg.pitch + c;
         *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
         *reinterpret_cast<uint2*>(dst + sg.lo_off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+        if (sg.sh2_off >= 0) {   // 4 consecutive units of one gate stay consecutive in the interleaved order
+          __nv_bfloat16* d2 = p.shadow + sg.sh2_off + (long long)r * sg.pitch + perm_gate_col4(c);
+          *reinterpret_cast<uint2*>(d2) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+          *reinterpret_cast<uint2*>(d2 + sg.lo_off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+        }
       } else {
         for (int e = 0; e < 4; ++e)
           if (i + e < sg.n) {
             __nv_bfloat16* dst = p.shadow + sg.sh_off + (long long)r * sg.pitch + c;
             dst[0] = h[e];
             dst[sg.lo_off] = l[e];
+            if (sg.sh2_off >= 0) {
+              __nv_bfloat16* d2 = p.shadow + sg.sh2_off + (long long)r * sg.pitch + perm_gate_col4(c);
+              d2[0] = h[e];
+              d2[sg.lo_off] = l[e];
+            }
             if (++c == (unsigned)sg.cols) { c = 0; ++r; }
           }
       }
@@ -418,6 +431,11 @@ __global__ void shadow_kernel(const float* theta, __nv_bfloat16* shadow, AdamSeg
     split_bf16(theta[sg.off + i], h, l);
     shadow[sg.sh_off + r * sg.pitch + c] = h;
     shadow[sg.sh_off + sg.lo_off + r * sg.pitch + c] = l;
+    if (sg.sh2_off >= 0) {
+      const long long c2 = perm_gate_col4((unsigned)c);
+      shadow[sg.sh2_off + r * sg.pitch + c2] = h;
+      shadow[sg.sh2_off + sg.lo_off + r * sg.pitch + c2] = l;
+    }
   }
 }
 int refresh_shadow(const float* theta, __nv_bfloat16* shadow, const AdamSeg& sg, cudaStream_t stream) {

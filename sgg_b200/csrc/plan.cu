@@ -100,7 +100,8 @@ struct ParamLayout {
   long long Watt, batt, K, lng[5], lnb[5], Wdec, bdec, Wemb, total;   // fp32 bucket offsets (floats)
   // bf16 shadow: each GEMM weight is stored as [hi rows | lo rows] (w ~= hi + lo, 2^-17 relative), rows padded
   // to a multiple of 64 with zeros, so that one tensor map serves both parts and a k-block never straddles them.
-  long long sWa, sWh, sK, sWdec, sWemb, stotal;                       // bf16 shadow offsets (elements)
+  long long sWa, sWh, sK, sKp, sWdec, sWemb, stotal;                  // bf16 shadow offsets (elements); sKp: the LSTM kernel
+                                                                      // again, columns interleaved for the fused gate kernel
   int pAtt, pK, pWdec, pWemb;                                         // shadow row pitches
   int rWa, rWh, rK, rWdec, rWemb;                                     // padded row counts (lo part starts at row r*)
 };
@@ -134,6 +135,7 @@ static ParamLayout param_layout(bool gen, const sgg_dims_t& d) {
   L.sWa = stake(2LL * L.rWa * L.pAtt);
   L.sWh = stake(2LL * L.rWh * L.pAtt);
   L.sK = stake(2LL * L.rK * L.pK);
+  L.sKp = stake(2LL * L.rK * L.pK);
   L.sWdec = gen ? stake(2LL * L.rWdec * L.pWdec) : -1;
   L.sWemb = gen ? -1 : stake(2LL * L.rWemb * L.pWemb);
   L.stotal = s;
@@ -156,6 +158,7 @@ static int fill_adam_segs(const ParamLayout& L, AdamSeg* seg) {
   seg[n++] = {L.Wdec, L.sWdec, L.OUT, L.pWdec, (long long)L.H * L.OUT, (long long)L.rWdec * L.pWdec};
   seg[n++] = {L.bdec, -1, L.OUT, L.OUT, L.OUT, 0};
   if (!L.gen) seg[n++] = {L.Wemb, L.sWemb, L.E, L.pWemb, (long long)L.V * L.E, (long long)L.rWemb * L.pWemb};
+  for (int i = 0; i < n; ++i) seg[i].sh2_off = (seg[i].off == L.K) ? L.sKp : -1;
   return n;
 }
 
@@ -165,6 +168,7 @@ struct NetWs {
   __nv_bfloat16* X; float* Cf; __nv_bfloat16* CH; float* EA; float* ED; float* Q; float* P;
   __nv_bfloat16* QB; float* XB; __nv_bfloat16* EB; float* CB; float* PB; __nv_bfloat16* PBH;
   float* Y;
+  float* GSCR;   // exchange scratch of the fused gate kernel (gates.cu)
 };
 struct Ws {
   NetWs g, d;
@@ -217,6 +221,7 @@ static Ws ws_layout(const sgg_dims_t& d, void* base) {
     n.PB = (float*)take((long long)m.B * m.RP * 4);
     n.PBH = (__nv_bfloat16*)take((long long)m.B * 2 * m.RP * 2);
     n.Y = disc ? (float*)take((long long)NR * T * 4) : nullptr;
+    n.GSCR = (float*)take(gates_scratch_floats(NR) * 4);
   };
   net(w.g, m.GS * m.B, m.KXG, false);
   net(w.d, 4 * m.B, m.KXD, true);
@@ -368,6 +373,7 @@ static int net_gates(const Net& n, int t, int row0, int nrows, bool prezeroed = 
 static int net_forward_step(const Net& n, int t, int nblk, bool ea0_prezeroed = false) {
   const Dm& m = n.m;
   const int rows = nblk * m.B;
+  const bool fused = gates_fused_available() && n.w.GSCR != nullptr;
   SGG_TRY(net_scores(n, t, 0, rows, false, /*prezeroed=*/t > 0 || ea0_prezeroed));
   AttnFwdParams ap{};
   ap.a = n.a; ap.B = m.B; ap.R = m.R; ap.nv = nblk; ap.early_a = t_ann_static;
@@ -375,8 +381,25 @@ static int net_forward_step(const Net& n, int t, int nblk, bool ea0_prezeroed = 
   ap.E = n.w.EA + n.t1(t) * n.sEA(); ap.ldE = m.RP;
   ap.alpha_out = n.w.EA + n.t1(t) * n.sEA(); ap.ldA = m.RP;
   ap.X = n.w.X + n.t2(t) * n.sX(); ap.ldX = 2 * n.KXP; ap.lo_off = n.KXP;
-  ap.zero_p = n.w.Q + n.t1(t) * n.sQ(); ap.zero_ld = 4 * m.H; ap.zero_cols = 4 * m.H;
+  if (!fused) { ap.zero_p = n.w.Q + n.t1(t) * n.sQ(); ap.zero_ld = 4 * m.H; ap.zero_cols = 4 * m.H; }
   SGG_TRY(attn_fwd(ap, 0, n.st));
+  if (fused) {   // gate GEMM with the LayerNorm / cell epilogue fused in (gates.cu): one launch, no read-back of q
+    GatesParams gp{};
+    gp.nrows = rows;
+    gp.Cin = n.w.Cf + n.t2(t) * n.sCf();
+    gp.ln = n.ln();
+    gp.Q = n.w.Q + n.t1(t) * n.sQ(); gp.ldQ = 4 * m.H;
+    gp.Cout = n.w.Cf + n.t2(t + 1) * n.sCf();
+    gp.CH = n.w.CH + n.t2(t + 1) * n.sCH(); gp.ldCH = 2 * m.H; gp.ch_lo = m.H;
+    gp.Xn = n.w.X + n.t2(t + 1) * n.sX(); gp.ldX = 2 * n.KXP; gp.x_lo = n.KXP; gp.hoff = n.hoff;
+    if (!n.gen) {
+      gp.wdec = n.theta + n.L.Wdec; gp.bdec = n.theta + n.L.bdec;
+      gp.Y = n.w.Y + t; gp.ldY = m.T;
+    }
+    if (t + 1 < m.T) gp.zero = ZeroRow{n.w.EA + n.t1(t + 1) * n.sEA(), m.RP, m.RP};
+    gp.scratch = n.w.GSCR;
+    return gates_fused(n.w.X + n.t2(t) * n.sX(), 2 * n.KXP, n.KXP, n.sh + n.L.sKp, n.L.rK, gp, n.st);
+  }
   SGG_TRY(net_gates(n, t, 0, rows, true));
   LstmFwdParams lp{};
   if (t + 1 < m.T) lp.zero = ZeroRow{n.w.EA + n.t1(t + 1) * n.sEA(), m.RP, m.RP};
@@ -1279,6 +1302,7 @@ static SampleWs sample_ws_layout(const sgg_dims_t& d, int chunk, void* base) {
     w.g[i].CH = (__nv_bfloat16*)take(2LL * Bc * 2 * m.H * 2);
     w.g[i].EA = (float*)take((long long)Bc * m.RP * 4);
     w.g[i].Q = (float*)take((long long)Bc * 4 * m.H * 4);
+    w.g[i].GSCR = (float*)take(gates_scratch_floats(Bc) * 4);
   }
   w.bytes = o;
   return w;
