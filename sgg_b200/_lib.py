@@ -56,6 +56,10 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def set_option(name: str, value: int) -> None:
+    check(lib().sgg_set_option(name.encode(), C.c_int32(int(value))), "sgg_set_option")
+
+
 def kernel_counts(reset: bool = False) -> dict:
     """{kernel name: launches} of every kernel this library has launched or captured so far (sgg_kernel_counts)."""
     L = lib()
@@ -133,7 +137,7 @@ SAMPLE_GREEDY, SAMPLE_GUMBEL = 0, 1
 
 # every symbol include/sgg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "sgg_last_error", "sgg_version", "sgg_launch_count", "sgg_kernel_counts", "sgg_timing_report", "sgg_gemm", "sgg_attn_forward", "sgg_attn_reverse", "sgg_param_table", "sgg_refresh_shadow", "sgg_adam_step", "sgg_adam_project",
+    "sgg_last_error", "sgg_version", "sgg_launch_count", "sgg_set_option", "sgg_kernel_counts", "sgg_timing_report", "sgg_gemm", "sgg_attn_forward", "sgg_attn_reverse", "sgg_param_table", "sgg_refresh_shadow", "sgg_adam_step", "sgg_adam_project",
     "sgg_rng_fill_normal", "sgg_rng_fill_uniform", "sgg_workspace_bytes", "sgg_gen_forward",
     "sgg_disc_forward", "sgg_disc_step", "sgg_gen_step", "sgg_ws_lookup", "sgg_train_iteration",
     "sgg_comm_unique_id", "sgg_comm_init", "sgg_comm_destroy", "sgg_comm_allreduce_sum",

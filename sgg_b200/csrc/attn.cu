@@ -707,9 +707,436 @@ __global__ void __launch_bounds__(A2_THREADS) attn_rev_mma_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, R2_TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------ persistent variants
+// One CTA per SM (grid = min(B, SM count)), each walking the samples b = blockIdx.x, blockIdx.x + grid, ...  The TMA ring
+// runs ACROSS samples: while the workers compute the softmax of the next sample, read the previous accumulator out of
+// TMEM and store z, the producer keeps up to AP_STAGES x 16 KB of annotation tiles in flight, so the HBM stream never
+// drains at a sample boundary (the one-CTA-per-sample kernels above pay barrier init, TMEM allocation, the softmax
+// before the first MMA and the epilogue once per 200 KB tile: 0.68 / 0.59 of HBM).  Weights and accumulators are
+// double-buffered: the softmax of sample i+1 overlaps the contraction of sample i.
+constexpr int AP_STAGES = 10;
+
+template <int MODE>
+__device__ __forceinline__ void attn_stream_weights(const AttnFwdParams& p, int b, int n, int lane, uint8_t* whi, uint8_t* wlo) {
+  const int R = p.R;
+  float v[AT_RMAX / 32];
+  const long long row = (long long)p.row_blk[n] * p.B + b;
+  const float* e = p.E + ((long long)p.e_blk[n] * p.B + b) * p.ldE;
+  if (MODE == 0) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) {
+      const int r = lane + 32 * i;
+      v[i] = (r < R) ? e[r] : -INFINITY;
+      mx = fmaxf(mx, v[i]);
+    }
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) {
+      v[i] = (lane + 32 * i < R) ? __expf(v[i] - mx) : 0.f;
+      s += v[i];
+    }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) v[i] *= inv;
+  } else {
+    const float* al = p.alpha_in + ((long long)p.ain_blk * p.B + b) * p.ldA;
+    float m = 0.f;
+    float ed[AT_RMAX / 32];
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) {
+      const int r = lane + 32 * i;
+      v[i] = (r < R) ? al[r] : 0.f;
+      ed[i] = (r < R) ? e[r] : 0.f;
+      m += v[i] * ed[i];
+    }
+    m = warp_sum(m);
+#pragma unroll
+    for (int i = 0; i < AT_RMAX / 32; ++i) v[i] = v[i] * (ed[i] - m);
+  }
+  float* ao = p.alpha_out + row * p.ldA;
+#pragma unroll
+  for (int i = 0; i < AT_RMAX / 32; ++i)
+    if (lane + 32 * i < R) ao[lane + 32 * i] = v[i];
+#pragma unroll
+  for (int i = 0; i < AT_RMAX / 32; ++i) {
+    __nv_bfloat16 h, l;
+    split_bf16(v[i], h, l);
+    const uint32_t off = a2_w_off(n, lane + 32 * i);
+    *reinterpret_cast<__nv_bfloat16*>(whi + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(wlo + off) = l;
+  }
+}
+
+struct AttnPSmem {
+  uint8_t stage[AP_STAGES][A2_STAGE_BYTES];
+  uint8_t whi[2][A2_W_BYTES];
+  uint8_t wlo[2][A2_W_BYTES];
+  uint64_t full[AP_STAGES];
+  uint64_t empty[AP_STAGES];
+  uint64_t wready[2], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_ptr;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(A2_THREADS, 1) attn_fwd_p_kernel(const __grid_constant__ CUtensorMap tmA, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnPSmem& sm = *reinterpret_cast<AttnPSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.R;
+  const int nch = (R + A2_ROWS - 1) / A2_ROWS;
+  const int G = gridDim.x;
+  const int n_items = ((int)blockIdx.x < p.B) ? (p.B - (int)blockIdx.x + G - 1) / G : 0;
+  pdl_trigger();
+  if (warp == 0 && elect_one()) tma_prefetch_desc(&tmA);
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < AP_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&sm.wready[s], 128); mbar_init(&sm.tmem_full[s], 1); mbar_init(&sm.tmem_empty[s], 128); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm.tmem_ptr, 2 * A2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer: the ring runs across samples =====================
+    if (elect_one()) {
+      if (!p.early_a) pdl_wait();   // annotations that a preceding kernel may have written
+      const uint64_t pol = l2_policy_evict_last();
+      int cg = 0;
+      for (int it = 0; it < n_items; ++it) {
+        const int b = (int)blockIdx.x + it * G;
+        for (int c = 0; c < nch; ++c, ++cg) {
+          const int st = cg % AP_STAGES;
+          mbar_wait(&sm.empty[st], ((cg / AP_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&sm.full[st], A2_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < AT_C / 64; ++j)
+            if (p.l2_keep) tma_load_3d_hint(sm.stage[st] + j * (A2_ROWS * 128), &tmA, &sm.full[st], 64 * j, c * A2_ROWS, b, pol);
+            else tma_load_3d(sm.stage[st] + j * (A2_ROWS * 128), &tmA, &sm.full[st], 64 * j, c * A2_ROWS, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(128, A2_NPAD, true, false);
+    int cg = 0;
+    for (int it = 0; it < n_items; ++it) {
+      const int slot = it & 1;
+      mbar_wait(&sm.wready[slot], (it >> 1) & 1);              // weights of this sample are in shared memory
+      mbar_wait(&sm.tmem_empty[slot], ((it >> 1) & 1) ^ 1);    // accumulator slot read out (sample it - 2)
+      tc_fence_after();
+      const uint32_t whi = smem_u32(sm.whi[slot]), wlo = smem_u32(sm.wlo[slot]);
+      const uint32_t acc = tmem_base + slot * A2_TMEM_COLS;
+      for (int c = 0; c < nch; ++c, ++cg) {
+        const int st = cg % AP_STAGES;
+        mbar_wait(&sm.full[st], (cg / AP_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sA = smem_u32(sm.stage[st]);
+          const uint32_t boff = (uint32_t)((c >> 2) * 2048 + (c & 3) * 32);   // k-step c = regions [16c, 16c+16)
+          const uint64_t dbh = make_smem_desc(whi + boff, 0, 1024);
+          const uint64_t dbl = make_smem_desc(wlo + boff, 0, 1024);
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            const uint64_t da = make_smem_desc(sA + mt * (2 * A2_ROWS * 128), A2_ROWS * 128, 1024);
+            umma_bf16(acc + mt * A2_NPAD, da, dbh, idesc, c ? 1u : 0u);
+            umma_bf16(acc + mt * A2_NPAD, da, dbl, idesc, 1u);
+          }
+          umma_commit(&sm.empty[st]);
+          if (c == nch - 1) umma_commit(&sm.tmem_full[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== workers: weights of sample it + 1, then read-out of sample it =====================
+    pdl_wait();
+    const int wi = warp - 2;
+    const int q = warp & 3;
+    auto weights = [&](int it) {
+      const int b = (int)blockIdx.x + it * G, slot = it & 1;
+#pragma unroll 1
+      for (int n = wi; n < p.nv; n += 4) attn_stream_weights<MODE>(p, b, n, lane, sm.whi[slot], sm.wlo[slot]);
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.wready[slot]);
+    };
+    if (n_items > 0) weights(0);
+    for (int it = 0; it < n_items; ++it) {
+      const int b = (int)blockIdx.x + it * G, slot = it & 1;
+      if (it + 1 < n_items) weights(it + 1);   // its weight slot was last read by the MMAs of sample it - 1 (tmem_full seen)
+      if (p.zero_p) {   // clear the gate pre-activation rows of this sample's streams
+        const int wt = threadIdx.x - 64;
+        for (int v = 0; v < p.nv; ++v) {
+          float4* d = reinterpret_cast<float4*>(p.zero_p + ((long long)p.row_blk[v] * p.B + b) * p.zero_ld);
+          for (int i = wt; i < (p.zero_cols >> 2); i += 128) d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      mbar_wait(&sm.tmem_full[slot], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * A2_TMEM_COLS + mt * A2_NPAD), r);
+        tmem_ld_wait();
+        const int ch = mt * 128 + q * 32 + lane;
+#pragma unroll
+        for (int v = 0; v < AT_MAXV; ++v) {
+          if (v < p.nv) {
+            const long long row = (long long)p.row_blk[v] * p.B + b;
+            __nv_bfloat16 h, l;
+            split_bf16(__uint_as_float(r[v]), h, l);
+            p.X[row * p.ldX + ch] = h;
+            p.X[row * p.ldX + p.lo_off + ch] = l;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.tmem_empty[slot]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * A2_TMEM_COLS);
+}
+
+constexpr int RP_STAGES = 8;
+struct AttnRevPSmem {
+  uint8_t stage[RP_STAGES][R2_STAGE_BYTES];
+  uint8_t zhi[2][R2_ZB_BYTES];
+  uint8_t zlo[2][R2_ZB_BYTES];
+  __align__(16) float w[AT_RMAX][AT_MAXV_REV];       // alpha_bar per region and stream
+  __align__(16) float eb[AT_MAXV_REV][AT_RMAX];      // e_bar per stream
+  uint64_t full[RP_STAGES];
+  uint64_t empty[RP_STAGES];
+  uint64_t zready[2], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_ptr;
+};
+
+__global__ void __launch_bounds__(A2_THREADS, 1) attn_rev_p_kernel(const __grid_constant__ CUtensorMap tmA, const AttnRevParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnRevPSmem& sm = *reinterpret_cast<AttnRevPSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.R;
+  const int nmt = (R + 127) / 128;            // region tiles
+  const int nch = nmt * (AT_C / 64);          // ring chunks per sample: (region tile, k-block of 64 channels)
+  const int G = gridDim.x;
+  const int n_items = ((int)blockIdx.x < p.B) ? (p.B - (int)blockIdx.x + G - 1) / G : 0;
+  pdl_trigger();
+  if (warp == 0 && elect_one()) tma_prefetch_desc(&tmA);
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < RP_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&sm.zready[s], 128); mbar_init(&sm.tmem_full[s], 1); mbar_init(&sm.tmem_empty[s], 128); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(&sm.tmem_ptr, 2 * R2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      if (!p.early_a) pdl_wait();
+      const uint64_t pol = l2_policy_evict_last();
+      int cg = 0;
+      for (int it = 0; it < n_items; ++it) {
+        const int b = (int)blockIdx.x + it * G;
+        for (int c = 0; c < nch; ++c, ++cg) {
+          const int st = cg % RP_STAGES;
+          mbar_wait(&sm.empty[st], ((cg / RP_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&sm.full[st], R2_STAGE_BYTES);
+          if (p.l2_keep) tma_load_3d_hint(sm.stage[st], &tmA, &sm.full[st], 64 * (c & 7), 128 * (c >> 3), b, pol);
+          else tma_load_3d(sm.stage[st], &tmA, &sm.full[st], 64 * (c & 7), 128 * (c >> 3), b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, A2_NPAD, false, false);
+    int cg = 0;
+    for (int it = 0; it < n_items; ++it) {
+      const int slot = it & 1;
+      mbar_wait(&sm.zready[slot], (it >> 1) & 1);
+      mbar_wait(&sm.tmem_empty[slot], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t zhi = smem_u32(sm.zhi[slot]), zlo = smem_u32(sm.zlo[slot]);
+      const uint32_t acc = tmem_base + slot * R2_TMEM_COLS;
+      for (int c = 0; c < nch; ++c, ++cg) {
+        const int st = cg % RP_STAGES;
+        mbar_wait(&sm.full[st], (cg / RP_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sA = smem_u32(sm.stage[st]);
+          const int kb = c & 7, mt = c >> 3;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(sA + k * 32, 0, 1024);
+            const uint64_t dbh = make_smem_desc(zhi + kb * 2048 + k * 32, 0, 1024);
+            const uint64_t dbl = make_smem_desc(zlo + kb * 2048 + k * 32, 0, 1024);
+            umma_bf16(acc + mt * A2_NPAD, da, dbh, idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(acc + mt * A2_NPAD, da, dbl, idesc, 1u);
+          }
+          umma_commit(&sm.empty[st]);
+          if (c == nch - 1) umma_commit(&sm.tmem_full[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    pdl_wait();
+    const int wi = warp - 2;
+    const int wtid = threadIdx.x - 64;         // 0..127 among the worker warps
+    const int q = warp & 3;
+    const int ns = (p.tan_stream >= 0) ? p.nv - 1 : p.nv;
+    const bool tan = (wi == p.tan_stream);
+    // z_bar of sample `it` -> B operand (stream n, channel k), K-major 128B-swizzled, hi/lo.  Thread owns 4 channels of
+    // every stream; rows of unused streams stay unwritten (their D columns are never read).
+    auto zprep = [&](int it) {
+      const int b = (int)blockIdx.x + it * G, slot = it & 1;
+      float4 zv[AT_MAXV_REV];
+#pragma unroll
+      for (int n = 0; n < AT_MAXV_REV; ++n)
+        zv[n] = (n < p.nv) ? *reinterpret_cast<const float4*>(p.XB + ((long long)p.row_blk[n] * p.B + b) * p.ldXB + wtid * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < AT_MAXV_REV; ++n) {
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(zv[n].x, h[0], l[0]); split_bf16(zv[n].y, h[1], l[1]);
+        split_bf16(zv[n].z, h[2], l[2]); split_bf16(zv[n].w, h[3], l[3]);
+        const uint32_t off = a2_w_off(n, wtid * 4);
+        *reinterpret_cast<uint2*>(sm.zhi[slot] + off) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        *reinterpret_cast<uint2*>(sm.zlo[slot] + off) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.zready[slot]);
+    };
+    if (n_items > 0) zprep(0);
+    for (int it = 0; it < n_items; ++it) {
+      const int b = (int)blockIdx.x + it * G, slot = it & 1;
+      if (it + 1 < n_items) zprep(it + 1);
+      // ---- loads of the softmax reverse that do not depend on the contraction go out before waiting for it
+      float alv[AT_RMAX / 32], ed[AT_RMAX / 32];
+      if (wi < ns) {
+        const float* al = p.alpha + ((long long)p.row_blk[wi] * p.B + b) * p.ldA;
+#pragma unroll
+        for (int i = 0; i < AT_RMAX / 32; ++i) {
+          const int r = lane + 32 * i;
+          alv[i] = (r < R) ? al[r] : 0.f;
+          ed[i] = (r < R && tan) ? p.edot[(long long)b * p.ldA + r] : 0.f;
+        }
+      }
+      // ---- alpha_bar from TMEM: lane = region within the tile, column = stream
+      mbar_wait(&sm.tmem_full[slot], (it >> 1) & 1);
+      tc_fence_after();
+      for (int mt = 0; mt < nmt; ++mt) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * R2_TMEM_COLS + mt * A2_NPAD), r);
+        tmem_ld_wait();
+        const int row = mt * 128 + q * 32 + lane;
+        if (row < R)
+          *reinterpret_cast<float4*>(sm.w[row]) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]),
+                                                              __uint_as_float(r[2]), __uint_as_float(r[3]));
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.tmem_empty[slot]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- softmax reverse: one warp per primal stream
+      if (wi < ns) {
+        const int v = wi;
+        const long long row = (long long)p.row_blk[v] * p.B + b;
+        float ab[AT_RMAX / 32], adb[AT_RMAX / 32];
+        float m_t = 0.f, m_e = 0.f;
+#pragma unroll
+        for (int i = 0; i < AT_RMAX / 32; ++i) {
+          const int r = lane + 32 * i;
+          const bool ok = r < R;
+          ab[i] = ok ? sm.w[r][v] : 0.f;
+          adb[i] = (ok && tan) ? sm.w[r][p.nv - 1] : 0.f;
+          m_t += alv[i] * adb[i];
+          m_e += alv[i] * ed[i];
+        }
+        float s = 0.f;
+        if (tan) {
+          m_t = warp_sum(m_t);
+          m_e = warp_sum(m_e);
+        }
+#pragma unroll
+        for (int i = 0; i < AT_RMAX / 32; ++i) {
+          if (tan) ab[i] = ab[i] + adb[i] * (ed[i] - m_e) - ed[i] * m_t;  // w = abar + second-order terms
+          s += alv[i] * ab[i];
+        }
+        s = warp_sum(s);
+        __nv_bfloat16* ebh = p.EB + row * p.ldEB;
+        __nv_bfloat16* tbh = tan ? p.EB + ((long long)p.row_blk[p.nv - 1] * p.B + b) * p.ldEB : nullptr;
+#pragma unroll
+        for (int i = 0; i < AT_RMAX / 32; ++i) {
+          const int r = lane + 32 * i;
+          if (r < R) {
+            const float ebar = alv[i] * (ab[i] - s);
+            sm.eb[v][r] = ebar;
+            __nv_bfloat16 h, l;
+            split_bf16(ebar, h, l);
+            ebh[r] = h;
+            ebh[p.lo_off + r] = l;
+            if (tan) {
+              const float edb = alv[i] * (adb[i] - m_t);
+              split_bf16(edb, h, l);
+              tbh[r] = h;
+              tbh[p.lo_off + r] = l;
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // eb complete; also: nobody still reads w when the next sample overwrites it
+      if (p.Pbar) {
+        for (int r = wtid; r < R; r += 128) {
+          float s = 0.f;
+          for (int v = 0; v < ns; ++v) s += sm.eb[v][r];
+          atomicAdd(p.Pbar + (long long)b * p.ldP + r, s);   // fire-and-forget reduction (one writer per address and launch)
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // eb is rewritten by the next sample
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * R2_TMEM_COLS);
+}
+
 static size_t attn_smem_bytes() { return sizeof(AttnSmem) + 128; }
 
 static size_t attn2_smem_bytes() { return sizeof(Attn2Smem) + 1024; }
+static int attn_sm_count() {
+  static int n = -1;
+  if (n < 0) {
+    int dev = 0;
+    cudaDeviceProp pr;
+    n = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&pr, dev) == cudaSuccess) ? pr.multiProcessorCount : 148;
+  }
+  return n;
+}
+// Which family serves a batch of B samples (tools/attn_micro.py, B200): up to two tiles per SM the one-CTA-per-sample
+// kernels win (all tiles stream concurrently at two CTAs per SM: 12.1 us vs 15.9 us at B = 256); from three tiles per SM
+// on the persistent kernels win (B = 444: 18.3 vs 22.0 us; B = 2368: 79.8 vs 87.2 us = 0.92 of measured HBM).
+// SGG_ATTN_PERSIST=0 / 1 forces a family.
+static bool attn_persistent(int B) {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("SGG_ATTN_PERSIST"); v = e ? (e[0] == '0' ? 0 : 1) : -1; }
+  if (v >= 0) return v == 1;
+  return B > 2 * attn_sm_count();
+}
 static bool attn_use_simt() {   // SGG_ATTN_SIMT=1 selects the CUDA-core forward kernel (A/B measurements)
   static int v = -1;
   if (v < 0) { const char* e = getenv("SGG_ATTN_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -728,11 +1155,19 @@ int attn_fwd(const AttnFwdParams& p_in, int mode, cudaStream_t stream) {
     SGG_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
     SGG_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2_smem_bytes()));
     SGG_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2_smem_bytes()));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(AttnPSmem) + 1024)));
+    SGG_CUDA(cudaFuncSetAttribute(attn_fwd_p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(AttnPSmem) + 1024)));
     configured = true;
   }
   if (!attn_use_simt()) {
     CUtensorMap tm;
     SGG_TRY(make_tmap_bf16_3d(&tm, p.a, (uint64_t)p.B, (uint64_t)p.R, AT_C, 64, A2_ROWS));
+    if (attn_persistent(p.B)) {
+      const int grid = p.B < attn_sm_count() ? p.B : attn_sm_count();
+      if (mode == 0) SGG_LAUNCH(attn_fwd_p_kernel<0>, grid, A2_THREADS, sizeof(AttnPSmem) + 1024, stream, tm, p);
+      else SGG_LAUNCH(attn_fwd_p_kernel<1>, grid, A2_THREADS, sizeof(AttnPSmem) + 1024, stream, tm, p);
+      return 0;
+    }
     if (mode == 0)
       SGG_LAUNCH(attn_fwd_mma_kernel<0>, p.B, A2_THREADS, attn2_smem_bytes(), stream, tm, p);
     else
@@ -762,11 +1197,17 @@ int attn_rev(const AttnRevParams& p_in, cudaStream_t stream) {
     SGG_CUDA(cudaFuncSetAttribute(attn_rev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes()));
     SGG_CUDA(cudaFuncSetAttribute(attn_rev_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(AttnRev2Smem) + 1024)));
+    SGG_CUDA(cudaFuncSetAttribute(attn_rev_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(AttnRevPSmem) + 1024)));
     configured = true;
   }
   if (!attn_use_simt()) {
     CUtensorMap tm;
     SGG_TRY(make_tmap_bf16_3d(&tm, p.a, (uint64_t)p.B, (uint64_t)p.R, AT_C, 64, 128));
+    if (attn_persistent(p.B)) {
+      const int grid = p.B < attn_sm_count() ? p.B : attn_sm_count();
+      SGG_LAUNCH(attn_rev_p_kernel, grid, A2_THREADS, sizeof(AttnRevPSmem) + 1024, stream, tm, p);
+      return 0;
+    }
     SGG_LAUNCH(attn_rev_mma_kernel, p.B, A2_THREADS, sizeof(AttnRev2Smem) + 1024, stream, tm, p);
     return 0;
   }

@@ -214,6 +214,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Multicast variant: the box lands at the same shared-memory offset in every CTA of the cluster whose bit is set in
+// `mask`, and each destination CTA's mbarrier (same offset as `bar`) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 // L2 eviction-priority policies (createpolicy) for TMA loads: the annotation tiles are re-read by every attention
 // launch of a step (evict_last keeps them resident), weight / optimiser streams are read once (evict_first).
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -280,6 +289,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// ... the arrive goes to the mbarrier at the same offset in every CTA of the cluster whose bit is set in `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
                : "memory");
 }
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (lane i of the warp gets row base+i).

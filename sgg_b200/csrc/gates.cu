@@ -55,12 +55,15 @@ struct GatesParams {
   const float* wdec; const float* bdec; float* Y; long long ldY;   // optional D head: Y[row * ldY] += partial dots (zero-filled)
   ZeroRow zero;               // optional: next step's scores rows
   float* scratch;             // [m-tiles][cluster][GF_NSTAT][128] fp32 exchange buffer
-  int debug;
 };
 
 template <int NPC>
 __global__ void __launch_bounds__(GF_THREADS, 1)
 gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GatesParams p) {
+  // tmA: box {64 k, 128 / CS rows}: every CTA of the cluster fetches 1/CS of the m-tile's A rows per k-block and
+  // MULTICASTS it to all CS CTAs (they share the A tile; only the weight columns differ).  Without it the 16 CTAs of a
+  // cluster -- one GPC -- pull the same 32 KB sixteen times through that GPC's L2 port, and the port, not the tensor
+  // pipe, paces the main loop (measured 0.69 us per k-block against 0.40 us of MMA time, independent of the cluster count).
   constexpr int CS = 512 / NPC;              // cluster size
   constexpr int N = 4 * NPC;                 // accumulator columns
   constexpr int UPT = NPC / 2;               // units per epilogue thread
@@ -88,7 +91,8 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1) {
     if (elect_one()) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      // a ring slot is free once ALL CTAs of the cluster have consumed it: peers multicast into it
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CS); }
       mbar_init(tmem_full_bar, 1);
       mbar_fence_init();
     }
@@ -100,11 +104,9 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  cluster_arrive_release();     // every CTA's barriers exist before a peer signals them
+  cluster_wait_acquire();
   pdl_wait();
-  unsigned long long tq[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const bool dbg = p.debug && threadIdx.x == 64 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == 5);
-#define SGG_TS(i) if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[i]))
-  SGG_TS(0);
 
   // per-row statistics produced by the epilogue (registers of the epilogue threads)
   if (warp == 0) {
@@ -116,8 +118,10 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint8_t* st = smem + stage * STAGE;
         mbar_expect_tx(&full_bar[stage], STAGE);
         const int kc = i * 64;
-        tma_load_2d(st, &tmA, &full_bar[stage], kc, m0);
-        tma_load_2d(st + A_PART, &tmA, &full_bar[stage], p.a_lo + kc, m0);
+        constexpr int RPS = 128 / CS;                       // A rows this CTA contributes (one or two swizzle atoms)
+        constexpr uint16_t ALL = (uint16_t)((1u << CS) - 1u);
+        tma_load_2d_mc(st + j * RPS * 128, &tmA, &full_bar[stage], kc, m0 + j * RPS, ALL);
+        tma_load_2d_mc(st + A_PART + j * RPS * 128, &tmA, &full_bar[stage], p.a_lo + kc, m0 + j * RPS, ALL);
 #pragma unroll
         for (int pb = 0; pb < 2; ++pb)
 #pragma unroll
@@ -134,17 +138,18 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sA0 = smem_u32(smem + stage * STAGE), sA1 = sA0 + A_PART;
-        const uint32_t sB0 = sA0 + 2 * A_PART, sB1 = sB0 + B_PART;
+        // descriptors differ between k-steps only in the start-address field (bits 0-13, units of 16 bytes): build one
+        // per operand part and k-block, then add the step offset (A, K-major: 32 B per step; B, MN-major: 16 k-rows = 2 KB)
+        const uint32_t sA0 = smem_u32(smem + stage * STAGE);
+        const uint64_t da0 = make_smem_desc(sA0, 0, 1024), da1 = make_smem_desc(sA0 + A_PART, 0, 1024);
+        const uint64_t db0 = make_smem_desc(sA0 + 2 * A_PART, 64 * 128, 1024), db1 = make_smem_desc(sA0 + 2 * A_PART + B_PART, 64 * 128, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t da0 = make_smem_desc(sA0 + k * 32, 0, 1024), da1 = make_smem_desc(sA1 + k * 32, 0, 1024);
-          const uint64_t db0 = make_smem_desc(sB0 + k * 2048, 64 * 128, 1024), db1 = make_smem_desc(sB1 + k * 2048, 64 * 128, 1024);
-          umma_bf16(tmem_base, da0, db0, idesc, (i | k) ? 1u : 0u);
-          umma_bf16(tmem_base, da1, db0, idesc, 1u);
-          umma_bf16(tmem_base, da0, db1, idesc, 1u);
+          umma_bf16(tmem_base, da0 + 2 * k, db0 + 128 * k, idesc, (i | k) ? 1u : 0u);
+          umma_bf16(tmem_base, da1 + 2 * k, db0 + 128 * k, idesc, 1u);
+          umma_bf16(tmem_base, da0 + 2 * k, db1 + 128 * k, idesc, 1u);
         }
-        umma_commit(&empty_bar[stage]);
+        umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));   // frees the slot in every CTA of the cluster
         if (i == p.kb - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
@@ -220,7 +225,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    SGG_TS(1);
     // ---- pass 1: (mean, M2) per gate and 16-unit chunk; pre-activations into the staging tile
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
@@ -267,7 +271,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   }
-  SGG_TS(2);
   cluster_arrive_release();
   float cin_pref[4] = {0.f, 0.f, 0.f, 0.f};
   if (epi) {
@@ -278,7 +281,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   }
   cluster_wait_acquire();
-  SGG_TS(3);
   if (epi) {
     // ---- pass 2: pull the CS x 8 gate partials of the m-tile (coalesced float4, one round trip), then per-row statistics
     {
@@ -290,9 +292,7 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         dst[i] = __ldcg(src + sblk * (GF_NSTAT * 32) + rem);
       }
     }
-    SGG_TS(6);
     asm volatile("bar.sync 1, 256;" ::: "memory");                    // also: every warp has finished its Q-store rows
-    SGG_TS(7);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float pm[CS], mu = 0.f, m2 = 0.f;
@@ -309,7 +309,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       gmean[g] = mu;
       grstd[g] = fast_rsqrt((m2 + dd * NPC) * (1.0f / 512.0f) + 1e-12f);
     }
-    SGG_TS(8);
     // ---- pass 3: gate activations and the cell update, chunk by chunk; c' and sigmoid(o) go to the staging tiles
 #pragma unroll 1
     for (int c = 0; c < NCH; ++c) {
@@ -325,8 +324,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int k = 0; k < 16; ++k) cin[k] = 0.f;
       }
-      if (dbg) { float acc = 0.f; for (int k = 0; k < 16; ++k) acc += cin[k]; if (acc == 12345.678f) printf("x"); }
-      SGG_TS(10);
       float cp[16], so[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) cp[k] = 0.f;
@@ -352,8 +349,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           so[k] = y;
         }
       }
-      if (dbg) { float acc = 0.f; for (int k = 0; k < 16; ++k) acc += cp[k] + so[k]; if (acc == 12345.678f) printf("x"); }
-      SGG_TS(11);
       float sum = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) sum += cp[k];
@@ -368,7 +363,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         *reinterpret_cast<float4*>(sH + rt * CSP + lu + k) = make_float4(so[k], so[k + 1], so[k + 2], so[k + 3]);
       }
     }
-    SGG_TS(9);
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (half == 0) {   // row partial of the state LayerNorm
       float pm[NSLOT], mu = 0.f, m2 = 0.f;
@@ -385,11 +379,9 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       dst[9 * 128] = m2;
     }
   }
-  SGG_TS(4);
   cluster_arrive_release();
   if (epi && kLateQ) store_q();
   cluster_wait_acquire();
-  SGG_TS(5);
   if (epi) {
     float rc, cmean;
     {
@@ -470,12 +462,6 @@ gates_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       p.Y[row * p.ldY] = y;
     }
   }
-  if (dbg) {
-    unsigned long long t6;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t6));
-    printf("gates<%d> cta %d rows %d kb %d: mainloop %llu  pass1 %llu  bar1 %llu  pass23 %llu [pull %llu bar %llu stats %llu cell %llu (cin %llu gates %llu) rest %llu]  bar2 %llu  tail %llu ns\n", NPC, (int)blockIdx.x,
-           p.nrows, p.kb, tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[6] - tq[3], tq[7] - tq[6], tq[8] - tq[7], tq[9] - tq[8], tq[10] - tq[8], tq[11] - tq[10], tq[4] - tq[9], tq[5] - tq[4], t6 - tq[5]);
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, N);
@@ -548,12 +534,17 @@ static int gates_max_clusters(int npc) {
 constexpr int GATES_SCRATCH_FLOATS_PER_MTILE = 16 * GF_NSTAT * 128;
 long long gates_scratch_floats(long long max_rows) { return (max_rows + 127) / 128 * GATES_SCRATCH_FLOATS_PER_MTILE; }
 
-// SGG_FUSED_GATES=0 keeps the gate GEMM and the cell as two kernels (A/B measurements); =16 / =8 force a cluster shape.
+// Selection.  Measured on B200 at config 2 (profiles/README.md, round 2): the fused kernel is on par with, not faster
+// than, the split-K gate GEMM + cell kernel pair (5.45 vs 5.32 ms per iteration): full-K accumulation per CTA limits the
+// grid to 96 CTAs whose operand feed (64 KB per k-block and SM) runs at the per-SM L2 -> shared-memory rate, and the
+// LayerNorm exchange adds three cluster barriers in series.  So the pair stays the default and the fused kernel is
+// selected with SGG_FUSED_GATES=1 (=16 / =8 force a cluster shape) or sgg_set_option("fused_gates", v).
+static int g_gates_mode = -2;
 static int gates_mode() {
-  static int v = -2;
-  if (v == -2) { const char* e = getenv("SGG_FUSED_GATES"); v = e ? atoi(e) : -1; }
-  return v;
+  if (g_gates_mode == -2) { const char* e = getenv("SGG_FUSED_GATES"); g_gates_mode = e ? atoi(e) : 0; }
+  return g_gates_mode;
 }
+void gates_set_mode(int v) { g_gates_mode = v; }
 bool gates_fused_available() {
   if (gates_mode() == 0) return false;
   return gates_max_clusters(64) > 0 || gates_max_clusters(32) > 0;
@@ -564,7 +555,6 @@ int gates_fused(const __nv_bfloat16* X, long long ldx, int KXP, const __nv_bfloa
   if (p.nrows <= 0) return 0;
   SGG_CHECK(KXP % 64 == 0, "gates_fused: KXP=%d must be a multiple of 64", KXP);
   p.kb = KXP / 64; p.a_lo = KXP; p.b_lo = rK;
-  { static int d = -1; if (d < 0) { const char* e = getenv("SGG_GATES_DEBUG"); d = (e && e[0] == '1') ? 1 : 0; } p.debug = d; }
   const int mt = (p.nrows + 127) / 128;
   const int c16 = gates_max_clusters(32), c8 = gates_max_clusters(64);
   int npc;
@@ -575,7 +565,7 @@ int gates_fused(const __nv_bfloat16* X, long long ldx, int KXP, const __nv_bfloa
   else npc = 64;
   SGG_CHECK((npc == 32 ? c16 : c8) > 0, "gates_fused: no cluster configuration can be scheduled on this device");
   CUtensorMap tmA, tmB;
-  SGG_TRY(make_tmap_bf16_2d(&tmA, X, (uint64_t)p.nrows, (uint64_t)(2 * KXP), (uint64_t)ldx, 64, 128));
+  SGG_TRY(make_tmap_bf16_2d(&tmA, X, (uint64_t)p.nrows, (uint64_t)(2 * KXP), (uint64_t)ldx, 64, npc == 32 ? 8 : 16));
   SGG_TRY(make_tmap_bf16_2d(&tmB, Kp, (uint64_t)(2 * rK), 2048, 2048, 64, 64));
   return npc == 32 ? launch_gates<32>(tmA, tmB, p, stream) : launch_gates<64>(tmA, tmB, p, stream);
 }

@@ -1383,6 +1383,14 @@ extern "C" int sgg_gen_sample(const sgg_sample_args_t* a, sgg_stream_t stream) {
   return decode_keys(w.keys, a->tokens_out, (long long)m.B * m.T, st);
 }
 
+// Run-time switches (same meaning as the environment variables read at first use; for A/B tests inside one process).
+extern "C" int sgg_set_option(const char* name, int32_t value) {
+  SGG_CHECK(name != nullptr, "sgg_set_option: null name");
+  if (strcmp(name, "fused_gates") == 0) { gates_set_mode(value); return 0; }
+  set_error("sgg_set_option: unknown option '%s'", name);
+  return -1;
+}
+
 // Debug / test accessor: location of an intermediate buffer inside the workspace.
 extern "C" int sgg_ws_lookup(const sgg_dims_t* d, const char* name, int64_t* offset_bytes, int64_t* elem_bytes) {
   SGG_CHECK(d && name && offset_bytes, "sgg_ws_lookup: null argument");

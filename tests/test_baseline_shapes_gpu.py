@@ -235,3 +235,27 @@ def test_projection_cache_follows_the_weights():
     want = orig.gen_forward()
     torch.cuda.synchronize()
     assert ((got - want).norm() / want.norm()).item() < 1e-5
+
+
+@pytest.mark.parametrize("mode", [16, 8])
+def test_fused_gate_epilogue_kernel(mode):
+    """csrc/gates.cu (north_star item 2: gate nonlinearities + LayerNorm fused into the tcgen05 epilogue; gen:79,87):
+    selected at run time, it must run (asserted by kernel name), match the oracle at config 2's shape within 1e-3, and
+    agree with the default gate GEMM + cell kernel pair.  mode = cluster shape (16 CTAs x 32 units / 8 CTAs x 64 units)."""
+    from sgg_b200._lib import kernel_counts, set_option
+    name = "gates_fused_kernel<32>" if mode == 16 else "gates_fused_kernel<64>"
+    try:
+        set_option("fused_gates", mode)
+        k0 = kernel_counts()
+        err, terr, _, k1 = _d_and_g_step(256, 3, 2000, 196, seed=7)
+        assert _ran(k0, k1, name) >= 9, k1            # 3 timesteps x (G forward, D forward, G step's two forwards)
+        for k, (got, ref) in err.items():
+            assert _scalar_close(got, ref), (k, got, ref)
+        for k, e in terr.items():
+            assert e < TOL, (k, e)
+        # ragged m-tile (rows not a multiple of 128) and T = 5
+        err, terr, _, _ = _d_and_g_step(5, 5, 130, 196, seed=8)
+        for k, e in terr.items():
+            assert e < TOL, (k, e)
+    finally:
+        set_option("fused_gates", 0)
