@@ -59,14 +59,15 @@ int comm_world(void* comm);
 // the HBM-bound chain overlaps the tensor-bound one.  Fork and join are event edges, hence capturable into a graph.
 // SGG_SIDE_STREAM=0 keeps everything on the caller's stream.
 struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
-static SideStream* side_stream() {
-  static thread_local SideStream ss[16] = {};
+// idx 0: the W_a chain of an optimiser step; idx 1: the auxiliary stream of the two-stream reverse pass (disc_step_core)
+static SideStream* side_stream(int idx = 0) {
+  static thread_local SideStream ss[16][2] = {};
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("SGG_SIDE_STREAM"); enabled = (e && e[0] == '0') ? 0 : 1; }
   if (!enabled) return nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  SideStream& x = ss[dev];
+  SideStream& x = ss[dev][idx];
   if (!x.ok) {
     if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -76,8 +77,8 @@ static SideStream* side_stream() {
   return &x;
 }
 // side stream starts after everything enqueued on `st` so far
-static int side_fork(cudaStream_t st, cudaStream_t* out) {
-  SideStream* ss = side_stream();
+static int side_fork(cudaStream_t st, cudaStream_t* out, int idx = 0) {
+  SideStream* ss = side_stream(idx);
   if (!ss) { *out = st; return 0; }
   SGG_CUDA(cudaEventRecord(ss->fork, st));
   SGG_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
@@ -85,9 +86,9 @@ static int side_fork(cudaStream_t st, cudaStream_t* out) {
   return 0;
 }
 // `st` continues after everything enqueued on the side stream so far
-static int side_join(cudaStream_t st, cudaStream_t s1) {
+static int side_join(cudaStream_t st, cudaStream_t s1, int idx = 0) {
   if (s1 == st) return 0;
-  SideStream* ss = side_stream();
+  SideStream* ss = side_stream(idx);
   SGG_CUDA(cudaEventRecord(ss->join, s1));
   SGG_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
   return 0;
@@ -182,6 +183,7 @@ struct Ws {
   __nv_bfloat16* TRIH;   // [T*B, 2*VP] arbitrary float triples hi/lo (sgg_disc_forward)
   float* slopes; float* coef;
   float* LNP;            // [lstm_rev grid][LR_NPART] partial LN / head gradients
+  float* LNP2;           // ... of the auxiliary stream of the two-stream reverse pass
   long long bytes;
 };
 
@@ -238,6 +240,7 @@ static Ws ws_layout(const sgg_dims_t& d, void* base) {
   w.slopes = (float*)take(m.B * 4);
   w.coef = (float*)take(m.B * 4);
   w.LNP = (float*)take(lstm_rev_partials_floats() * 4);
+  w.LNP2 = (float*)take(lstm_rev_partials_floats() * 4);
   w.bytes = o;
   return w;
 }
@@ -464,15 +467,14 @@ struct RevCfg {
   bool clear_P;          // the W_a chain's hi/lo packing kernel also clears P (the fused Adam + projection accumulates into it)
 };
 
-// Reverse pass over T steps.  With wgrad: LN / head gradients inside lstm_rev, P_bar in attn_rev, and
-// the weight-gradient GEMMs afterwards (contraction over all rows and timesteps at once).
-static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = nullptr) {
+// Reverse time loop over T steps for the stream blocks of `rc` (with wgrad: LN / head gradient partials into n.lnp,
+// P_bar accumulated by attn_rev into PB, which the caller has cleared).
+static int net_reverse_loop(const Net& n, const RevCfg& rc) {
   const Dm& m = n.m;
   const bool tan = rc.tan_blk >= 0;
   const int row0 = rc.blk0 * m.B;
   const int nrows_p = rc.nblk * m.B;                       // primal rows
   const int nrows_all = nrows_p + (tan ? m.B : 0);         // tangent block directly follows
-  if (rc.wgrad) SGG_TRY(zero_2d(n.w.PB, (long long)m.B * m.RP, (long long)m.B * m.RP, 1, n.st));
   for (int t = m.T - 1; t >= 0; --t) {
     const bool last = (t == m.T - 1);
     LstmRevParams lp{};
@@ -528,17 +530,30 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
       SGG_TRY(gemm(g, n.st));
     }
   }
-  if (!rc.wgrad) return 0;
-  {  // LN gamma/beta (and D head) gradients: sum the per-CTA partials of the T launches above
+  return 0;
+}
+// CTAs (= partial slices) the lstm_rev launches of a reverse loop over `rc` use
+static int rev_slices(const Net& n, const RevCfg& rc) {
+  const bool tan = rc.tan_blk >= 0;
+  return lstm_rev_grid((tan ? (rc.tan_pblk - rc.blk0) : rc.nblk) * n.m.B + (tan ? n.m.B : 0));
+}
+
+// Parameter gradients after the reverse loop(s) over ALL active rows of the network: LN gamma / beta (and D head) from
+// the per-CTA partials of up to two loops, then one GEMM per kernel over all timesteps / streams.
+static int net_reverse_wgrad(const Net& n, bool clear_P, cudaStream_t* side_out, const float* lnp0, int slices0,
+                             const float* lnp1 = nullptr, int slices1 = 0) {
+  const Dm& m = n.m;
+  for (int k = 0; k < 2; ++k) {
+    const float* part = k == 0 ? lnp0 : lnp1;
+    if (!part) continue;
     LnGradParams lg{};
-    lg.partials = n.lnp; lg.nslices = lstm_rev_grid(nrows_all - (tan ? m.B : 0));
+    lg.partials = part; lg.nslices = k == 0 ? slices0 : slices1;
     for (int i = 0; i < 5; ++i) { lg.dgamma[i] = n.grad + n.L.lng[i]; lg.dbeta[i] = n.grad + n.L.lnb[i]; }
     if (!n.gen) { lg.dwdec = n.grad + n.L.Wdec; lg.dbdec = n.grad + n.L.bdec; }
     SGG_TRY(lngrad_reduce(lg, n.st));
   }
   // ---------------- weight gradients: one GEMM per kernel over all timesteps / streams
-  const long long rowsT = (long long)m.T * n.NR;   // requires blk0 == 0 and nrows_all == NR
-  SGG_CHECK(rc.blk0 == 0 && nrows_all == n.NR, "net_reverse: weight gradients need all active rows");
+  const long long rowsT = (long long)m.T * n.NR;
   SGG_TRY(colsum(n.w.PB, m.RP, m.B, m.R, n.grad + n.L.batt, n.st));   // db_att = column sums of P_bar
   {  // dW_a = flat(a)^T P_bar  [R*C, R]: on the side stream when the caller takes it over (it joins later)
     cudaStream_t s1 = n.st;
@@ -565,7 +580,7 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
     } else {
       pk.rows = m.B; pk.cols = m.R; pk.src = n.w.PB; pk.ld = m.RP;
       pk.dst = n.w.PBH; pk.ldd = 2 * m.RP; pk.lo_off = m.RP;
-      if (rc.clear_P) { pk.zero_p = reinterpret_cast<float4*>(n.w.P); pk.zero_n4 = (long long)m.B * m.RP / 4; }
+      if (clear_P) { pk.zero_p = reinterpret_cast<float4*>(n.w.P); pk.zero_n4 = (long long)m.B * m.RP / 4; }
       SGG_TRY(pack_hl(pk, s1));
       g.A = n.a; g.a_rows = m.B; g.a_cols = K; g.a_ld = K; g.a_mn_major = 1;
       g.B = n.w.PBH; g.b_rows = m.B; g.b_cols = 2 * m.RP; g.b_ld = 2 * m.RP; g.b_mn_major = 1;
@@ -596,6 +611,17 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
     SGG_TRY(gemm(g, n.st));
   }
   return 0;
+}
+
+// Reverse pass over T steps as one sequence: loop, then (with wgrad) the parameter gradients.
+static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = nullptr) {
+  const Dm& m = n.m;
+  if (rc.wgrad) SGG_TRY(zero_2d(n.w.PB, (long long)m.B * m.RP, (long long)m.B * m.RP, 1, n.st));
+  SGG_TRY(net_reverse_loop(n, rc));
+  if (!rc.wgrad) return 0;
+  const bool tan = rc.tan_blk >= 0;
+  SGG_CHECK(rc.blk0 == 0 && rc.nblk * m.B + (tan ? m.B : 0) == n.NR, "net_reverse: weight gradients need all active rows");
+  return net_reverse_wgrad(n, rc.clear_P, side_out, n.lnp, rev_slices(n, rc));
 }
 
 // ============================================================================ generator forward
@@ -911,6 +937,26 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   SGG_TRY(net_forward(d, 3, pre_ea0));
   LossParams lp{B, T, d.w.Y, 0, 1, invBT, scalars};
   SGG_TRY(losses(lp, st));
+  // The reverse pass of the fake and real streams is first order and needs nothing from the gradient-penalty chain
+  // (interp data-path reverse -> slopes -> tangent forward -> reverse over interp + tangent): it runs on the auxiliary
+  // stream beside that chain (both are sequences of small latency-bound kernels); the streams meet before the
+  // weight-gradient GEMMs, which contract over all rows.  Measured (B200, config 2): 5.43 ms per iteration against 5.32 ms
+  // with one reverse loop over all streams -- every kernel of either chain fills the SMs (one CTA per SM GEMMs, two-per-SM
+  // attention), so the chains do not overlap and the split costs 60 launches and a second annotation read per step.
+  // Hence off by default; SGG_TWO_STREAM_REV=1 enables it.
+  static int two_env = -1;
+  if (two_env < 0) { const char* e = getenv("SGG_TWO_STREAM_REV"); two_env = (e && e[0] == '1') ? 1 : 0; }
+  cudaStream_t sB = st;
+  RevCfg rfr{};
+  rfr.blk0 = 0; rfr.nblk = 2; rfr.tan_pblk = -1; rfr.tan_blk = -1; rfr.ybar_blk[0] = invBT; rfr.ybar_blk[1] = -invBT; rfr.wgrad = true;
+  const bool two = two_env != 0 && side_stream(1) != nullptr;
+  if (two) {
+    SGG_TRY(zero_2d(d.w.PB, (long long)m.B * m.RP, (long long)m.B * m.RP, 1, st));   // both loops accumulate P_bar
+    SGG_TRY(side_fork(st, &sB, 1));
+    Net dB = d;
+    dB.st = sB; dB.lnp = w.LNP2;
+    SGG_TRY(net_reverse_loop(dB, rfr));
+  }
   // 4. g = d sum D(x_hat) / d x_hat : data-path reverse on the interp block
   RevCfg ig{};
   ig.blk0 = 2; ig.nblk = 1; ig.tan_pblk = -1; ig.tan_blk = -1; ig.ybar_blk[2] = 1.0f; ig.wgrad = false;
@@ -948,14 +994,22 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     SGG_TRY(embed_mix(et, st));
     SGG_TRY(net_tangent(d, 2, 3, pre_t));
   }
-  // 6. one reverse pass over the three primal streams and the tangent
-  RevCfg rv{};
-  rv.blk0 = 0; rv.nblk = 3; rv.tan_pblk = 2; rv.tan_blk = 3;
-  rv.ybar_blk[0] = invBT; rv.ybar_blk[1] = -invBT; rv.ybar_blk[2] = 0.f; rv.ydot_bar = a->lam;
-  rv.wgrad = true;
-  rv.clear_P = pre && pre->clear_P;
+  // 6. reverse over the primal streams and the tangent
   cudaStream_t s1 = st;
-  SGG_TRY(net_reverse(d, rv, &s1));
+  if (two) {
+    RevCfg rit{};
+    rit.blk0 = 2; rit.nblk = 1; rit.tan_pblk = 2; rit.tan_blk = 3; rit.ybar_blk[2] = 0.f; rit.ydot_bar = a->lam; rit.wgrad = true;
+    SGG_TRY(net_reverse_loop(d, rit));
+    SGG_TRY(side_join(st, sB, 1));
+    SGG_TRY(net_reverse_wgrad(d, pre && pre->clear_P, &s1, w.LNP, rev_slices(d, rit), w.LNP2, rev_slices(d, rfr)));
+  } else {
+    RevCfg rv{};
+    rv.blk0 = 0; rv.nblk = 3; rv.tan_pblk = 2; rv.tan_blk = 3;
+    rv.ybar_blk[0] = invBT; rv.ybar_blk[1] = -invBT; rv.ybar_blk[2] = 0.f; rv.ydot_bar = a->lam;
+    rv.wgrad = true;
+    rv.clear_P = pre && pre->clear_P;
+    SGG_TRY(net_reverse(d, rv, &s1));
+  }
   // 7. embedding gradient: fake^T (ub_f + al ub_i) + scatter(labels, ub_r + (1-al) ub_i) + v^T udot_bar
   {
     PackParams pk{};
