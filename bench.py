@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=32, help="bounded CPU sample: images per CPU iteration (config 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gemm-rooflines", action="store_true", help="skip the per-GEMM-class tensor-pipe micro-timings")
     ap.add_argument("--kernel-profile", action="store_true", help="only run the roofline kernel micro-timing")
     ap.add_argument("--workload", default="train", choices=["train", "sample"],
                     help="train = BASELINE configs[1] (default, the headline metric); sample = configs[4] generator-only "
@@ -102,6 +103,58 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ----------------------------------------------------------------------------------------------- host placement
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pins this process (and therefore the pinned staging buffers it allocates afterwards: first touch) to the CPU cores
+    of the NUMA node the GPU hangs off, so that the 103 MB per iteration of host-to-device traffic of each rank does not
+    cross the socket interconnect.  Returns a dict for the bench line; never fails the run."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["cpus"] = len(allowed)
+    except Exception as e:          # no nvml / sysfs: leave the default placement
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
+def h2d_probe(host_batch, n=8):
+    """Host-to-device rate of one rank's batch copy from pinned memory (GB/s), all ranks copying at the same time."""
+    import torch
+    dst = [torch.empty_like(t, device="cuda") for t in host_batch]
+    nbytes = sum(t.numel() * t.element_size() for t in host_batch)
+    for d, s in zip(dst, host_batch):
+        d.copy_(s, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        for d, s in zip(dst, host_batch):
+            d.copy_(s, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return nbytes * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 # ----------------------------------------------------------------------------------------------- CPU reference arm
 def cpu_reference_iterations(args, n_iters: int, warmup: int):
     """The literal CPU restatement of the reference arithmetic (oracle/sgg_oracle.py: concat-form attention
@@ -140,7 +193,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": config_name(args), "cpu_sample_batch": args.cpu_batch},
+        "config": {"workload": config_name(args, args.cpu_batch) + f" -- a bounded sample (batch {args.cpu_batch} per step) of the GPU arm's "
+                               f"workload ({config_name(args)})", "cpu_sample_batch": args.cpu_batch},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
@@ -148,8 +202,20 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def config_name(args):
-    return (f"BASELINE configs[1]: full G+D WGAN-GP iteration, batch {args.batch}/GPU, 196x512 annotations, "
+def config_index(batch, T, V, nc):
+    """Which BASELINE.json configs[] entry a shape is (None: a custom shape)."""
+    if (T, V, nc) == (3, 2000, 5):
+        return {32: 0, 256: 1}.get(batch)
+    if (batch, T, V) == (256, 30, 5000):
+        return 2
+    return None
+
+
+def config_name(args, batch=None):
+    batch = args.batch if batch is None else batch
+    idx = config_index(batch, args.timesteps, args.vocab, args.critic_iters)
+    tag = f"BASELINE configs[{idx}]" if idx is not None else "custom shape (no BASELINE config)"
+    return (f"{tag}: full G+D WGAN-GP iteration, batch {batch}/GPU, 196x512 annotations, "
             f"{args.timesteps // 3 if args.timesteps % 3 == 0 else args.timesteps / 3} triple(s) (T={args.timesteps}), "
             f"vocab {args.vocab}, n_critic={args.critic_iters}")
 
@@ -203,19 +269,22 @@ def kernel_rooflines(trainer, args, pk, dev_batches):
     anns = [t for hb in dev_batches for t in hb[:2]]
     out = []
 
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the same
-    # kernels at this shape (profiles/r1b_*_kernels.raw.csv); only valid for the default config 2 shape
-    traffic = {}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed ncu --set full capture of the same
+    # kernels at this shape (profiles/traffic.json names the capture and the commit it was taken at); it is NOT measured
+    # inside this run (a number taken under a profiler is never a bench value) and only applies to the config 2 shape
+    traffic, traffic_src = {}, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and (B, T, V) == (256, 3, 2000):
         with open(tpath) as f:
             traffic = json.load(f)
+        traffic_src = traffic.pop("_source", "profiles/traffic.json (ncu --set full capture, not measured in this run)")
 
     def entry(name, secs, nbytes, note):
         ach = nbytes / secs / 1e9
         key = name.split(" ")[0].split("<")[0]
         return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": traffic.get(key), "us_per_launch": secs * 1e6, "algorithmic_bytes": nbytes, "peak_source": pk["source"],
+                "traffic": traffic.get(key), "traffic_source": traffic_src if traffic.get(key) is not None else None,
+                "us_per_launch": secs * 1e6, "algorithmic_bytes": nbytes, "peak_source": pk["source"],
                 "l2": note}
 
     # ---- attention step forward, 3 streams (fake / real / interpolate) sharing one tile read
@@ -287,6 +356,18 @@ def kernel_rooflines(trainer, args, pk, dev_batches):
         out.append(entry("adam_proj_kernel (Adam on W_a fused with the next P = flat(a) W_a; incl. its zero-fill launch)", t, nbytes,
                          "10 back-to-back launches; 28 B/param over W_a (551 MB) + one annotation tensor (51 MB) per launch"))
 
+    # ---- dW_a = flat(a)^T P_bar (M = 100352, N = 196, K = B; fp32 gradient written once): HBM-bound
+    PBH = torch.randn(B, 512, device=dev).bfloat16()
+    dWa = torch.empty(R * 512, R, dtype=torch.float32, device=dev)
+
+    def dwa(i):
+        a = anns[i % len(anns)]
+        ops.gemm(a.view(B, R * 512), PBH, R * 512, R, a_mn=True, b_mn=True, segs=[(0, 0, 0, 0, B), (0, 0, 0, 256, B)], out=dWa, splits=1)
+    t = _time_launches(dwa, 12)
+    nbytes = B * R * 512 * 2 + R * 512 * R * 4 + 2 * B * R * 2 * 2
+    out.append(entry("gemm_kernel_dWa : dW_a = flat(a)^T P_bar (M=100352, N=196, K=B, fp32 gradient out)", t, nbytes,
+                     "12 back-to-back launches, rotating annotation tensors; 51 MB read + 79 MB written per launch"))
+
     # ---- Adam over the discriminator bucket (+ hi/lo shadow rewrite)
     n = bucket.theta.numel()
     th, gr, mm, vv = (torch.zeros(n, device=dev) for _ in range(4))
@@ -309,6 +390,77 @@ def kernel_rooflines(trainer, args, pk, dev_batches):
     return out
 
 
+def gemm_rooflines(args, pk):
+    """Tensor-pipe view of the step's tcgen05 GEMM classes at the shapes this run uses: each is replayed back to back from a
+    CUDA graph (the host-side launch cost would otherwise dominate these 10-60 us kernels) and timed with CUDA events.
+    `achieved` counts ALGORITHMIC flops (2 M N K once -- the hi/lo split issues every product three times, reported as
+    `issued_tflops`), `peak` is the measured sustained bf16 rate (a kernel timed inside a long train)."""
+    import torch
+    from sgg_b200 import ops
+    dev = "cuda"
+    B, T, V = args.batch, args.timesteps, args.vocab
+    KXD, KXG = 1344, 1536
+    shapes = [   # name, M, N, K, a_mn, b_mn, kwargs
+        ("gates D fwd: q = [z,u,h] K, 3 streams", 3 * B, 2048, KXD, False, True, dict(atomic=2)),
+        ("gates G fwd, 5 noise draws", args.critic_iters * B, 2048, KXG, False, True, dict(atomic=2)),
+        ("x_bar = q_bar K^T, 4 row blocks", 4 * B, 1324, 2048, False, False, dict(atomic=2)),
+        ("dK = X^T q_bar over all steps / streams", 1324, 2048, 4 * B * T, True, True, dict(atomic=1)),
+        ("scores: e = P + c W_h, 3 streams", 3 * B, 196, 512, False, True, dict(addm=True, atomic=2)),
+        ("logits: h W_dec, 5 draws x T steps (hi/lo out)", args.critic_iters * B * T, V, 512, False, True, dict(hl=True)),
+        ("embedding: x W_emb (soft one-hot), T steps", B * T, 300, V, False, True, dict(atomic=2)),
+    ]
+    out = []
+    for name, M, N, K, a_mn, b_mn, kw in shapes:
+        KP = (K + 63) // 64 * 64
+        if not a_mn:
+            A = torch.randn(M, 2 * KP, device=dev).bfloat16(); a_seg = [(0, 0), (KP, 0)]
+        else:
+            MP = (M + 63) // 64 * 64
+            A = torch.randn(K, 2 * MP, device=dev).bfloat16(); a_seg = [(0, 0), (0, MP)]
+        if not b_mn:
+            NPad = (N + 63) // 64 * 64
+            Bm = torch.randn(2 * NPad, KP, device=dev).bfloat16(); b_seg = [(0, 0), (0, NPad)]
+        else:
+            Bm = torch.randn(2 * KP, (N + 7) // 8 * 8, device=dev).bfloat16(); b_seg = [(0, 0), (KP, 0)]
+        segs = [(a_seg[0][0], a_seg[0][1], b_seg[0][0], b_seg[0][1], K), (a_seg[1][0], a_seg[1][1], b_seg[0][0], b_seg[0][1], K),
+                (a_seg[0][0], a_seg[0][1], b_seg[1][0], b_seg[1][1], K)]
+        NP = (N + 63) // 64 * 64
+        o = torch.zeros(M, NP, device=dev)
+        add = torch.randn(B, NP, device=dev) if kw.get("addm") else None
+        ohl = torch.zeros(M, 2 * NP, device=dev, dtype=torch.bfloat16) if kw.get("hl") else None
+
+        def call():
+            ops.gemm(A, Bm, M, N, a_mn=a_mn, b_mn=b_mn, segs=segs, out=None if ohl is not None else o[:, :N], atomic=kw.get("atomic", 0),
+                     out_hl=ohl, lo_off=NP, addm=add, add_mod=B if add is not None else 0, splits=0, block_n=0)
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        reps = 30
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(reps):
+                call()
+        g.replay()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) * 1e-3 / reps
+            best = t if best is None or t < best else best
+        fl = 2.0 * M * N * K
+        out.append({"bound": "tensor", "kernel": f"gemm_kernel ({name}; M={M} N={N} K={K})", "achieved": fl / best / 1e12,
+                    "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": fl / best / 1e12 / pk["bf16_sustained"], "traffic": None,
+                    "us_per_launch": best * 1e6, "algorithmic_flops": fl, "issued_tflops": 3 * fl / best / 1e12,
+                    "peak_source": pk["source"] + ", sustained bf16", "l2": f"{reps} graph-replayed back-to-back launches, operands L2-resident "
+                    "(as in the step: every operand was just written by the preceding kernel)"})
+        del g
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -319,6 +471,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the sgg_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    placement = bind_to_gpu_numa_node(local) if os.environ.get("SGG_NUMA_BIND", "1") != "0" else {"numa_node": None, "cpus": None}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
@@ -388,7 +541,19 @@ def run_gpu_arm(args):
         secs, e2e_max = t[0].item(), t[1].item()
         e2e_secs = e2e_max if e2e_secs is not None else None
 
+    # host-to-device rate of the batch copy with every rank copying at once (what bounds the end-to-end number at N = 8)
+    barrier()
+    h2d_gbs = h2d_probe(host[0])
+    if world > 1:
+        t = torch.tensor([h2d_gbs], device="cuda", dtype=torch.float64)
+        lo, sm_ = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+        h2d_min, h2d_sum = lo.item(), sm_.item()
+    else:
+        h2d_min = h2d_sum = h2d_gbs
     roofs = kernel_rooflines(tr, args, pk, dev_batches) if rank == 0 else None
+    if rank == 0 and roofs is not None and not args.no_gemm_rooflines:
+        roofs += gemm_rooflines(args, pk)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, times, cores = cpu_reference_iterations(args, 4, 1)
@@ -409,6 +574,8 @@ def run_gpu_arm(args):
             "e2e": None if e2e_secs is None else {
                 "value": images / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": tr.h2d_bytes_per_batch,
                 "d2h_bytes_per_step": tr.d2h_bytes_per_iteration,
+                "h2d_GBps_per_rank_min": h2d_min, "h2d_GBps_all_ranks": h2d_sum, "host_placement": placement,
+                "h2d_ms_per_step_at_that_rate": 1e3 * tr.h2d_bytes_per_batch / (h2d_min * 1e9),
                 "api": "HotPathTrainer.fit(pinned host batches): double-buffered H2D on a copy stream + a 96 B loss read per iteration "
                        "(enqueued behind the iteration, consumed by the host one iteration later)"},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,

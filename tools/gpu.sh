@@ -47,7 +47,7 @@ for stage in "$@"; do
       timeout 900 $NCU --metrics gpu__time_duration.sum -c 8000 --csv --log-file $out.csv \
         python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $out.log 2>&1; rc=$? ;;
     full)
-      timeout 900 $NCU --set full --import-source on -k "regex:$arg" -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-6} -o $out -f python tools/profile_iter.py > $out.log 2>&1; rc=$?
+      timeout 900 $NCU --set full --import-source on ${NCU_EXTRA:-} -k "regex:$arg" -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-6} -o $out -f python tools/profile_iter.py > $out.log 2>&1; rc=$?
       [ -f $out.ncu-rep ] && ncu -i $out.ncu-rep --page raw --csv > $out.raw.csv 2>/dev/null ;;
     events)
       SGG_TIMING=1 SGG_PDL=0 timeout 600 python tools/profile_events.py > $out.md 2> $out.err; rc=$? ;;
