@@ -45,3 +45,39 @@ def test_product_arm_fails_loudly_without_a_gpu():
     out = _run("--steps", "1", "--warmup", "0")
     assert out.returncode != 0
     assert "no CUDA device" in (out.stderr + out.stdout)
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_workload_label_names_the_baseline_config_of_the_shape():
+    """config.workload must name BASELINE.json's configs[] entry of the SHAPE that ran (round-1 verdict: every shape was
+    labelled configs[1], and the reference arm claimed batch 256 while running 32)."""
+    import argparse
+    b = _bench_module()
+    assert b.config_index(256, 3, 2000, 5) == 1 and b.config_index(32, 3, 2000, 5) == 0
+    assert b.config_index(256, 30, 5000, 5) == 2 and b.config_index(64, 3, 2000, 5) is None
+    a = argparse.Namespace(batch=256, timesteps=3, vocab=2000, critic_iters=5, cpu_batch=32)
+    assert b.config_name(a).startswith("BASELINE configs[1]") and "batch 256/GPU" in b.config_name(a)
+    assert b.config_name(a, 32).startswith("BASELINE configs[0]") and "batch 32/GPU" in b.config_name(a, 32)
+    a3 = argparse.Namespace(batch=256, timesteps=30, vocab=5000, critic_iters=5, cpu_batch=32)
+    assert b.config_name(a3).startswith("BASELINE configs[2]") and "10 triple" in b.config_name(a3)
+    out = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-batch", "2", "--critic-iters", "1", "--vocab", "50")
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert "batch 2/GPU" in d["config"]["workload"] and d["config"]["cpu_sample_batch"] == 2
+
+
+def test_numa_binding_never_fails_the_run():
+    """Host placement is best effort: without NVML / sysfs NUMA information it reports why and changes nothing."""
+    b = _bench_module()
+    before = os.sched_getaffinity(0)
+    info = b.bind_to_gpu_numa_node(0)
+    assert set(info) >= {"numa_node", "cpus"}
+    if info["cpus"] is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
