@@ -290,15 +290,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
       const bool full = (col0 + 32 <= p.N);
+      // bias / broadcast-add operands: 16-byte loads where the row is aligned (a thread owns a row, so every scalar
+      // load instruction would touch 32 different lines; the scores GEMM's epilogue was dominated by 64 of them)
+      const bool vec4 = ((p.N & 3) == 0);
       if (p.bias && blockIdx.z == 0) {
+        if (vec4 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
       }
       if (addrow && blockIdx.z == 0) {
+        if (vec4 && (p.ld_addm & 3) == 0 && (reinterpret_cast<uintptr_t>(p.addm) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || col0 + j < p.N) v[j] += __ldg(addrow + col0 + j);
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.N) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(addrow + col0 + j));
+              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < p.N) v[j] += __ldg(addrow + col0 + j);
+        }
       }
       if (p.amax) {
         float g[32];

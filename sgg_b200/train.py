@@ -92,7 +92,34 @@ class SceneGraphGAN(object):
         if tr.dist is not None:
             tr.dist.barrier(group=tr.pg)
 
+    def load_tf_checkpoint(self, prefix: str):
+        """Restores a checkpoint written by the reference's ``tf.train.Saver`` (train.py:280,288-292; TF V2 format
+        ``<prefix>.index`` + ``<prefix>.data-*``): the hot-path variables go into the parameter buckets under their TF
+        names, the ``/Adam`` and ``/Adam_1`` slots into the Adam moments, ``beta1_power`` / ``beta1_power_1`` give the
+        optimiser steps (generator's optimiser is created first, train.py:258-259).  Variables of the convolutional
+        front-end are ignored (outside the hot path).  Returns the names that were not consumed."""
+        from . import tf_checkpoint as T
+        parts = T.split_for_buckets(T.read_checkpoint(prefix), beta1=self.trainer.beta1)
+        e = self.trainer.eng
+        for bucket, key in ((e.g, "generator"), (e.d, "discriminator")):
+            bucket.load_state_dict({k: torch.from_numpy(v) for k, v in parts[key].items()})
+            mv, vv = bucket._views(bucket.m), bucket._views(bucket.v)
+            for k in bucket.views():
+                if k in parts["adam_m"]:
+                    mv[k].copy_(torch.from_numpy(parts["adam_m"][k]).reshape(mv[k].shape))
+                if k in parts["adam_v"]:
+                    vv[k].copy_(torch.from_numpy(parts["adam_v"][k]).reshape(vv[k].shape))
+        e.g.step = parts["step"].get("beta1_power", 0)
+        e.d.step = parts["step"].get("beta1_power_1", 0)
+        e.counters.fill_(e.g.step)
+        return sorted(parts["other"])
+
     def _loadModel(self):
+        if not os.path.exists(self._ckpt()):      # a reference (TensorFlow) checkpoint in the directory?
+            tf_prefix = os.path.join(self.checkpoints_dir, "model.ckpt")
+            if os.path.exists(tf_prefix + ".index"):
+                self.load_tf_checkpoint(tf_prefix)
+                return
         ck = torch.load(self._ckpt(), map_location="cpu")
         e = self.trainer.eng
         e.g.load_state_dict(ck["generator"])

@@ -100,6 +100,41 @@ def test_scene_graph_gan_trainer(tmp_path):
     assert int(gan2.trainer.eng.counters.item()) == 3
 
 
+def test_resume_from_a_tensorflow_checkpoint(tmp_path):
+    """train.py:280,288-292,348-349: --resume restores a tf.train.Saver checkpoint.  A V2 checkpoint carrying the reference's
+    variable names (plus the Adam slots, beta powers and a conv-front-end variable that must be ignored) is written with
+    sgg_b200.tf_checkpoint.write_checkpoint and restored into a fresh trainer through the --resume path."""
+    import numpy as np
+    from sgg_b200 import tf_checkpoint as T
+    from sgg_b200.train import SceneGraphGAN
+    V, B = 30, 4
+    src = SceneGraphGAN(str(tmp_path / "a"), None, None, None, None, None, None, critic_iters=2, batch_size=B, lambda_=10,
+                        resume=False, vocab_size=V, seed=4)
+    src.train(max_iterations=2)
+    torch.cuda.synchronize()
+    e = src.trainer.eng
+    tensors = {}
+    for bucket in (e.g, e.d):
+        mv, vv = bucket._views(bucket.m), bucket._views(bucket.v)
+        for k, v in bucket.views().items():
+            tensors[k] = v.cpu().numpy()
+            tensors[k + "/Adam"] = mv[k].cpu().numpy()
+            tensors[k + "/Adam_1"] = vv[k].cpu().numpy()
+    tensors["beta1_power"] = np.float32(0.5 ** e.g.step)          # generator's optimiser is created first (train.py:258)
+    tensors["beta1_power_1"] = np.float32(0.5 ** e.d.step)
+    tensors["Generator/Generator/conv1_1/kernel"] = np.zeros((3, 3, 3, 64), np.float32)
+    ck = tmp_path / "b"
+    T.write_checkpoint(str(ck / "model.ckpt"), tensors)
+    dst = SceneGraphGAN(str(ck), None, None, None, None, None, None, critic_iters=2, batch_size=B, lambda_=10, resume=True,
+                        vocab_size=V, seed=99)
+    d = dst.trainer.eng
+    assert (d.g.step, d.d.step) == (e.g.step, e.d.step) == (2, 4)
+    for a, b in ((e.g, d.g), (e.d, d.d)):
+        assert torch.equal(a.theta, b.theta) and torch.equal(a.m, b.m) and torch.equal(a.v, b.v)
+        assert torch.equal(a.shadow, b.shadow)                     # the bf16 operand shadow was rebuilt from the loaded weights
+    assert dst.load_tf_checkpoint(str(ck / "model.ckpt")) == ["Generator/Generator/conv1_1/kernel"]
+
+
 def test_recall_at_k_evaluation(tmp_path):
     """SceneGraphGAN.test (train.py:297-335): fakes ranked by critic score, R@50 / R@100 against the real triples.
     Checked against a host restatement that uses the classes' own build_generator / build_discriminator outputs."""
