@@ -201,6 +201,7 @@ struct GpSlopesParams {
   int B, T, V; const float* g; long long ld;
   float* slopes; float* coef; float* scal;  // scal[2] (gp) accumulated atomically
   float inv_Bglobal;
+  __nv_bfloat16* vhl; long long ldv; long long v_lo;   // optional: v = coef_b * g as a bf16 hi/lo pair (the tangent direction)
 };
 __global__ void __launch_bounds__(256) gp_slopes_kernel(const GpSlopesParams p) {
   pdl_trigger();
@@ -222,7 +223,21 @@ __global__ void __launch_bounds__(256) gp_slopes_kernel(const GpSlopesParams p) 
     const float ex = fmaxf(slope - 1.0f, 0.f);
     p.slopes[b] = slope;
     p.coef[b] = 2.0f * p.inv_Bglobal * ex / slope;
+    red[0] = p.coef[b];
     atomicAdd(p.scal + 2, ex * ex * p.inv_Bglobal);
+  }
+  if (p.vhl == nullptr) return;
+  __syncthreads();
+  const float coef = red[0];   // the rows of this sample were just read: they come back from L1 / L2
+  for (int t = 0; t < p.T; ++t) {
+    const float* row = p.g + ((long long)t * p.B + b) * p.ld;
+    __nv_bfloat16* dst = p.vhl + ((long long)t * p.B + b) * p.ldv;
+    for (int v = threadIdx.x; v < p.V; v += 256) {
+      __nv_bfloat16 h, l;
+      split_bf16(coef * row[v], h, l);
+      dst[v] = h;
+      dst[p.v_lo + v] = l;
+    }
   }
 }
 int gp_slopes(const GpSlopesParams& p, cudaStream_t stream) {

@@ -464,6 +464,7 @@ struct RevCfg {
   float ydot_bar;        // D head tangent upstream (lambda)
   const float* HB;       // G: [T*B, H] h_bar contributions from the logits (row t*B+b), or null
   bool wgrad;            // accumulate parameter gradients
+  bool pb_prezeroed;     // P_bar was cleared by the step's zero-fill list
   bool clear_P;          // the W_a chain's hi/lo packing kernel also clears P (the fused Adam + projection accumulates into it)
 };
 
@@ -538,11 +539,32 @@ static int rev_slices(const Net& n, const RevCfg& rc) {
   return lstm_rev_grid((tan ? (rc.tan_pblk - rc.blk0) : rc.nblk) * n.m.B + (tan ? n.m.B : 0));
 }
 
+// Tiny reduction kernels (losses, LN-gradient partial sums, column sums, the one-hot embedding scatter) occupy a handful of
+// CTAs for a few microseconds each; on the step's serial chain each of them costs a full launch slot.  They run on the
+// auxiliary stream instead (forked where their inputs are complete, joined at the end of the step), beside the SM-filling
+// kernels of the main chain.  SGG_AUX_STREAM=0 keeps them in line.
+static bool aux_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SGG_AUX_STREAM"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1 && side_stream(1) != nullptr;
+}
+static int aux_fork(cudaStream_t st, cudaStream_t* out) {
+  *out = st;
+  if (!aux_enabled()) return 0;
+  return side_fork(st, out, 1);
+}
+static int aux_join(cudaStream_t st) {
+  if (!aux_enabled()) return 0;
+  return side_join(st, side_stream(1)->s, 1);
+}
+
 // Parameter gradients after the reverse loop(s) over ALL active rows of the network: LN gamma / beta (and D head) from
 // the per-CTA partials of up to two loops, then one GEMM per kernel over all timesteps / streams.
 static int net_reverse_wgrad(const Net& n, bool clear_P, cudaStream_t* side_out, const float* lnp0, int slices0,
                              const float* lnp1 = nullptr, int slices1 = 0) {
   const Dm& m = n.m;
+  cudaStream_t ax = n.st;
+  SGG_TRY(aux_fork(n.st, &ax));   // joined by the caller at the end of the step (aux_join)
   for (int k = 0; k < 2; ++k) {
     const float* part = k == 0 ? lnp0 : lnp1;
     if (!part) continue;
@@ -550,11 +572,11 @@ static int net_reverse_wgrad(const Net& n, bool clear_P, cudaStream_t* side_out,
     lg.partials = part; lg.nslices = k == 0 ? slices0 : slices1;
     for (int i = 0; i < 5; ++i) { lg.dgamma[i] = n.grad + n.L.lng[i]; lg.dbeta[i] = n.grad + n.L.lnb[i]; }
     if (!n.gen) { lg.dwdec = n.grad + n.L.Wdec; lg.dbdec = n.grad + n.L.bdec; }
-    SGG_TRY(lngrad_reduce(lg, n.st));
+    SGG_TRY(lngrad_reduce(lg, ax));
   }
   // ---------------- weight gradients: one GEMM per kernel over all timesteps / streams
   const long long rowsT = (long long)m.T * n.NR;
-  SGG_TRY(colsum(n.w.PB, m.RP, m.B, m.R, n.grad + n.L.batt, n.st));   // db_att = column sums of P_bar
+  SGG_TRY(colsum(n.w.PB, m.RP, m.B, m.R, n.grad + n.L.batt, ax));   // db_att = column sums of P_bar
   {  // dW_a = flat(a)^T P_bar  [R*C, R]: on the side stream when the caller takes it over (it joins later)
     cudaStream_t s1 = n.st;
     if (side_out) { SGG_TRY(side_fork(n.st, &s1)); *side_out = s1; }
@@ -616,7 +638,7 @@ static int net_reverse_wgrad(const Net& n, bool clear_P, cudaStream_t* side_out,
 // Reverse pass over T steps as one sequence: loop, then (with wgrad) the parameter gradients.
 static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = nullptr) {
   const Dm& m = n.m;
-  if (rc.wgrad) SGG_TRY(zero_2d(n.w.PB, (long long)m.B * m.RP, (long long)m.B * m.RP, 1, n.st));
+  if (rc.wgrad && !rc.pb_prezeroed) SGG_TRY(zero_2d(n.w.PB, (long long)m.B * m.RP, (long long)m.B * m.RP, 1, n.st));
   SGG_TRY(net_reverse_loop(n, rc));
   if (!rc.wgrad) return 0;
   const bool tan = rc.tan_blk >= 0;
@@ -914,7 +936,8 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     // bucket, the loss scalars, the embedding GEMM's output and the step-0 scores of the three streams
     ZeroList zl;
     if (zl.add(a->d_grad + skip, (d.L.total - skip) * 4) && zl.add(scalars, 16) &&
-        zl.add(w.UF, (long long)T * B * m.EP * 4) && zl.add(d.w.EA, 3LL * B * m.RP * 4)) {
+        zl.add(w.UF, (long long)T * B * m.EP * 4) && zl.add(d.w.EA, 3LL * B * m.RP * 4) &&
+        zl.add(d.w.PB, (long long)B * m.RP * 4)) {   // P_bar: accumulated by the last reverse pass of this step
       SGG_TRY(zero_fill(zl, st));
       pre_uf = pre_ea0 = true;
     } else {
@@ -936,7 +959,11 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   if (pre && pre->have_proj && pre->proj_stream != st) SGG_TRY(side_join(st, pre->proj_stream));
   SGG_TRY(net_forward(d, 3, pre_ea0));
   LossParams lp{B, T, d.w.Y, 0, 1, invBT, scalars};
-  SGG_TRY(losses(lp, st));
+  {
+    cudaStream_t ax = st;
+    SGG_TRY(aux_fork(st, &ax));
+    SGG_TRY(losses(lp, ax));
+  }
   // The reverse pass of the fake and real streams is first order and needs nothing from the gradient-penalty chain
   // (interp data-path reverse -> slopes -> tangent forward -> reverse over interp + tangent): it runs on the auxiliary
   // stream beside that chain (both are sequences of small latency-bound kernels); the streams meet before the
@@ -963,6 +990,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   SGG_TRY(net_reverse(d, ig));
   SGG_TRY(embed_input_grad(d, w, 2, false));
   GpSlopesParams sp{B, T, m.V, w.DFAKE, m.VP, w.slopes, w.coef, scalars, 1.0f / ((float)B * a->world)};
+  sp.vhl = w.VHL; sp.ldv = 2 * m.VP; sp.v_lo = m.VP;    // the tangent direction v = coef * g, packed hi/lo by the same kernel
   SGG_TRY(gp_slopes(sp, st));
   // 5. tangent forward along v = coef * g
   {
@@ -981,11 +1009,6 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
       SGG_CUDA(cudaMemsetAsync(d.w.CH + 3LL * B * 2 * m.H, 0, (size_t)B * 2 * m.H * 2, st));
       SGG_CUDA(cudaMemsetAsync(d.w.ED, 0, (size_t)B * m.RP * 4, st));
     }
-    PackParams pk{};
-    pk.rows = T * B; pk.cols = m.V; pk.src = w.DFAKE; pk.ld = m.VP;
-    pk.scale = w.coef; pk.smod = B;
-    pk.dst = w.VHL; pk.ldd = 2 * m.VP; pk.lo_off = m.VP;
-    SGG_TRY(pack_hl(pk, st));
     SGG_TRY(embed_dense(d, w, w.VHL, pre_t));
     EmbedMixParams et{};
     et.B = B; et.T = T; et.E = m.E; et.V = m.V; et.Uf = w.UF; et.ldUf = m.EP;
@@ -1007,6 +1030,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     rv.blk0 = 0; rv.nblk = 3; rv.tan_pblk = 2; rv.tan_blk = 3;
     rv.ybar_blk[0] = invBT; rv.ybar_blk[1] = -invBT; rv.ybar_blk[2] = 0.f; rv.ydot_bar = a->lam;
     rv.wgrad = true;
+    rv.pb_prezeroed = pre_uf;
     rv.clear_P = pre && pre->clear_P;
     SGG_TRY(net_reverse(d, rv, &s1));
   }
@@ -1038,8 +1062,11 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     es.B = B; es.T = T; es.E = m.E; es.V = m.V; es.labels = a->labels; es.gp_alpha = gp_alpha;
     es.XB = d.w.XB; es.ldXB = d.KXP; es.strideT = d.sXB(); es.uoff = d.uoff;
     es.blk_real = 1; es.blk_int = 2; es.dWemb = a->d_grad + d.L.Wemb;
-    SGG_TRY(embed_scatter(es, st));
+    cudaStream_t ax = st;
+    SGG_TRY(aux_fork(st, &ax));          // the x_bar rows it reads are complete; its reductions commute with the GEMMs'
+    SGG_TRY(embed_scatter(es, ax));
   }
+  SGG_TRY(aux_join(st));
   if (side_out) *side_out = s1;
   else SGG_TRY(side_join(st, s1));
   return 0;
@@ -1067,11 +1094,13 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   const Dm& m = d.m;
   const int B = m.B, T = m.T;
   const float invBT = 1.0f / ((float)B * a->world * T);
+  bool g_pb_zeroed = false;
   {
     const long long skip = (long long)m.R * m.C * m.R;   // dW_a is overwritten by its GEMM
     ZeroList zl;
-    if (zl.add(a->g_grad + skip, (g.L.total - skip) * 4) && zl.add(scalars, 16)) {
+    if (zl.add(a->g_grad + skip, (g.L.total - skip) * 4) && zl.add(scalars, 16) && zl.add(g.w.PB, (long long)B * m.RP * 4)) {
       SGG_TRY(zero_fill(zl, st));
+      g_pb_zeroed = true;
     } else {
       SGG_CUDA(cudaMemsetAsync(a->g_grad + skip, 0, (size_t)(g.L.total - skip) * 4, st));
       SGG_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
@@ -1090,7 +1119,11 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   if (pre && pre->have_proj && pre->proj_stream != st) SGG_TRY(side_join(st, pre->proj_stream));
   SGG_TRY(net_forward(d, 1));
   LossParams lp{B, T, d.w.Y, 0, -1, invBT, scalars};
-  SGG_TRY(losses(lp, st));
+  {
+    cudaStream_t ax = st;
+    SGG_TRY(aux_fork(st, &ax));
+    SGG_TRY(losses(lp, ax));
+  }
   // d gen_cost / d fake through D's data path
   RevCfg rd{};
   rd.blk0 = 0; rd.nblk = 1; rd.tan_pblk = -1; rd.tan_blk = -1; rd.ybar_blk[0] = -invBT; rd.wgrad = false;
@@ -1107,7 +1140,7 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
     SGG_TRY(gemm(q, st));
   }
   RevCfg rg{};
-  rg.blk0 = 0; rg.nblk = 1; rg.tan_pblk = -1; rg.tan_blk = -1; rg.HB = w.HB; rg.wgrad = true;
+  rg.blk0 = 0; rg.nblk = 1; rg.tan_pblk = -1; rg.tan_blk = -1; rg.HB = w.HB; rg.wgrad = true; rg.pb_prezeroed = g_pb_zeroed;
   cudaStream_t s1 = st;
   SGG_TRY(net_reverse(g, rg, &s1));
   {  // dW_dec = H^T dfake [H, V], db_dec = column sums of dfake
@@ -1119,8 +1152,11 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
     q.seg_b_mn[1] = m.VP; q.seg_a_mn[2] = g.KXP + g.hoff;
     q.C = a->g_grad + g.L.Wdec; q.ldc = m.V; q.atomic = 1;
     SGG_TRY(gemm(q, st));
-    SGG_TRY(colsum(w.DFAKE, m.VP, T * B, m.V, a->g_grad + g.L.bdec, st));
+    cudaStream_t ax = st;
+    SGG_TRY(aux_fork(st, &ax));
+    SGG_TRY(colsum(w.DFAKE, m.VP, T * B, m.V, a->g_grad + g.L.bdec, ax));
   }
+  SGG_TRY(aux_join(st));
   if (side_out) *side_out = s1;
   else SGG_TRY(side_join(st, s1));
   return 0;
