@@ -16,9 +16,9 @@ constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 // Zero-fill as a KERNEL (not a memset node): it takes part in the programmatic-dependent-launch chain, so the launch
-// of the kernel behind it still overlaps, which a memset node in the middle of the chain prevents.  Up to 8 pitched
+// of the kernel behind it still overlaps, which a memset node in the middle of the chain prevents.  Up to 12 pitched
 // regions per launch; widths / pitches / pointers in multiples of 16 bytes.
-constexpr int ZERO_MAX_SEG = 8;
+constexpr int ZERO_MAX_SEG = 12;
 struct ZeroSegs { void* p[ZERO_MAX_SEG]; long long pitch16[ZERO_MAX_SEG], width16[ZERO_MAX_SEG], rows[ZERO_MAX_SEG]; long long start[ZERO_MAX_SEG + 1]; int n; };
 __global__ void __launch_bounds__(256) zero_kernel(const ZeroSegs z) {
   pdl_trigger();

@@ -178,6 +178,7 @@ struct Ws {
   __nv_bfloat16* VHL;    // [T*B, 2*VP] v = coef * g hi/lo
   float* HB;             // [T*B, H]
   float* UF;             // [T*B, EP] fp32 embedding temp
+  float* UF2;            // ... of the tangent pass (so that both can be cleared by the step's one zero-fill launch)
   __nv_bfloat16* UBH;    // [T*B, 2*EP]
   __nv_bfloat16* UDB;    // [T*B, 2*EP]
   __nv_bfloat16* TRIH;   // [T*B, 2*VP] arbitrary float triples hi/lo (sgg_disc_forward)
@@ -234,6 +235,7 @@ static Ws ws_layout(const sgg_dims_t& d, void* base) {
   w.VHL = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
   w.HB = (float*)take(TB * m.H * 4);
   w.UF = (float*)take(TB * m.EP * 4);
+  w.UF2 = (float*)take(TB * m.EP * 4);
   w.UBH = (__nv_bfloat16*)take(TB * 2 * m.EP * 2);
   w.UDB = (__nv_bfloat16*)take(TB * 2 * m.EP * 2);
   w.TRIH = (__nv_bfloat16*)take(TB * 2 * m.VP * 2);
@@ -694,15 +696,15 @@ static int gen_forward(const Net& g, const Ws& w, const float* noise, int ns, in
 }
 
 // u = x W_emb for a dense [T*B, 2*VP] hi/lo input; result fp32 in w.UF
-static int embed_dense(const Net& d, const Ws& w, const __nv_bfloat16* xhl, bool prezeroed = false) {
+static int embed_dense(const Net& d, const Ws& w, const __nv_bfloat16* xhl, bool prezeroed = false, float* out = nullptr) {
   const Dm& m = d.m;
   sgg_gemm_desc_t g = gd_zero();
   g.A = xhl; g.a_rows = (long long)m.T * m.B; g.a_cols = 2 * m.VP; g.a_ld = 2 * m.VP;
   g.B = d.sh + d.L.sWemb; g.b_rows = 2LL * d.L.rWemb; g.b_cols = m.E; g.b_ld = d.L.pWemb; g.b_mn_major = 1;
   g.M = m.T * m.B; g.N = m.E;
   segs_act_weight(g, 0, m.VP, d.L.rWemb, true, m.VP);
-  g.C = w.UF; g.ldc = m.EP;
-  if (prezeroed) g.atomic = 2;   // UF was cleared by the caller's zero-fill list
+  g.C = out ? out : w.UF; g.ldc = m.EP;
+  if (prezeroed) g.atomic = 2;   // the output was cleared by the caller's zero-fill list
   return gemm(g, d.st);
 }
 
@@ -937,7 +939,12 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     ZeroList zl;
     if (zl.add(a->d_grad + skip, (d.L.total - skip) * 4) && zl.add(scalars, 16) &&
         zl.add(w.UF, (long long)T * B * m.EP * 4) && zl.add(d.w.EA, 3LL * B * m.RP * 4) &&
-        zl.add(d.w.PB, (long long)B * m.RP * 4)) {   // P_bar: accumulated by the last reverse pass of this step
+        zl.add(d.w.PB, (long long)B * m.RP * 4) &&   // P_bar: accumulated by the last reverse pass of this step
+        // the tangent pass's start state (zero: c0 / h0 do not depend on the triples; the generator step uses the same
+        // workspace with another row count), its embedding GEMM's output and its step-0 scores / gate rows
+        zl.add(d.w.X + 3LL * B * 2 * d.KXP, (long long)B * 2 * d.KXP * 2) && zl.add(d.w.Cf + 3LL * B * m.H, (long long)B * m.H * 4) &&
+        zl.add(d.w.CH + 3LL * B * 2 * m.H, (long long)B * 2 * m.H * 2) && zl.add(d.w.ED, (long long)B * m.RP * 4) &&
+        zl.add(w.UF2, (long long)T * B * m.EP * 4) && zl.add(d.w.Q + 3LL * B * 4 * m.H, (long long)B * 4 * m.H * 4)) {
       SGG_TRY(zero_fill(zl, st));
       pre_uf = pre_ea0 = true;
     } else {
@@ -994,24 +1001,16 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   SGG_TRY(gp_slopes(sp, st));
   // 5. tangent forward along v = coef * g
   {
-    // The tangent state at t = 0 is zero (c0/h0 do not depend on the triples); the generator step uses
-    // the same workspace with another row count, so clear those rows explicitly.
-    ZeroList zl;
-    bool pre_t = false;
-    if (zl.add(d.w.X + 3LL * B * 2 * d.KXP, (long long)B * 2 * d.KXP * 2) && zl.add(d.w.Cf + 3LL * B * m.H, (long long)B * m.H * 4) &&
-        zl.add(d.w.CH + 3LL * B * 2 * m.H, (long long)B * 2 * m.H * 2) && zl.add(d.w.ED, (long long)B * m.RP * 4) &&
-        zl.add(w.UF, (long long)T * B * m.EP * 4) && zl.add(d.w.Q + 3LL * B * 4 * m.H, (long long)B * 4 * m.H * 4)) {
-      SGG_TRY(zero_fill(zl, st));   // also: the tangent embedding GEMM's output and the step-0 gate rows of the tangent block
-      pre_t = true;
-    } else {
+    bool pre_t = pre_uf;   // cleared by the step's first zero-fill launch (see above)
+    if (!pre_t) {
       SGG_CUDA(cudaMemsetAsync(d.w.X + 3LL * B * 2 * d.KXP, 0, (size_t)B * 2 * d.KXP * 2, st));
       SGG_CUDA(cudaMemsetAsync(d.w.Cf + 3LL * B * m.H, 0, (size_t)B * m.H * 4, st));
       SGG_CUDA(cudaMemsetAsync(d.w.CH + 3LL * B * 2 * m.H, 0, (size_t)B * 2 * m.H * 2, st));
       SGG_CUDA(cudaMemsetAsync(d.w.ED, 0, (size_t)B * m.RP * 4, st));
     }
-    SGG_TRY(embed_dense(d, w, w.VHL, pre_t));
+    SGG_TRY(embed_dense(d, w, w.VHL, pre_t, w.UF2));
     EmbedMixParams et{};
-    et.B = B; et.T = T; et.E = m.E; et.V = m.V; et.Uf = w.UF; et.ldUf = m.EP;
+    et.B = B; et.T = T; et.E = m.E; et.V = m.V; et.Uf = w.UF2; et.ldUf = m.EP;
     et.blk_fake = 3; et.blk_real = -1; et.blk_int = -1;
     et.X = d.w.X; et.ldX = 2 * d.KXP; et.x_lo = d.KXP; et.strideT = d.sX(); et.uoff = d.uoff;
     SGG_TRY(embed_mix(et, st));
