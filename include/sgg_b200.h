@@ -35,7 +35,9 @@ int sgg_version(void);
  * process so far.  Lets a caller report how much of a timed region ran in these kernels. */
 int64_t sgg_launch_count(void);
 /* Run-time switches, for A/B comparisons inside one process.  "fused_gates": 0 = gate GEMM + cell kernel (default),
- * 1 = gate GEMM with the LayerNorm / cell epilogue fused in (csrc/gates.cu), 16 / 8 = force its cluster shape. */
+ * 1 = gate GEMM with the LayerNorm / cell epilogue fused in (csrc/gates.cu), 16 / 8 = force its cluster shape.
+ * "attn_persistent": -1 = choose the attention kernel family by batch size (default), 0 = one CTA per sample,
+ * 1 = persistent CTAs with the TMA ring running across samples. */
 int sgg_set_option(const char* name, int32_t value);
 /* Launches per kernel entry point so far, as "demangled kernel name;launches" lines (NUL-terminated, truncated to cap;
  * returns the size needed).  reset != 0 clears the counters.  Lets a test assert WHICH kernel variants a call ran. */

@@ -1131,10 +1131,11 @@ static int attn_sm_count() {
 // kernels win (all tiles stream concurrently at two CTAs per SM: 12.1 us vs 15.9 us at B = 256); from three tiles per SM
 // on the persistent kernels win (B = 444: 18.3 vs 22.0 us; B = 2368: 79.8 vs 87.2 us = 0.92 of measured HBM).
 // SGG_ATTN_PERSIST=0 / 1 forces a family.
+static int g_attn_persist = -2;   // -1 = by batch size, 0 / 1 = forced (SGG_ATTN_PERSIST or sgg_set_option("attn_persistent", v))
+void attn_set_persistent(int v) { g_attn_persist = v < 0 ? -1 : (v ? 1 : 0); }
 static bool attn_persistent(int B) {
-  static int v = -2;
-  if (v == -2) { const char* e = getenv("SGG_ATTN_PERSIST"); v = e ? (e[0] == '0' ? 0 : 1) : -1; }
-  if (v >= 0) return v == 1;
+  if (g_attn_persist == -2) { const char* e = getenv("SGG_ATTN_PERSIST"); g_attn_persist = e ? (e[0] == '0' ? 0 : 1) : -1; }
+  if (g_attn_persist >= 0) return g_attn_persist == 1;
   return B > 2 * attn_sm_count();
 }
 static bool attn_use_simt() {   // SGG_ATTN_SIMT=1 selects the CUDA-core forward kernel (A/B measurements)

@@ -1476,6 +1476,7 @@ extern "C" int sgg_gen_sample(const sgg_sample_args_t* a, sgg_stream_t stream) {
 extern "C" int sgg_set_option(const char* name, int32_t value) {
   SGG_CHECK(name != nullptr, "sgg_set_option: null name");
   if (strcmp(name, "fused_gates") == 0) { gates_set_mode(value); return 0; }
+  if (strcmp(name, "attn_persistent") == 0) { attn_set_persistent(value); return 0; }
   set_error("sgg_set_option: unknown option '%s'", name);
   return -1;
 }

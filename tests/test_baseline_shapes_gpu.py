@@ -259,3 +259,55 @@ def test_fused_gate_epilogue_kernel(mode):
             assert e < TOL, (k, e)
     finally:
         set_option("fused_gates", 0)
+
+
+def test_persistent_attention_kernels():
+    """The persistent attention kernels (selected by default above two tiles per SM, i.e. B > 296 on B200) forced on at
+    small shapes: the op-level forward / reverse entry points against torch references (several samples per CTA is
+    exercised by B = 333 > SM count), and a D + G step through them against the oracle."""
+    import ctypes as C
+    from sgg_b200._lib import check, kernel_counts, lib, set_option, stream_ptr
+    try:
+        set_option("attn_persistent", 1)
+        k0 = kernel_counts()
+        for B, R, nv in ((333, 196, 3), (5, 100, 2), (150, 29, 4)):
+            g = torch.Generator().manual_seed(B)
+            a = torch.randn(B, R, 512, generator=g).bfloat16()
+            e = torch.randn(nv * B, 256, generator=g) * 3
+            a_d, e_d = a.cuda(), e.cuda()
+            alpha = torch.empty_like(e_d)
+            z = torch.zeros(nv * B, 1024, dtype=torch.bfloat16, device="cuda")
+            check(lib().sgg_attn_forward(C.c_void_p(a_d.data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv), C.c_void_p(e_d.data_ptr()),
+                                         C.c_void_p(alpha.data_ptr()), C.c_int64(256), C.c_void_p(z.data_ptr()), C.c_int64(1024),
+                                         C.c_int64(512), stream_ptr()), "attn")
+            torch.cuda.synchronize()
+            ref_al = torch.softmax(e[:, :R].double(), -1)
+            ref_z = torch.einsum("sbr,brc->sbc", ref_al.reshape(nv, B, R), a.double()).reshape(nv * B, 512)
+            got_z = z[:, :512].float().double() + z[:, 512:].float().double()
+            assert (alpha[:, :R].cpu().double() - ref_al).abs().max().item() < 1e-6
+            assert ((got_z.cpu() - ref_z).norm() / ref_z.norm()).item() < 1e-5
+            # reverse
+            ed = (torch.randn(nv * B, R, generator=g, dtype=torch.float64) * 2).requires_grad_(True)
+            zb = torch.randn(nv * B, 512, generator=g, dtype=torch.float64)
+            al = torch.softmax(ed, -1)
+            (torch.einsum("sbr,brc->sbc", al.reshape(nv, B, R), a.double()).reshape(nv * B, 512) * zb).sum().backward()
+            alpha_d = torch.zeros(nv * B, 256, device="cuda"); alpha_d[:, :R] = al.detach().float().cuda()
+            zb_d = zb.float().cuda().contiguous()
+            eb = torch.zeros(nv * B, 512, dtype=torch.bfloat16, device="cuda")
+            pb = torch.zeros(B, 256, device="cuda")
+            check(lib().sgg_attn_reverse(C.c_void_p(a_d.data_ptr()), C.c_int32(B), C.c_int32(R), C.c_int32(nv), C.c_void_p(zb_d.data_ptr()),
+                                         C.c_int64(512), C.c_void_p(alpha_d.data_ptr()), C.c_int64(256), C.c_void_p(eb.data_ptr()),
+                                         C.c_int64(512), C.c_int64(256), C.c_void_p(pb.data_ptr()), C.c_int64(256), stream_ptr()), "attn_rev")
+            torch.cuda.synchronize()
+            got = eb[:, :R].float().double().cpu() + eb[:, 256:256 + R].float().double().cpu()
+            assert ((got - ed.grad).norm() / ed.grad.norm()).item() < 1e-4
+            ref_pb = ed.grad.reshape(nv, B, R).sum(0)
+            assert ((pb[:, :R].double().cpu() - ref_pb).norm() / ref_pb.norm()).item() < 1e-4
+        err, terr, _, k1 = _d_and_g_step(6, 3, 96, 196, seed=9)
+        assert _ran(k0, k1, "attn_fwd_p_kernel<0>") >= 3 and _ran(k0, k1, "attn_fwd_p_kernel<1>") >= 1 and _ran(k0, k1, "attn_rev_p_kernel") >= 3, k1
+        for k, (got, ref) in err.items():
+            assert _scalar_close(got, ref), (k, got, ref)
+        for k, e2 in terr.items():
+            assert e2 < TOL, (k, e2)
+    finally:
+        set_option("attn_persistent", -1)
