@@ -119,9 +119,25 @@ def bind_to_gpu_numa_node(local_rank: int):
         bus = bus.lower()
         if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs a 4-digit one
             bus = bus[4:]
-        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
-            node = int(f.read().strip())
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+        except OSError:
+            node = -1
         info["numa_node"] = node
+        if node < 0:
+            # containers often hide the sysfs NUMA node: NVML still knows the CPUs closest to the GPU
+            n_words = (os.cpu_count() + 63) // 64
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            allowed = cpus & os.sched_getaffinity(0)
+            if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+                os.sched_setaffinity(0, allowed)
+                info["cpus"] = len(allowed)
+                info["source"] = "nvmlDeviceGetCpuAffinity"
+            else:
+                info["source"] = "nvmlDeviceGetCpuAffinity: no restriction (all CPUs are equally close)"
         if node >= 0:
             with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
                 cpus = set()
@@ -471,6 +487,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the sgg_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
     placement = bind_to_gpu_numa_node(local) if os.environ.get("SGG_NUMA_BIND", "1") != "0" else {"numa_node": None, "cpus": None}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -556,6 +573,7 @@ def run_gpu_arm(args):
         roofs += gemm_rooflines(args, pk)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)       # the CPU baseline uses every host core, not only the GPU's NUMA node
         val, times, cores = cpu_reference_iterations(args, 4, 1)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"4 iterations of {args.cpu_batch} images (config 1 batch, same T/V/n_critic) after 1 warm-up; literal "
