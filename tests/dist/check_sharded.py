@@ -79,7 +79,7 @@ def main():
         r0, r1 = eng.wa_rows(rank)
         return gather_cat(flat[off + r0 * cols: off + r1 * cols].clone(), world), off, n_wa
 
-    def run_case(case, iters, nc, tol_grad, tol_m, tol_v, tol_update):
+    def run_case(case, iters, nc, tol_grad, tol_m, tol_v, tol_update, tol_loss=1e-3):
         results, draws = {}, []
         for mode in ("1", "0"):
             os.environ["SGG_WA_SHARD"] = mode
@@ -178,7 +178,7 @@ def main():
                 t = torch.tensor([got["losses"][k]], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t)
                 lsum[k] = t.item()
-                if not abs(lsum[k] - ref_losses[k]) <= 1e-3 * (abs(ref_losses[k]) + 1e-2):
+                if not abs(lsum[k] - ref_losses[k]) <= tol_loss * (abs(ref_losses[k]) + 1e-2):
                     failures.append((tag, "loss " + k, lsum[k], ref_losses[k]))
             report[tag] = (errs, worst_upd, lsum)
         if rank == 0:
@@ -206,7 +206,7 @@ def main():
     #     moved by +-lr in different directions, so the LAST gradients are taken at slightly different weights
     #     (measured: the references of two ranks, same code, same inputs, differ by up to 1.2e-3 on d.grad), so this case
     #     only bounds the drift: 5e-3, or 5 x the reference's own spread across ranks
-    run_case("trajectory", a.iters, a.critic_iters, 5e-3, 5e-3, 1e-2, 5e-2)
+    run_case("trajectory", a.iters, a.critic_iters, 5e-3, 5e-3, 1e-2, 5e-2, tol_loss=1e-2)
     nc = a.critic_iters
 
     # ---- checkpoint under sharding: rank 0 writes what every rank holds after the gather
