@@ -200,6 +200,14 @@ typedef struct sgg_step_args {
   float* scalars;         /* [4] device floats: {-, w_disc, gp, gen_cost} */
   float* logits_out;      /* optional [B,T,V] fp32 generator logits */
   int32_t flags;
+  /* Optional outputs for a caller that trains the convolutional front-end (gen:29-68 / disc:29-68, whose variables are
+   * in the var_lists of train:262-263): the adjoint of the annotations, [B,R,C] fp32, overwritten.
+   *   sgg_gen_step : ann_g_grad = d gen_cost / d ann_g      sgg_disc_step : ann_d_grad = d disc_cost / d ann_d
+   * (the generator is a constant of the discriminator step and vice versa, so the other pointer is ignored by each).
+   * Costs one GEMM (P_bar W_a^T, M = B, N = R*C, K = R) and one HBM pass over the output per step.  Step-level entry
+   * points only: sgg_train_iteration updates no front-end between its steps and rejects non-NULL pointers. */
+  float* ann_g_grad;
+  float* ann_d_grad;
 } sgg_step_args_t;
 
 /* gen:74-91 (from self.downsampled): logits [B,T,V] into logits_out. */
@@ -207,9 +215,10 @@ int sgg_gen_forward(const sgg_step_args_t* a, sgg_stream_t stream);
 /* disc:73-93 on caller-supplied float triples [B,T,V]: scores [B,T]. */
 int sgg_disc_forward(const sgg_step_args_t* a, const float* triples, float* scores_out, sgg_stream_t stream);
 /* train:365 minus the optimizer: d disc_cost / d Discriminator* into d_grad (overwritten),
- * disc_cost = scalars[1] + lam * scalars[2]  (train:245-253). */
+ * disc_cost = scalars[1] + lam * scalars[2]  (train:245-253); optionally d disc_cost / d ann_d into ann_d_grad. */
 int sgg_disc_step(const sgg_step_args_t* a, sgg_stream_t stream);
-/* train:368 minus the optimizer: d gen_cost / d Generator* into g_grad, scalars[3] = gen_cost. */
+/* train:368 minus the optimizer: d gen_cost / d Generator* into g_grad, scalars[3] = gen_cost; optionally
+ * d gen_cost / d ann_g into ann_g_grad. */
 int sgg_gen_step(const sgg_step_args_t* a, sgg_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------

@@ -212,10 +212,14 @@ def wgan_gp_losses(gp: Dict[str, Tensor], dp: Dict[str, Tensor], ann_g: Tensor, 
             "gp_gradients": gradients}
 
 
-def disc_step_grads(gp, dp, ann_g, ann_d, real, noise, gp_alpha, lam, n_steps=3):
+def disc_step_grads(gp, dp, ann_g, ann_d, real, noise, gp_alpha, lam, n_steps=3, ann_grad=False):
     """Gradients of disc_cost w.r.t. every `Discriminator*` variable (train:263,266).
-    G's forward is a constant here (var_list = disc_params)."""
+    G's forward is a constant here (var_list = disc_params).
+    ann_grad: also return d disc_cost / d self.downsampled of the discriminator (disc:68) -- what TF
+    back-propagates into the discriminator's conv variables, which are in disc_params (train:263)."""
     dp_req = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in dp.items())
+    if ann_grad:
+        ann_d = ann_d.detach().clone().requires_grad_(True)
     with torch.no_grad():
         fake = generator_forward(gp, ann_g, noise, n_steps)
     d_fake = discriminator_forward(dp_req, fake, ann_d, n_steps)
@@ -227,26 +231,31 @@ def disc_step_grads(gp, dp, ann_g, ann_d, real, noise, gp_alpha, lam, n_steps=3)
     slopes = torch.sqrt((gradients ** 2).sum(dim=(1, 2)) + GP_EPS)
     penalty = (torch.clamp(slopes / GP_TARGET - 1.0, min=0.0) ** 2).mean()
     disc_cost = w_disc + lam * penalty
-    grads = torch.autograd.grad(disc_cost, list(dp_req.values()), allow_unused=True)
+    grads = torch.autograd.grad(disc_cost, list(dp_req.values()) + ([ann_d] if ann_grad else []), allow_unused=True)
     gd = OrderedDict((k, (g if g is not None else torch.zeros_like(v)))
                      for (k, v), g in zip(dp_req.items(), grads))
-    return {"disc_cost": disc_cost.detach(), "w_disc": w_disc.detach(), "gp": penalty.detach(),
+    extra = {"ann_grad": grads[-1].detach()} if ann_grad else {}
+    return {**extra, "disc_cost": disc_cost.detach(), "w_disc": w_disc.detach(), "gp": penalty.detach(),
             "slopes": slopes.detach(), "gp_gradients": gradients.detach(), "fake": fake,
             "d_fake": d_fake.detach(), "d_real": d_real.detach(), "d_interp": d_interp.detach(),
             "grads": gd}
 
 
-def gen_step_grads(gp, dp, ann_g, ann_d, noise, n_steps=3):
+def gen_step_grads(gp, dp, ann_g, ann_d, noise, n_steps=3, ann_grad=False):
     """Gradients of gen_cost = -mean(D(G(z))) w.r.t. every `Generator*` variable
-    (train:262,265).  D's variables are constants here."""
+    (train:262,265).  D's variables are constants here.
+    ann_grad: also return d gen_cost / d self.downsampled of the generator (gen:68)."""
     gp_req = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in gp.items())
+    if ann_grad:
+        ann_g = ann_g.detach().clone().requires_grad_(True)
     fake = generator_forward(gp_req, ann_g, noise, n_steps)
     d_fake = discriminator_forward(dp, fake, ann_d, n_steps)
     gen_cost = -d_fake.mean()
-    grads = torch.autograd.grad(gen_cost, list(gp_req.values()), allow_unused=True)
+    grads = torch.autograd.grad(gen_cost, list(gp_req.values()) + ([ann_g] if ann_grad else []), allow_unused=True)
     gd = OrderedDict((k, (g if g is not None else torch.zeros_like(v)))
                      for (k, v), g in zip(gp_req.items(), grads))
-    return {"gen_cost": gen_cost.detach(), "fake": fake.detach(), "d_fake": d_fake.detach(), "grads": gd}
+    extra = {"ann_grad": grads[-1].detach()} if ann_grad else {}
+    return {**extra, "gen_cost": gen_cost.detach(), "fake": fake.detach(), "d_fake": d_fake.detach(), "grads": gd}
 
 
 # --------------------------------------------------------------------------------------

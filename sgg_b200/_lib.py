@@ -103,6 +103,7 @@ class StepArgs(C.Structure):
         ("noise", C.c_void_p), ("gp_alpha", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("scalars", C.c_void_p), ("logits_out", C.c_void_p), ("flags", C.c_int32),
+        ("ann_g_grad", C.c_void_p), ("ann_d_grad", C.c_void_p),
     ]
 
 

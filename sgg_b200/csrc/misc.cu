@@ -289,6 +289,83 @@ int colsum(const float* src, long long ld, int rows, int cols, float* out, cudaS
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ annotation adjoint
+// What a conv front-end (gen:29-68) back-propagates: d cost / d self.downsampled.  The tile a[b] enters the recurrent half
+// through z_t = sum_r alpha_r a_r (gen:17; the gradient penalty's tangent adds zdot_t = sum_r adot_r a_r), through the
+// hoisted projection P = flat(a) W_a (gen:14-15) and through c0 = h0 = mean_r a_r (gen:76-77):
+//   a_bar[b, r, :] = sum_{t, v} alpha[t][v][b][r] * z_bar[t][v][b][:]  +  (P_bar W_a^T)[b, r, :]
+//                  + (1/R) sum_{primal v} (c0_bar + h0_bar)[v][b][:]
+// The middle term is a GEMM (plan.cu net_ann_grad) that runs first and overwrites `out`; this kernel adds the other two:
+// a rank-(T * streams) update per sample from the saved alpha rows and the z_bar columns of x_bar.  The tangent vector's
+// "alpha" row is adot (zero at t = 0, where its buffer is not written) and its start state is the constant 0.
+constexpr int AG_KT = 16;      // (t, v) pairs per pass over the output chunk
+constexpr int AG_RCH = 49;     // regions per CTA (196 = 4 * 49)
+struct AnnGradParams {
+  int B, R, T, nv;
+  int row_blk[8];              // row block of vector v in alpha / XB / CB0
+  int tan_v;                   // index of the tangent vector, or -1
+  const float* alpha; long long ldA, strideA;            // alpha + t * strideA + (row_blk[v] * B + b) * ldA
+  const float* XB; long long ldXB, strideXB; int hoff;   // z_bar = XB[t][row][0:512], h0_bar = XB[0][row][hoff:hoff+512]
+  const float* CB0;            // [rows, 512] total c_bar of step 0
+  float* out;                  // [B, R, 512] fp32, accumulated into
+};
+__global__ void __launch_bounds__(128) ann_grad_kernel(const AnnGradParams p) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float al[AG_KT][AG_RCH];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int r0 = blockIdx.y * AG_RCH;
+  const int nr = min(AG_RCH, p.R - r0);
+  const int K = p.T * p.nv;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = 0; v < p.nv; ++v) {
+    if (v == p.tan_v) continue;
+    const long long row = (long long)p.row_blk[v] * p.B + b;
+    const float4 c = *reinterpret_cast<const float4*>(p.CB0 + row * 512 + tid * 4);
+    const float4 h = *reinterpret_cast<const float4*>(p.XB + row * p.ldXB + p.hoff + tid * 4);
+    s0.x += c.x + h.x; s0.y += c.y + h.y; s0.z += c.z + h.z; s0.w += c.w + h.w;
+  }
+  const float invR = 1.0f / (float)p.R;
+  s0.x *= invR; s0.y *= invR; s0.z *= invR; s0.w *= invR;
+  float* out_b = p.out + ((long long)b * p.R + r0) * 512 + tid * 4;
+  for (int k0 = 0; k0 < K; k0 += AG_KT) {
+    float4 zb[AG_KT];
+#pragma unroll
+    for (int kk = 0; kk < AG_KT; ++kk) {
+      const int k = k0 + kk, t = k / p.nv, v = k % p.nv;
+      zb[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < K && !(v == p.tan_v && t == 0))
+        zb[kk] = *reinterpret_cast<const float4*>(p.XB + t * p.strideXB + ((long long)p.row_blk[v] * p.B + b) * p.ldXB + tid * 4);
+    }
+    __syncthreads();   // the previous pass has finished reading al
+    for (int i = tid; i < AG_KT * nr; i += 128) {
+      const int kk = i / nr, rr = i - kk * nr;
+      const int k = k0 + kk, t = k / p.nv, v = k % p.nv;
+      float a = 0.f;
+      if (k < K && !(v == p.tan_v && t == 0))
+        a = p.alpha[t * p.strideA + ((long long)p.row_blk[v] * p.B + b) * p.ldA + r0 + rr];
+      al[kk][rr] = a;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < nr; ++rr) {
+      float4 acc = *reinterpret_cast<const float4*>(out_b + (long long)rr * 512);
+      if (k0 == 0) { acc.x += s0.x; acc.y += s0.y; acc.z += s0.z; acc.w += s0.w; }
+#pragma unroll
+      for (int kk = 0; kk < AG_KT; ++kk) {
+        const float a = al[kk][rr];
+        acc.x = fmaf(a, zb[kk].x, acc.x); acc.y = fmaf(a, zb[kk].y, acc.y);
+        acc.z = fmaf(a, zb[kk].z, acc.z); acc.w = fmaf(a, zb[kk].w, acc.w);
+      }
+      *reinterpret_cast<float4*>(out_b + (long long)rr * 512) = acc;
+    }
+  }
+}
+int ann_grad(const AnnGradParams& p, cudaStream_t stream) {
+  dim3 grid(p.B, (p.R + AG_RCH - 1) / AG_RCH);
+  SGG_LAUNCH(ann_grad_kernel, grid, 128, 0, stream, p);
+  return 0;
+}
+
 }  // namespace sgg
 
 // ------------------------------------------------------------------------------------ Adam

@@ -468,6 +468,8 @@ struct RevCfg {
   bool wgrad;            // accumulate parameter gradients
   bool pb_prezeroed;     // P_bar was cleared by the step's zero-fill list
   bool clear_P;          // the W_a chain's hi/lo packing kernel also clears P (the fused Adam + projection accumulates into it)
+  bool ann_grad;         // the caller wants d cost / d annotations: c0 = mean_r a is then a function of an input, so the
+                         // step-0 state adjoint is completed too (c_bar_0 += e_bar_0 W_h^T)
 };
 
 // Reverse time loop over T steps for the stream blocks of `rc` (with wgrad: LN / head gradient partials into n.lnp,
@@ -522,7 +524,7 @@ static int net_reverse_loop(const Net& n, const RevCfg& rc) {
     ap.EB = n.w.EB + t * n.sEB(); ap.ldEB = 2 * m.RP; ap.lo_off = m.RP;
     ap.Pbar = rc.wgrad ? n.w.PB : nullptr; ap.ldP = m.RP;
     SGG_TRY(attn_rev(ap, n.st));
-    if (t > 0) {  // c_bar of step t (in place) += e_bar W_h^T
+    if (t > 0 || rc.ann_grad) {  // c_bar of step t (in place) += e_bar W_h^T
       sgg_gemm_desc_t g = gd_zero();
       g.A = n.w.EB + t * n.sEB() + (long long)row0 * 2 * m.RP; g.a_rows = nrows_all; g.a_cols = 2 * m.RP; g.a_ld = 2 * m.RP;
       g.B = n.sh + n.L.sWh; g.b_rows = 2LL * n.L.rWh; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 0;
@@ -646,6 +648,36 @@ static int net_reverse(const Net& n, const RevCfg& rc, cudaStream_t* side_out = 
   const bool tan = rc.tan_blk >= 0;
   SGG_CHECK(rc.blk0 == 0 && rc.nblk * m.B + (tan ? m.B : 0) == n.NR, "net_reverse: weight gradients need all active rows");
   return net_reverse_wgrad(n, rc.clear_P, side_out, n.lnp, rev_slices(n, rc));
+}
+
+// d cost / d annotations [B,R,C] fp32 (gen:68 / disc:68 self.downsampled) after a reverse pass with weight gradients and
+// RevCfg::ann_grad over primal blocks [0, nprimal) (+ the tangent block tan_blk): K1's reverse P_bar W_a^T as a GEMM that
+// overwrites `out`, then the attention / initial-state terms (misc.cu ann_grad_kernel).  Needs P_bar packed hi/lo (done
+// by the dW_a chain) and the replicated W_a shadow (not available under the row-sharded projection).
+struct AnnGradParams;
+int ann_grad(const AnnGradParams& p, cudaStream_t stream);
+static int net_ann_grad(const Net& n, int nprimal, int tan_blk, float* out) {
+  const Dm& m = n.m;
+  SGG_CHECK(t_shard == nullptr, "annotation gradients are not available with the row-sharded attention projection");
+  SGG_CHECK(nprimal + (tan_blk >= 0 ? 1 : 0) <= 8, "net_ann_grad: too many stream blocks");
+  const long long K = (long long)m.R * m.C;
+  sgg_gemm_desc_t g = gd_zero();
+  g.A = n.w.PBH; g.a_rows = m.B; g.a_cols = 2 * m.RP; g.a_ld = 2 * m.RP;
+  g.B = n.sh + n.L.sWa; g.b_rows = 2LL * n.L.rWa; g.b_cols = m.R; g.b_ld = n.L.pAtt; g.b_mn_major = 0;
+  g.M = m.B; g.N = (int)K;
+  segs_act_weight(g, 0, m.RP, n.L.rWa, false, m.RP);
+  g.C = out; g.ldc = K; g.splits = 1;
+  SGG_TRY(gemm(g, n.st));
+  AnnGradParams p{};
+  p.B = m.B; p.R = m.R; p.T = m.T; p.nv = nprimal + (tan_blk >= 0 ? 1 : 0);
+  for (int v = 0; v < nprimal; ++v) p.row_blk[v] = v;
+  p.tan_v = -1;
+  if (tan_blk >= 0) { p.row_blk[nprimal] = tan_blk; p.tan_v = nprimal; }
+  p.alpha = n.w.EA; p.ldA = m.RP; p.strideA = n.sEA();
+  p.XB = n.w.XB; p.ldXB = n.KXP; p.strideXB = n.sXB(); p.hoff = n.hoff;
+  p.CB0 = n.w.CB;
+  p.out = out;
+  return ann_grad(p, n.st);
 }
 
 // ============================================================================ generator forward
@@ -984,6 +1016,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   RevCfg rfr{};
   rfr.blk0 = 0; rfr.nblk = 2; rfr.tan_pblk = -1; rfr.tan_blk = -1; rfr.ybar_blk[0] = invBT; rfr.ybar_blk[1] = -invBT; rfr.wgrad = true;
   const bool two = two_env != 0 && side_stream(1) != nullptr;
+  rfr.ann_grad = a->ann_d_grad != nullptr;
   if (two) {
     SGG_TRY(zero_2d(d.w.PB, (long long)m.B * m.RP, (long long)m.B * m.RP, 1, st));   // both loops accumulate P_bar
     SGG_TRY(side_fork(st, &sB, 1));
@@ -1021,6 +1054,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
   if (two) {
     RevCfg rit{};
     rit.blk0 = 2; rit.nblk = 1; rit.tan_pblk = 2; rit.tan_blk = 3; rit.ybar_blk[2] = 0.f; rit.ydot_bar = a->lam; rit.wgrad = true;
+    rit.ann_grad = a->ann_d_grad != nullptr;
     SGG_TRY(net_reverse_loop(d, rit));
     SGG_TRY(side_join(st, sB, 1));
     SGG_TRY(net_reverse_wgrad(d, pre && pre->clear_P, &s1, w.LNP, rev_slices(d, rit), w.LNP2, rev_slices(d, rfr)));
@@ -1031,6 +1065,7 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     rv.wgrad = true;
     rv.pb_prezeroed = pre_uf;
     rv.clear_P = pre && pre->clear_P;
+    rv.ann_grad = a->ann_d_grad != nullptr;
     SGG_TRY(net_reverse(d, rv, &s1));
   }
   // 7. embedding gradient: fake^T (ub_f + al ub_i) + scatter(labels, ub_r + (1-al) ub_i) + v^T udot_bar
@@ -1066,6 +1101,11 @@ static int disc_step_core(const sgg_step_args_t* a, const Ws& w, const __nv_bflo
     SGG_TRY(embed_scatter(es, ax));
   }
   SGG_TRY(aux_join(st));
+  if (a->ann_d_grad) {   // d disc_cost / d ann_d for the caller's conv front-end (disc:29-68); step-level entry point only
+    SGG_CHECK(side_out == nullptr, "annotation gradients are produced by sgg_disc_step / sgg_gen_step, not by sgg_train_iteration");
+    SGG_TRY(side_join(st, s1));
+    return net_ann_grad(d, 3, 3, a->ann_d_grad);
+  }
   if (side_out) *side_out = s1;
   else SGG_TRY(side_join(st, s1));
   return 0;
@@ -1140,6 +1180,7 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
   }
   RevCfg rg{};
   rg.blk0 = 0; rg.nblk = 1; rg.tan_pblk = -1; rg.tan_blk = -1; rg.HB = w.HB; rg.wgrad = true; rg.pb_prezeroed = g_pb_zeroed;
+  rg.ann_grad = a->ann_g_grad != nullptr;
   cudaStream_t s1 = st;
   SGG_TRY(net_reverse(g, rg, &s1));
   {  // dW_dec = H^T dfake [H, V], db_dec = column sums of dfake
@@ -1156,6 +1197,11 @@ static int gen_step_core(const sgg_step_args_t* a, const Ws& w, const float* noi
     SGG_TRY(colsum(w.DFAKE, m.VP, T * B, m.V, a->g_grad + g.L.bdec, ax));
   }
   SGG_TRY(aux_join(st));
+  if (a->ann_g_grad) {   // d gen_cost / d ann_g for the caller's conv front-end (gen:29-68); step-level entry point only
+    SGG_CHECK(side_out == nullptr, "annotation gradients are produced by sgg_disc_step / sgg_gen_step, not by sgg_train_iteration");
+    SGG_TRY(side_join(st, s1));
+    return net_ann_grad(g, 1, -1, a->ann_g_grad);
+  }
   if (side_out) *side_out = s1;
   else SGG_TRY(side_join(st, s1));
   return 0;
@@ -1229,6 +1275,7 @@ extern "C" int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t strea
   SGG_CHECK(it->critic_iters >= 0 && it->critic_iters <= a->dims.S, "sgg_train_iteration: critic_iters=%d exceeds dims.S=%d",
             it->critic_iters, a->dims.S);
   SGG_CHECK(it->counters && it->noise_all && it->gp_alpha_all && it->scalars_all, "sgg_train_iteration: missing buffers");
+  SGG_CHECK(!a->ann_g_grad && !a->ann_d_grad, "sgg_train_iteration: annotation gradients are produced by sgg_disc_step / sgg_gen_step only");
   cudaStream_t st = (cudaStream_t)stream;
   AnnStaticScope ann_static;
   const sgg_dims_t& dd = a->dims;

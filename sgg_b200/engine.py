@@ -101,6 +101,12 @@ class Engine:
                                          stream_ptr(stream)), "rng")
         self._rng_off += (self.B + 3) // 4
 
+    def _ann_grad_buffer(self, which: str) -> torch.Tensor:
+        name = "_ann_grad_" + which
+        if getattr(self, name, None) is None:
+            setattr(self, name, torch.empty(self.B, self.R, 512, dtype=torch.float32, device=self.device))
+        return getattr(self, name)
+
     def _args(self, want_logits=False) -> StepArgs:
         a = StepArgs()
         a.dims, a.world, a.lam = self.dims, self.world, self.lam
@@ -135,17 +141,26 @@ class Engine:
                                      stream_ptr(stream)), "sgg_disc_forward")
         return out
 
-    def disc_step(self, stream=None) -> None:
-        """Gradients of disc_cost into self.d.grad; scalars[1] = w_disc, scalars[2] = gp."""
+    def disc_step(self, stream=None, ann_grad: bool = False) -> Optional[torch.Tensor]:
+        """Gradients of disc_cost into self.d.grad; scalars[1] = w_disc, scalars[2] = gp.
+        ann_grad=True also returns d disc_cost / d ann_d [B,R,512] fp32 (what the discriminator's conv front-end
+        disc:29-68 back-propagates; the buffer is reused by the next call)."""
         a = self._args()
+        out = self._ann_grad_buffer("d") if ann_grad else None
+        a.ann_d_grad = _p(out)
         check(lib().sgg_disc_step(C.byref(a), stream_ptr(stream)), "sgg_disc_step")
         self._proj_cached()
+        return out
 
-    def gen_step(self, stream=None) -> None:
-        """Gradients of gen_cost into self.g.grad; scalars[3] = gen_cost."""
+    def gen_step(self, stream=None, ann_grad: bool = False) -> Optional[torch.Tensor]:
+        """Gradients of gen_cost into self.g.grad; scalars[3] = gen_cost.
+        ann_grad=True also returns d gen_cost / d ann_g [B,R,512] fp32 (gen:29-68's upstream gradient)."""
         a = self._args()
+        out = self._ann_grad_buffer("g") if ann_grad else None
+        a.ann_g_grad = _p(out)
         check(lib().sgg_gen_step(C.byref(a), stream_ptr(stream)), "sgg_gen_step")
         self._proj_cached()
+        return out
 
     def train_iteration(self, critic_iters: Optional[int] = None, comm=None, lr=1e-4, beta1=0.5, beta2=0.9,
                         eps=1e-8, stream=None) -> None:

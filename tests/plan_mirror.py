@@ -271,7 +271,7 @@ def net_tangent(a, w, steps, udot_list):
         edot, adot, zdot = attn_step_tan(a, s["alpha"], cdot, w)
         xdot = torch.cat([zdot, udot, hdot], 1)
         t = lstm_tan(s, xdot @ w["K"], cdot, w)
-        t.update({"edot": edot, "x": xdot})
+        t.update({"edot": edot, "adot": adot, "x": xdot})
         tans.append(t)
         cdot, hdot = t["cn"], t["h"]
     return tans
@@ -280,7 +280,10 @@ def net_tangent(a, w, steps, udot_list):
 def net_reverse(a, w, steps, S, ybar_list, tans=None, ydot_bar_list=None, tan_rows=None,
                 need_weight_grads=True, C=None):
     """Reverse pass over T steps for S stacked streams.  Tangent data (if any) belongs to the
-    rows `tan_rows` (a slice).  Returns dict: ubar[t] (adjoint of u_t), udot_bar[t], grads."""
+    rows `tan_rows` (a slice).  Returns dict: ubar[t] (adjoint of u_t), udot_bar[t], grads, and `abar`
+    [B,R,C], the adjoint of the annotations (what the conv front-end gen:29-68 back-propagates): the tile enters
+    through z_t = sum_r alpha_r a_r (and zdot_t = sum_r adot_r a_r), through P = flat(a) W_a and through
+    c0 = h0 = mean_r a_r; the tangent's start state is the constant 0."""
     B, R, Cc = a.shape
     H = w["Wh"].shape[0]
     T = len(steps)
@@ -295,6 +298,7 @@ def net_reverse(a, w, steps, S, ybar_list, tans=None, ydot_bar_list=None, tan_ro
         cndb = torch.zeros(B, H, dtype=dt)
     G = {k: torch.zeros_like(v) for k, v in w.items() if k not in ("Kz", "Ku", "Kh")}
     Pbar = torch.zeros(B, R, dtype=dt)
+    abar = torch.zeros(B, R, Cc, dtype=dt)
     ubar, udot_bar = [None] * T, [None] * T
     for ti in reversed(range(T)):
         s = steps[ti]
@@ -358,10 +362,16 @@ def net_reverse(a, w, steps, S, ybar_list, tans=None, ydot_bar_list=None, tan_ro
         if need_weight_grads:
             G["Wh"] += s["c_in"].T @ ebar
             Pbar += ebar.reshape(S, B, R).sum(0)
+            # ann_grad kernel: rank-(T * streams) outer-product sum over the saved alpha and the z_bar rows
+            abar += torch.einsum("sbr,sbc->brc", s["alpha"].reshape(S, B, R), zbar.reshape(S, B, Cc))
+            if tans is not None and ti > 0:       # adot_0 = 0
+                abar += torch.einsum("br,bc->brc", t["adot"], zdb)
     if need_weight_grads:
         G["Wa"] = a.reshape(B, -1).T @ Pbar
         G["b_att"] = Pbar.sum(0)
-    return {"ubar": ubar, "udot_bar": udot_bar, "grads": G, "Pbar": Pbar}
+        abar += (Pbar @ w["Wa"].T).reshape(B, R, Cc)                                   # K1 reverse
+        abar += ((cnbar + hbar).reshape(S, B, H).sum(0) / R).reshape(B, 1, Cc)         # c0 = h0 = mean_r a_r
+    return {"ubar": ubar, "udot_bar": udot_bar, "grads": G, "Pbar": Pbar, "abar": abar}
 
 
 def pack_grads(G, prefix):
@@ -434,7 +444,7 @@ def disc_step(gp, dp, ann_g, ann_d, labels, noise, gp_alpha, lam, T):
         gW += v[:, t].T @ rv["udot_bar"][t]
     grads["Discriminator/W"] = gW
     return {"disc_cost": w_disc + lam * pen, "w_disc": w_disc, "gp": pen, "slopes": slopes,
-            "gp_gradients": g, "grads": grads, "fake": fake,
+            "gp_gradients": g, "grads": grads, "fake": fake, "ann_grad": rv["abar"],
             "debug": {"steps": steps, "tans": tans, "rv": rv, "ig": ig, "P": P, "c0": c0, "y": y, "coef": coef,
                       "v": v, "u_list": u_list, "udot": udot}}
 
@@ -453,4 +463,5 @@ def gen_step(gp, dp, ann_g, ann_d, noise, T):
     dfake = [ub @ Wemb.T for ub in rd["ubar"]]                           # [B,V] per t
     rg = net_reverse(ann_g, wg, gsteps, 1, dfake)
     return {"gen_cost": gen_cost, "grads": pack_grads(rg["grads"], "Generator/Generator"), "fake": fake,
+            "ann_grad": rg["abar"],
             "debug": {"gsteps": gsteps, "dsteps": dsteps, "rd": rd, "rg": rg, "dfake": dfake, "y": y}}

@@ -35,22 +35,25 @@ def _d_and_g_step(B, T, V, R, seed=0, ann_bf16=True, lam=10.0):
     prob = make_problem(B, T, V, R=R, seed=seed, dtype=torch.float64, ann_bf16=ann_bf16)
     eng = make_engine(prob, B, T, V, R=R, lam=lam)
     k0 = kernel_counts()
-    ref = O.disc_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["real"], prob["noise"], prob["alpha"], lam, T)
-    eng.disc_step()
+    ref = O.disc_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["real"], prob["noise"], prob["alpha"], lam, T,
+                            ann_grad=True)
+    ann_d_grad = eng.disc_step(ann_grad=True)
     torch.cuda.synchronize()
     sc = eng.scalars.cpu()
     err = {"w_disc": (float(sc[1]), float(ref["w_disc"])), "gp": (float(sc[2]), float(ref["gp"]))}
-    terr = {"slopes": rel(eng.ws_view("slopes", (B,), torch.float32), ref["slopes"])}
+    terr = {"slopes": rel(eng.ws_view("slopes", (B,), torch.float32), ref["slopes"]),
+            "d disc_cost / d ann_d": rel(ann_d_grad, ref["ann_grad"])}      # what disc:29-68 would back-propagate
     gv = eng.d.grad_views()
     for k, v in ref["grads"].items():
         if k == "Discriminator/Discriminator/decoder/bias":      # analytically zero
             assert abs(float(gv[k])) < 1e-5
             continue
         terr[k] = rel(gv[k], v)
-    refg = O.gen_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["noise"], T)
-    eng.gen_step()
+    refg = O.gen_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["noise"], T, ann_grad=True)
+    ann_g_grad = eng.gen_step(ann_grad=True)
     torch.cuda.synchronize()
     err["gen_cost"] = (float(eng.scalars[3]), float(refg["gen_cost"]))
+    terr["d gen_cost / d ann_g"] = rel(ann_g_grad, refg["ann_grad"])
     gv = eng.g.grad_views()
     for k, v in refg["grads"].items():
         terr[k] = rel(gv[k], v)

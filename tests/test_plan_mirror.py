@@ -18,9 +18,10 @@ def _close(a, b, tol=1e-9):
 @pytest.mark.parametrize("B,T,V", [(3, 3, 11), (2, 5, 7), (1, 1, 4)])
 def test_disc_step_plan_equals_oracle(B, T, V):
     gp, dp, ann_g, ann_d, labels, real, noise, alpha = _small_problem(B, T, V)
-    ref = O.disc_step_grads(gp, dp, ann_g, ann_d, real, noise, alpha, 10.0, T)
+    ref = O.disc_step_grads(gp, dp, ann_g, ann_d, real, noise, alpha, 10.0, T, ann_grad=True)
     got = M.disc_step(gp, dp, ann_g, ann_d, labels, noise, alpha, 10.0, T)
     assert _close(got["fake"], ref["fake"])
+    assert _close(got["ann_grad"], ref["ann_grad"], 1e-8)     # d disc_cost / d self.downsampled (disc:68)
     assert abs(float(got["w_disc"] - ref["w_disc"])) < 1e-12
     assert abs(float(got["gp"] - ref["gp"])) < 1e-11
     assert _close(got["slopes"], ref["slopes"])
@@ -33,9 +34,10 @@ def test_disc_step_plan_equals_oracle(B, T, V):
 @pytest.mark.parametrize("B,T,V", [(3, 3, 11), (2, 4, 9)])
 def test_gen_step_plan_equals_oracle(B, T, V):
     gp, dp, ann_g, ann_d, labels, real, noise, alpha = _small_problem(B, T, V)
-    ref = O.gen_step_grads(gp, dp, ann_g, ann_d, noise, T)
+    ref = O.gen_step_grads(gp, dp, ann_g, ann_d, noise, T, ann_grad=True)
     got = M.gen_step(gp, dp, ann_g, ann_d, noise, T)
     assert abs(float(got["gen_cost"] - ref["gen_cost"])) < 1e-12
+    assert _close(got["ann_grad"], ref["ann_grad"], 1e-8)     # d gen_cost / d self.downsampled (gen:68)
     for k, v in ref["grads"].items():
         assert _close(got["grads"][k], v, 1e-8), k
 

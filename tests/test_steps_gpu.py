@@ -105,6 +105,38 @@ def test_gen_step_matches_oracle(B, T, V, R):
         assert rel(gv[k], v) < TOL, k
 
 
+@pytest.mark.parametrize("B,T,V,R", CASES + LONG_CASES)
+def test_annotation_gradients_match_oracle(B, T, V, R):
+    """d disc_cost / d ann_d (through the gradient penalty's double backward) and d gen_cost / d ann_g: the upstream
+    gradients of the conv front-ends (disc:29-68, gen:29-68), whose variables are in the var_lists of train:262-263.
+    Asking for them must not change the parameter gradients."""
+    from oracle import sgg_oracle as O
+    from tests.util import rel
+    lam = 10.0
+    prob, eng = _setup(B, T, V, R, lam=lam)
+    ref = O.disc_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["real"], prob["noise"],
+                            prob["alpha"], lam, T, ann_grad=True)
+    eng.disc_step()
+    torch.cuda.synchronize()
+    plain = eng.d.grad.clone()
+    got = eng.disc_step(ann_grad=True)
+    torch.cuda.synchronize()
+    assert got.shape == (B, R, 512) and torch.isfinite(got).all()
+    assert rel(got, ref["ann_grad"]) < TOL
+    assert rel(eng.d.grad, plain) < 1e-4            # split-K atomics reorder fp32 sums from run to run
+    refg = O.gen_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["noise"], T, ann_grad=True)
+    eng.gen_step()
+    torch.cuda.synchronize()
+    plain = eng.g.grad.clone()
+    got = eng.gen_step(ann_grad=True)
+    torch.cuda.synchronize()
+    assert rel(got, refg["ann_grad"]) < TOL
+    assert rel(eng.g.grad, plain) < 1e-4
+    gv = eng.g.grad_views()
+    for k, v in refg["grads"].items():
+        assert rel(gv[k], v) < TOL, k
+
+
 def test_steps_can_interleave_on_one_workspace():
     """D step, G step, D step on the same engine (train:362-368 order) give the same answers as fresh engines."""
     prob, eng = _setup(6, 3, 50)
