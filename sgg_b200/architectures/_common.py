@@ -16,11 +16,13 @@ REGION_CHANNELS = 512
 def as_annotations(images: torch.Tensor, device) -> torch.Tensor:
     """The hot path starts at ``self.downsampled`` (gen:68 / disc:68): ``images`` must already be the
     [B, 14, 14, 512] annotation grid (any [B, h, w, 512] or [B, R, 512] is accepted).  The reference's conv
-    front-end that produces it from 221x221x3 images is outside this path."""
+    front-end that produces it from 221x221x3 images is outside this path; a caller-side version on
+    library convolutions is ``sgg_b200.frontend.ConvFrontEnd``."""
     if images.dim() not in (3, 4) or images.shape[-1] != REGION_CHANNELS:
         raise ValueError(
             f"expected annotations [B,14,14,512] (the reference's self.downsampled), got {tuple(images.shape)}; "
-            "the convolutional front-end is not part of the B200 hot path")
+            "the convolutional front-end is not part of the B200 hot path (sgg_b200.frontend.ConvFrontEnd produces "
+            "the grid from pixels with library convolutions)")
     return images.to(device=device, dtype=torch.bfloat16).contiguous()
 
 

@@ -179,6 +179,14 @@ class TFAdam:
             p.addcdiv_(m, v.sqrt().add_(self.eps), value=-lr_t)
             p.grad = None
 
+    def state(self):
+        return {"t": self.t, "m": [m.cpu().clone() for m in self.m], "v": [v.cpu().clone() for v in self.v]}
+
+    def load_state(self, st) -> None:
+        self.t = int(st["t"])
+        for dst, src in zip(self.m + self.v, list(st["m"]) + list(st["v"])):
+            dst.copy_(src)
+
 
 class FrontEndTrainer:
     """train:362-368 with the conv front-ends in the loop: ``CRITIC_ITERS`` x {D step, Adam on Discriminator*} then

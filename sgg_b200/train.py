@@ -3,8 +3,9 @@
 Kept from the reference: the constructor signature (train.py:23-24), ``_Generator`` / ``_Discriminator`` /
 ``train`` method names, the CLI flag names (train.py:399-412), the step schedule (CRITIC_ITERS D steps then one G
 step on the same batch, train.py:185-187,362-368), the losses (train.py:245-253) and the two Adam optimisers
-(train.py:258-259).  Not reproduced (outside the hot path): the conv front-end, the tf.data JPEG
-pipeline, summaries.  Documented deviations: the R@k ranking bug of train.py:320 (see ``test``); the reference passes batch_size / critic_iters to
+(train.py:258-259).  Not reproduced (outside the hot path): the tf.data JPEG pipeline, summaries.  The conv
+front-end (gen:29-68) exists as a caller-side module on library convolutions (``frontend.py``, ``train_from_images``);
+the hot path proper starts at the annotation grid.  Documented deviations: the R@k ranking bug of train.py:320 (see ``test``); the reference passes batch_size / critic_iters to
 the constructor in swapped order (train.py:420-421 vs 23-24) -- here each flag reaches its own parameter; the
 constructor does not delete the contents of the checkpoint / summary directories (train.py:50-53).
 """
@@ -64,6 +65,8 @@ class SceneGraphGAN(object):
         self.d = Discriminator(vocab_size, self.trainer.eng.d.views()["Discriminator/W"], self.n_steps)
         self.g._attach(self.trainer.eng)
         self.d._attach(self.trainer.eng)
+        self.front = None                      # FrontEndTrainer, created by the first train_from_images() / on load
+        self._seed = seed
         if self.resume:
             self._loadModel()
 
@@ -73,6 +76,13 @@ class SceneGraphGAN(object):
 
     def _Discriminator(self, triple_input, images, is_training=True):
         return self.d.build_discriminator(triple_input, images, is_training)
+
+    def _front(self):
+        """The conv front-ends (gen:29-68 / disc:29-68) and their optimisers; library convolutions, see frontend.py."""
+        if self.front is None:
+            from .frontend import FrontEndTrainer
+            self.front = FrontEndTrainer(self.trainer, seed=self._seed)
+        return self.front
 
     # ------------------------------------------------------------------ train.py:288-292 (never called there)
     def _ckpt(self):
@@ -86,9 +96,14 @@ class SceneGraphGAN(object):
         tr.gather_sharded()
         e = tr.eng
         if tr.rank == 0:
-            torch.save({"generator": e.g.state_dict(), "discriminator": e.d.state_dict(),
-                        "adam": {"g": (e.g.m.cpu(), e.g.v.cpu(), e.g.step), "d": (e.d.m.cpu(), e.d.v.cpu(), e.d.step)},
-                        "iterations": int(e.counters.item())}, self._ckpt())
+            ck = {"generator": e.g.state_dict(), "discriminator": e.d.state_dict(),
+                  "adam": {"g": (e.g.m.cpu(), e.g.v.cpu(), e.g.step), "d": (e.d.m.cpu(), e.d.v.cpu(), e.d.step)},
+                  "iterations": int(e.counters.item())}
+            if self.front is not None:      # conv variables under their TF names (HWIO kernels) + their Adam state
+                f = self.front
+                ck["front_end"] = {k: v.cpu().clone() for net in (f.fg, f.fd) for k, v in net.tf_variables().items()}
+                ck["front_end_adam"] = {"g": f.adam_fg.state(), "d": f.adam_fd.state()}
+            torch.save(ck, self._ckpt())
         if tr.dist is not None:
             tr.dist.barrier(group=tr.pg)
 
@@ -112,7 +127,13 @@ class SceneGraphGAN(object):
         e.g.step = parts["step"].get("beta1_power", 0)
         e.d.step = parts["step"].get("beta1_power_1", 0)
         e.counters.fill_(e.g.step)
-        return sorted(parts["other"])
+        other = parts["other"]
+        if any("/conv2d" in k for k in other):     # the conv front-end's variables (gen:29-68), if the caller trains it
+            f = self._front()
+            for net in (f.fg, f.fd):
+                for name in net.load_tf_variables({k: torch.from_numpy(v) for k, v in other.items()}, strict=False):
+                    other.pop(name)
+        return sorted(other)
 
     def _loadModel(self):
         if not os.path.exists(self._ckpt()):      # a reference (TensorFlow) checkpoint in the directory?
@@ -128,6 +149,12 @@ class SceneGraphGAN(object):
             m, v, step = ck["adam"][key]
             b.m.copy_(m); b.v.copy_(v); b.step = step
         e.counters.fill_(ck["iterations"])
+        if "front_end" in ck:
+            f = self._front()
+            f.fg.load_tf_variables(ck["front_end"])
+            f.fd.load_tf_variables(ck["front_end"])
+            f.adam_fg.load_state(ck["front_end_adam"]["g"])
+            f.adam_fd.load_state(ck["front_end_adam"]["d"])
 
     # ------------------------------------------------------------------ train.py:341-388
     def train(self, batches: Optional[Iterable] = None, max_iterations: Optional[int] = None, log_every: int = 10):
@@ -156,6 +183,23 @@ class SceneGraphGAN(object):
             if out:
                 out.close()
         return n
+
+    def train_from_images(self, batches: Iterable, max_iterations: Optional[int] = None):
+        """The reference's loop on pixels (train.py:362-368 with gen:29-68 / disc:29-68 in the graph): ``batches`` yields
+        (images [B,221,221,3] float, standardised as train.py:170 does; labels [B, n_steps] int64).  The convolutional
+        front-ends are library calls (frontend.py); every step's recurrent half runs through the step-level C ABI
+        (sgg_disc_step / sgg_gen_step with the annotation adjoint as an extra output), not through the graph-captured
+        sgg_train_iteration -- the conv variables change between the steps.  Single GPU.  Returns the per-iteration logs."""
+        if self.trainer.world > 1:
+            raise RuntimeError("train_from_images: the conv front-end is not data-parallel in this build")
+        f = self._front()
+        dev = self.trainer.eng.device
+        logs = []
+        for images, labels in batches:
+            logs.append(f.iteration(images.to(device=dev, dtype=torch.float32), labels.to(device=dev, dtype=torch.int64).contiguous()))
+            if max_iterations and len(logs) >= max_iterations:
+                break
+        return logs
 
     @staticmethod
     def _recall(fake, real, N):

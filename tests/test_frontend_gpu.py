@@ -1,0 +1,112 @@
+"""The seam between the caller-side conv front-end (library convolutions, sgg_b200/frontend.py) and the CUDA hot path:
+conv-variable gradients obtained by back-propagating the annotation adjoint that sgg_disc_step / sgg_gen_step return
+must equal the oracle differentiated end to end (front-end restated in fp64 + oracle/sgg_oracle.py), and the reference's
+loop on pixels must run through SceneGraphGAN.train_from_images."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 5e-3     # conv gradients are linear images of the annotation adjoint (itself within 1e-3); fp32 convolutions on the GPU side
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-300)).item()
+
+
+def test_conv_gradients_through_the_seam_match_the_oracle_end_to_end():
+    from oracle import sgg_oracle as O
+    from sgg_b200.frontend import ConvFrontEnd, FrontEndTrainer
+    from sgg_b200.trainer import HotPathTrainer
+    B, T, V, R, lam = 4, 2, 50, 4, 10.0
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        tr = HotPathTrainer(B, T, V, critic_iters=1, lam=lam, regions=R, use_graph=False)
+        ft = FrontEndTrainer(tr, seed=3)
+        eng = tr.eng
+        gp = O.init_generator_params(V, seed=5, R=R, C=512, H=512)
+        dp = O.init_discriminator_params(V, seed=6, R=R, C=512, H=512, E=300)
+        dp["Discriminator/W"] = dp["Discriminator/W"] * 40          # slopes above 1: the penalty is active
+        eng.g.load_state_dict(gp); eng.d.load_state_dict(dp)
+        g = torch.Generator().manual_seed(9)
+        images = torch.randn(B, 17, 17, 3, generator=g)              # 17 -> 9 -> 5 -> 3 -> 2: R = 4
+        labels = torch.randint(0, V, (B, T), generator=g)
+        noise, alpha = torch.randn(B, 512, generator=g), torch.rand(B, generator=g)
+        real = torch.nn.functional.one_hot(labels, V).double()
+        gp64, dp64 = {k: v.double() for k, v in gp.items()}, {k: v.double() for k, v in dp.items()}
+        dev = eng.device
+        # ---------------- GPU: front-end (cuDNN, fp32) -> hot path -> annotation adjoint -> front-end backward
+        ann_g = ft.fg(images.to(dev)).reshape(B, R, 512)
+        ann_d = ft.fd(images.to(dev)).reshape(B, R, 512)
+        ag16, ad16 = ann_g.detach().to(torch.bfloat16).contiguous(), ann_d.detach().to(torch.bfloat16).contiguous()
+        eng.set_batch(ag16, ad16, labels.to(dev))
+        eng.noise.copy_(noise); eng.gp_alpha.copy_(alpha)
+        got_d = torch.autograd.grad(ann_d, list(ft.fd.live_parameters()), grad_outputs=eng.disc_step(ann_grad=True))
+        gp_value = float(eng.scalars[2])
+        got_g = torch.autograd.grad(ann_g, list(ft.fg.live_parameters()), grad_outputs=eng.gen_step(ann_grad=True))
+        torch.cuda.synchronize()
+        # ---------------- CPU: the same front-ends in fp64, annotation VALUES as the GPU saw them (bf16), end-to-end autograd
+        def twin(net):
+            t = ConvFrontEnd(net.scope).double()
+            t.load_tf_variables({k: v.cpu().double() for k, v in net.tf_variables().items()})
+            return t
+        fg64, fd64 = twin(ft.fg), twin(ft.fd)
+
+        def straight_through(net64, seen16):
+            a = net64(images.double()).reshape(B, R, 512)
+            assert _rel(a, seen16.float()) < 1e-2               # the GPU front-end computed the same annotations (bf16-rounded)
+            return a + (seen16.cpu().double() - a).detach()
+        losses = O.wgan_gp_losses(gp64, dp64, ag16.cpu().double(), straight_through(fd64, ad16), real, noise.double(),
+                                  alpha.double(), lam, T)
+        assert float(losses["gp"]) > 0 and abs(gp_value - float(losses["gp"])) <= 1e-3 * float(losses["gp"]) + 1e-5
+        ref_d = torch.autograd.grad(losses["disc_cost"], list(fd64.live_parameters()))
+        losses = O.wgan_gp_losses(gp64, dp64, straight_through(fg64, ag16), ad16.cpu().double(), real, noise.double(),
+                                  alpha.double(), lam, T)
+        ref_g = torch.autograd.grad(losses["gen_cost"], list(fg64.live_parameters()))
+        worst = {"disc": max(_rel(a, b) for a, b in zip(got_d, ref_d)), "gen": max(_rel(a, b) for a, b in zip(got_g, ref_g))}
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", "frontend_seam.json"), "w") as f:
+            json.dump({"worst_relative_l2_of_conv_gradients": worst, "tolerance": TOL, "gp": gp_value}, f)
+        assert worst["disc"] < TOL and worst["gen"] < TOL, worst
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+
+
+def test_train_from_images_runs_the_reference_loop_on_pixels(tmp_path):
+    """train:362-368 with the conv stacks in the loop at the reference's image size (221 x 221 -> 14 x 14 x 512): losses are
+    finite, every live conv variable of both stacks moves, the dead ones (gen:59-62) do not, and the front-end travels
+    through the checkpoint."""
+    from sgg_b200.train import SceneGraphGAN
+    B, V, nc = 2, 60, 2
+    gan = SceneGraphGAN(str(tmp_path / "ck"), str(tmp_path / "logs"), None, None, None, None, None, critic_iters=nc, batch_size=B,
+                        lambda_=10, resume=False, vocab_size=V)
+    g = torch.Generator().manual_seed(1)
+    batches = [(torch.randn(B, 221, 221, 3, generator=g), torch.randint(0, V, (B, 3), generator=g)) for _ in range(2)]
+    f = gan._front()
+    before = {k: v.clone() for net in (f.fg, f.fd) for k, v in net.tf_variables().items()}
+    hot_before = gan.trainer.eng.d.theta.clone()
+    logs = gan.train_from_images(batches)
+    torch.cuda.synchronize()
+    assert len(logs) == 2 and all(len(l["disc_cost"]) == nc for l in logs)
+    for l in logs:
+        assert all(map(lambda x: x == x and abs(x) < 1e6, l["disc_cost"] + l["gp"] + [l["gen_cost"]])), l
+    after = {k: v for net in (f.fg, f.fd) for k, v in net.tf_variables().items()}
+    dead = ("conv2d_10/", "conv2d_11/", "LayerNorm_10/", "LayerNorm_11/")
+    for k, v in after.items():
+        assert torch.equal(v, before[k]) == any(d in k for d in dead), k
+    assert not torch.equal(gan.trainer.eng.d.theta, hot_before)
+    assert f.adam_fd.t == 2 * nc and f.adam_fg.t == 2 and gan.trainer.eng.d.step == 2 * nc
+    gan._saveModel()
+    again = SceneGraphGAN(str(tmp_path / "ck"), str(tmp_path / "logs"), None, None, None, None, None, critic_iters=nc, batch_size=B,
+                          lambda_=10, resume=True, vocab_size=V)
+    assert again.front is not None and again.front.adam_fd.t == 2 * nc
+    for net_a, net_b in ((f.fg, again.front.fg), (f.fd, again.front.fd)):
+        for (k, a), b in zip(net_a.tf_variables().items(), net_b.tf_variables().values()):
+            assert torch.equal(a, b), k
+    for a, b in zip(f.adam_fd.m + f.adam_fd.v, again.front.adam_fd.m + again.front.adam_fd.v):
+        assert torch.equal(a, b)
+    gan.trainer.close(); again.trainer.close()
