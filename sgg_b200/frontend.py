@@ -209,6 +209,22 @@ class FrontEndTrainer:
             with torch.autocast("cuda", dtype=self.compute_dtype):
                 return net(images).float()
 
+    def annotations(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(ann_g, ann_d) [B,R,512] bf16 of a batch of images, no gradient (evaluation, train.py:269-275)."""
+        B = images.shape[0]
+        return tuple(self._annotations(net, images, grad=False).reshape(B, -1, 512).to(torch.bfloat16).contiguous()
+                     for net in (self.fg, self.fd))
+
+    def validation_cost(self, images: torch.Tensor, labels: torch.Tensor) -> float:
+        """disc_cost on a held-out batch (train.py:380), nothing is updated."""
+        eng = self.tr.eng
+        ann_g, ann_d = self.annotations(images)
+        eng.set_batch(ann_g, ann_d, labels)
+        eng.sample_noise(); eng.sample_gp_alpha()
+        eng.disc_step()
+        sc = eng.scalars.tolist()
+        return sc[1] + self.tr.lam * sc[2]
+
     def iteration(self, images: torch.Tensor, labels: torch.Tensor) -> Dict[str, list]:
         """One pass of the reference loop body on device tensors ``images`` [B,221,221,3] fp32, ``labels`` [B,T] int64."""
         tr, eng = self.tr, self.tr.eng

@@ -34,6 +34,8 @@ class SceneGraphGAN(object):
         self.resume = bool(resume)
         self.allow_synthetic = bool(allow_synthetic)
         self.checkpoints_dir, self.summaries_dir = checkpoints_dir, summaries_dir
+        self.path_to_ims_to_triples = path_to_ims_to_triples
+        self.path_to_image_means, self.path_to_image_stds = path_to_image_means, path_to_image_stds
         for d in (checkpoints_dir, summaries_dir):
             if d and not os.path.exists(d):
                 os.makedirs(d)
@@ -164,10 +166,19 @@ class SceneGraphGAN(object):
         tr = self.trainer
         if batches is None:
             if self.ims_to_triples is not None and not self.allow_synthetic:
-                raise RuntimeError(
-                    "SceneGraphGAN.train(): an ims_to_triples file was loaded but no annotation batches were given. The "
-                    "hot path starts at the annotation grid (gen:68); the JPEG -> conv front-end that produces it is "
-                    "outside this build (SURVEY 8f-1/f4). Pass `batches`, or --synthetic to train on synthetic inputs.")
+                # the reference's own mode: JPEG files -> conv front-ends -> recurrent half (train.py:341-388)
+                have_stats = all(p and os.path.exists(p) for p in (self.path_to_image_means, self.path_to_image_stds))
+                if not have_stats or tr.R != 196 or tr.world > 1:
+                    raise RuntimeError(
+                        "SceneGraphGAN.train(): an ims_to_triples file was loaded but training from its images needs "
+                        "image_means.txt / image_stds.txt, 196 regions and a single GPU (the conv front-end is a caller-side "
+                        "module on library convolutions). Pass annotation `batches`, or --synthetic.")
+                from .data import load_dataset
+                ds = load_dataset(self.path_to_ims_to_triples, self.path_to_image_means, self.path_to_image_stds, tr.B,
+                                  test_batch_multiplier=self.TEST_BATCH_MULTIPLIER, seed=self._seed, eval_batch_size=tr.B)
+                self.dataset = ds
+                return len(self.train_from_images(ds["train"], max_iterations or ds["max_iterations"], ds["val"],
+                                                  ds["validate_iterations"]))
             batches = synthetic_batches(tr.B, tr.T, tr.V, tr.R, max_iterations or 100, seed=1234 + tr.rank)
         log_path = os.path.join(self.summaries_dir, "train_log.jsonl") if (self.summaries_dir and tr.rank == 0) else None
         t0, n = time.time(), 0
@@ -184,22 +195,46 @@ class SceneGraphGAN(object):
                 out.close()
         return n
 
-    def train_from_images(self, batches: Iterable, max_iterations: Optional[int] = None):
+    def train_from_images(self, batches: Iterable, max_iterations: Optional[int] = None, val_batches: Optional[Iterable] = None,
+                          validate_every: Optional[int] = None):
         """The reference's loop on pixels (train.py:362-368 with gen:29-68 / disc:29-68 in the graph): ``batches`` yields
         (images [B,221,221,3] float, standardised as train.py:170 does; labels [B, n_steps] int64).  The convolutional
         front-ends are library calls (frontend.py); every step's recurrent half runs through the step-level C ABI
         (sgg_disc_step / sgg_gen_step with the annotation adjoint as an extra output), not through the graph-captured
-        sgg_train_iteration -- the conv variables change between the steps.  Single GPU.  Returns the per-iteration logs."""
+        sgg_train_iteration -- the conv variables change between the steps.  Single GPU.
+        With ``val_batches`` the reference's early stopping applies (train.py:378-388): every ``validate_every`` iterations
+        disc_cost of one held-out batch is compared with the previous one; three consecutive increases end the run.
+        Returns the per-iteration logs."""
         if self.trainer.world > 1:
             raise RuntimeError("train_from_images: the conv front-end is not data-parallel in this build")
         f = self._front()
         dev = self.trainer.eng.device
-        logs = []
-        for images, labels in batches:
-            logs.append(f.iteration(images.to(device=dev, dtype=torch.float32), labels.to(device=dev, dtype=torch.int64).contiguous()))
+        put = lambda im, lb: (im.to(device=dev, dtype=torch.float32), lb.to(device=dev, dtype=torch.int64).contiguous())
+        val_it = iter(val_batches) if val_batches is not None else None
+        logs, last_loss, worse = [], float("inf"), 0
+        for itr, (images, labels) in enumerate(batches):
+            logs.append(f.iteration(*put(images, labels)))
+            if val_it is not None and validate_every and itr % validate_every == 0:
+                loss = f.validation_cost(*put(*next(val_it)))
+                logs[-1]["val_disc_cost"] = loss
+                worse = worse + 1 if last_loss < loss else 0
+                if worse == 3:
+                    break
+                last_loss = loss
             if max_iterations and len(logs) >= max_iterations:
                 break
         return logs
+
+    def test_from_images(self, batches: Iterable, multiplier: Optional[int] = None, out_path: Optional[str] = None):
+        """train.py:297-335 on pixels: the annotations of every test batch come from the conv front-ends, then ``test``."""
+        f = self._front()
+        dev = self.trainer.eng.device
+
+        def annotated():
+            for images, labels in batches:
+                ag, ad = f.annotations(images.to(device=dev, dtype=torch.float32))
+                yield ag, ad, labels
+        return self.test(annotated(), multiplier, out_path)
 
     @staticmethod
     def _recall(fake, real, N):

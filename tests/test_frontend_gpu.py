@@ -9,7 +9,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-TOL = 5e-3     # conv gradients are linear images of the annotation adjoint (itself within 1e-3); fp32 convolutions on the GPU side
+TOL = 1e-3     # conv gradients are linear images of the annotation adjoint (itself within 1e-3); measured 2e-5
 
 
 def _rel(a, b):
@@ -110,3 +110,36 @@ def test_train_from_images_runs_the_reference_loop_on_pixels(tmp_path):
     for a, b in zip(f.adam_fd.m + f.adam_fd.v, again.front.adam_fd.m + again.front.adam_fd.v):
         assert torch.equal(a, b)
     gan.trainer.close(); again.trainer.close()
+
+
+def test_training_from_a_dataset_directory_in_the_reference_formats(tmp_path):
+    """vocab.json / ims_to_triples.json / image_means.txt / image_stds.txt / JPEG files (dataset_creation/*.py) ->
+    SceneGraphGAN.train() -> R@k evaluation on the test split: the reference's own mode of operation (train.py:341-395)."""
+    import random
+
+    import numpy as np
+    from PIL import Image
+
+    from sgg_b200.train import SceneGraphGAN
+    rng, nrng = random.Random(0), np.random.RandomState(0)
+    vocab = {f"w{i}": i for i in range(30)}
+    ims = {}
+    for i in range(20):
+        p = str(tmp_path / f"{i}.jpg")
+        Image.fromarray(nrng.randint(0, 256, size=(48, 64, 3), dtype=np.uint8)).save(p)
+        ims[p] = [[rng.randrange(30) for _ in range(3)] for _ in range(2 + i % 3)]
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "ims.json").write_text(json.dumps(ims))
+    (tmp_path / "means.txt").write_text("119.6\n115.1\n106.1\n")
+    (tmp_path / "stds.txt").write_text("30.4\n30.5\n36.7\n")
+    np.save(str(tmp_path / "emb.npy"), nrng.uniform(-0.1, 0.1, size=(30, 300)))
+    gan = SceneGraphGAN(str(tmp_path / "ck"), str(tmp_path / "logs"), str(tmp_path / "ims.json"), str(tmp_path / "vocab.json"),
+                        str(tmp_path / "emb.npy"), str(tmp_path / "means.txt"), str(tmp_path / "stds.txt"), critic_iters=1,
+                        batch_size=2, lambda_=10, resume=False, allow_synthetic=False)
+    assert gan.trainer.V == 30
+    n = gan.train(max_iterations=2)
+    assert n == 2 and gan.front is not None and gan.front.adam_fd.t == 2
+    r50, r100 = gan.test_from_images(list(gan.dataset["test"])[:2], multiplier=2, out_path=str(tmp_path / "recalls.txt"))
+    assert 0.0 <= r50 <= 1.0 and 0.0 <= r100 <= 1.0
+    assert (tmp_path / "recalls.txt").read_text().count("\n") == 1
+    gan.trainer.close()
