@@ -125,3 +125,30 @@ def test_annotation_adjoint_is_the_seam_between_front_end_and_hot_path():
     e2e = torch.autograd.grad(losses["gen_cost"], list(fg.live_parameters()))
     for a, b in zip(seam, e2e):
         assert (a - b).norm() <= 1e-9 * b.norm() + 1e-14
+
+
+def test_conv_variables_travel_through_a_tensorflow_checkpoint(tmp_path):
+    """A checkpoint in the TensorFlow V2 format with the reference graph's conv variables (HWIO kernels, their Adam slots,
+    the hot-path variables next to them): the reader hands the conv variables to ConvFrontEnd under their TF names."""
+    import numpy as np
+
+    from sgg_b200 import tf_checkpoint as T
+    src = _randomised("Generator/Generator", 21).float()
+    tensors = {k: v.contiguous().numpy() for k, v in src.tf_variables().items()}
+    tensors.update({k + "/Adam": np.zeros_like(v) for k, v in list(tensors.items())[:4]})
+    tensors["Generator/Generator/decoder/bias"] = np.arange(7, dtype=np.float32)
+    tensors["beta1_power"] = np.float32(0.5 ** 3)
+    T.write_checkpoint(str(tmp_path / "model.ckpt"), tensors)
+    parts = T.split_for_buckets(T.read_checkpoint(str(tmp_path / "model.ckpt")))
+    assert parts["step"]["beta1_power"] == 3 and "Generator/Generator/decoder/bias" in parts["generator"]
+    conv = {k: torch.from_numpy(v) for k, v in parts["other"].items()}
+    assert "Generator/Generator/conv2d_13/kernel" in conv and conv["Generator/Generator/conv2d_13/kernel"].shape == (5, 5, 512, 512)
+    dst = ConvFrontEnd("Generator/Generator", seed=0)
+    used = dst.load_tf_variables(conv)
+    assert len(used) == 54
+    for a, b in zip(src.parameters(), dst.parameters()):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        dst.load_tf_variables({"Generator/Generator/conv2d/kernel": torch.zeros(3, 3, 3, 31)}, strict=False)
+    with pytest.raises(KeyError):
+        dst.load_tf_variables({})
