@@ -302,6 +302,21 @@ typedef struct sgg_iter_args {
 
 int sgg_train_iteration(const sgg_iter_args_t* it, sgg_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------
+ * Caller-side front-end helper (gen:29-68): tf.contrib.layers.layer_norm(activation_fn=tf.nn.elu) as used after every
+ * convolution of the stack (gen:30,32,36,...): x [B, H*W, C] fp32 (NHWC), moments over all H*W*C elements of a sample
+ * (biased variance, eps inside the rsqrt), gamma / beta [C], y = elu(gamma * (x - mean) * rstd + beta).  C must divide
+ * 1024 and be a multiple of 4.  stats [B, 2] receives (mean, rstd) for the reverse pass, which recomputes the
+ * pre-activation from x (x is the only tensor to keep) and returns dx, dgamma, dbeta (overwritten).
+ * scratch: sgg_ln_elu_scratch_floats(B, HW, C) floats, contents private.  HBM-bound: 3 (forward) / 5 (reverse) passes.
+ * -------------------------------------------------------------------------------------- */
+int64_t sgg_ln_elu_scratch_floats(int64_t B, int64_t HW, int32_t C);
+int sgg_ln_elu_forward(const float* x, const float* gamma, const float* beta, int64_t B, int64_t HW, int32_t C, float eps,
+                       float* y, float* stats, float* scratch, sgg_stream_t stream);
+int sgg_ln_elu_backward(const float* x, const float* dy, const float* gamma, const float* beta, const float* stats,
+                        int64_t B, int64_t HW, int32_t C, float* dx, float* dgamma, float* dbeta, float* scratch,
+                        sgg_stream_t stream);
+
 /* Test/debug accessor: byte offset of a named intermediate buffer inside the workspace. */
 int sgg_ws_lookup(const sgg_dims_t* d, const char* name, int64_t* offset_bytes, int64_t* elem_bytes);
 

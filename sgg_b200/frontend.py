@@ -1,7 +1,8 @@
 """The caller-side producer of the annotations: the convolutional front-end of gen:29-68 / disc:29-68.
 
-NOT part of the B200 hot path and NOT hand-written kernels: the convolutions, the layer norms and their backward pass
-are PyTorch library calls (cuDNN on the GPU).  What this module adds to the hot path is the seam: ``annotations =
+NOT part of the B200 hot path.  The convolutions and their backward pass are PyTorch library calls (cuDNN on the GPU); the
+HBM-bound half of the stack -- the H*W*C layer norm with its ELU, forward and reverse -- runs on this repo's kernels
+(``csrc/frontend.cu``, ``sgg_ln_elu_forward`` / ``sgg_ln_elu_backward``) for fp32 CUDA tensors.  What this module adds to the hot path is the seam: ``annotations =
 front_end(images)`` feeds ``Engine.set_batch``, and the annotation adjoint the step functions return
 (``sgg_step_args_t.ann_g_grad`` / ``ann_d_grad``: d gen_cost / d ann_g, d disc_cost / d ann_d incl. the gradient
 penalty's second-order path) is back-propagated through the stack with ``annotations.backward(adjoint)``, so that the
@@ -69,12 +70,69 @@ def he_normal_(w: torch.Tensor, generator: Optional[torch.Generator] = None) -> 
         return torch.nn.init.trunc_normal_(w, 0.0, std, -2 * std, 2 * std, generator=generator)
 
 
+class _LayerNormELU(torch.autograd.Function):
+    """tf.contrib.layers.layer_norm(activation_fn=tf.nn.elu) on a channels-last fp32 CUDA tensor through the C ABI
+    (csrc/frontend.cu): two passes forward, two passes reverse, x is the only saved activation."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        import ctypes as C
+
+        from ._lib import check, lib, stream_ptr
+        B, Cc, H, W = x.shape
+        xs = x.contiguous(memory_format=torch.channels_last)          # storage order [B, H, W, C]
+        y = torch.empty_like(xs, memory_format=torch.channels_last)
+        stats = torch.empty(B, 2, dtype=torch.float32, device=x.device)
+        L = lib()
+        L.sgg_ln_elu_scratch_floats.restype = C.c_int64
+        n_scr = L.sgg_ln_elu_scratch_floats(C.c_int64(B), C.c_int64(H * W), C.c_int32(Cc))
+        if n_scr < 0:
+            raise RuntimeError("sgg_ln_elu_scratch_floats: " + L.sgg_last_error().decode())
+        scratch = torch.empty(n_scr, dtype=torch.float32, device=x.device)
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        check(L.sgg_ln_elu_forward(C.c_void_p(xs.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(b.data_ptr()), C.c_int64(B),
+                                   C.c_int64(H * W), C.c_int32(Cc), C.c_float(LN_EPS), C.c_void_p(y.data_ptr()),
+                                   C.c_void_p(stats.data_ptr()), C.c_void_p(scratch.data_ptr()), stream_ptr()), "sgg_ln_elu_forward")
+        ctx.save_for_backward(xs, g, b, stats)
+        ctx.n_scr = n_scr
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes as C
+
+        from ._lib import check, lib, stream_ptr
+        xs, g, b, stats = ctx.saved_tensors
+        B, Cc, H, W = xs.shape
+        dys = dy.float().contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(xs, memory_format=torch.channels_last)
+        dg, db = torch.empty_like(g), torch.empty_like(b)
+        scratch = torch.empty(ctx.n_scr, dtype=torch.float32, device=xs.device)
+        check(lib().sgg_ln_elu_backward(C.c_void_p(xs.data_ptr()), C.c_void_p(dys.data_ptr()), C.c_void_p(g.data_ptr()),
+                                        C.c_void_p(b.data_ptr()), C.c_void_p(stats.data_ptr()), C.c_int64(B), C.c_int64(H * W),
+                                        C.c_int32(Cc), C.c_void_p(dx.data_ptr()), C.c_void_p(dg.data_ptr()), C.c_void_p(db.data_ptr()),
+                                        C.c_void_p(scratch.data_ptr()), stream_ptr()), "sgg_ln_elu_backward")
+        return dx, dg, db
+
+
+def layer_norm_elu(y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, fused: Optional[bool] = None) -> torch.Tensor:
+    """gen:30 on an NCHW-shaped tensor: moments over (C, H, W) per sample, per-channel gamma / beta, ELU.  fp32 CUDA tensors go
+    through this repo's kernels; anything else (CPU tensors of the tests, autocast dtypes) through torch's group_norm + elu,
+    which compute the same function."""
+    if fused is None:
+        fused = y.is_cuda and y.dtype == torch.float32 and gamma.dtype == torch.float32
+    if fused:
+        return _LayerNormELU.apply(y, gamma, beta)
+    return F.elu(F.group_norm(y, 1, gamma.to(y.dtype), beta.to(y.dtype), LN_EPS))
+
+
 class ConvFrontEnd(torch.nn.Module):
     """images [B, H, W, 3] (NHWC, standardised as in train:170) -> self.downsampled [B, h, w, 512] (gen:29-68)."""
 
     def __init__(self, scope: str = "Generator/Generator", seed: Optional[int] = None):
         super().__init__()
         self.scope = scope
+        self.fused_norm: Optional[bool] = None      # None: this repo's kernels for fp32 CUDA tensors; False: torch ops
         g = torch.Generator().manual_seed(seed) if seed is not None else None
         self.kernels = torch.nn.ParameterList()
         self.biases = torch.nn.ParameterList()
@@ -109,8 +167,7 @@ class ConvFrontEnd(torch.nn.Module):
                 y = F.conv2d(F.pad(h, (pl, pr, pt, pb)), self.kernels[i].to(h.dtype), self.biases[i].to(h.dtype), stride=stride)
             if norm:
                 j = self._norm_index(i)
-                # one group = moments over (C, H, W) per sample; per-channel gamma / beta
-                y = F.elu(F.group_norm(y, 1, self.gammas[j].to(y.dtype), self.betas[j].to(y.dtype), LN_EPS))
+                y = layer_norm_elu(y, self.gammas[j], self.betas[j], self.fused_norm)
             outs[i] = y
         return outs[len(_LAYERS) - 1].permute(0, 2, 3, 1)    # NHWC [B, h, w, 512]
 

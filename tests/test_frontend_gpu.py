@@ -144,3 +144,54 @@ def test_training_from_a_dataset_directory_in_the_reference_formats(tmp_path):
     assert 0.0 <= r50 <= 1.0 and 0.0 <= r100 <= 1.0
     assert (tmp_path / "recalls.txt").read_text().count("\n") == 1
     gan.trainer.close()
+
+
+@pytest.mark.parametrize("B,C,H,W", [(3, 32, 37, 41), (2, 512, 5, 7), (1, 4, 3, 3), (2, 64, 111, 111), (5, 128, 1, 1)])
+def test_fused_layer_norm_elu_kernels(B, C, H, W):
+    """sgg_ln_elu_forward / _backward (csrc/frontend.cu) against torch's group_norm + elu in fp64 and against the numpy
+    restatement of tf.contrib.layers.layer_norm(activation_fn=elu) (gen:30): several chunks per sample, ragged tails,
+    a single-pixel sample (variance of C values only), non-trivial gamma / beta, a mean far from zero."""
+    import numpy as np
+
+    from oracle import frontend_oracle as FO
+    from sgg_b200._lib import kernel_counts
+    from sgg_b200.frontend import layer_norm_elu
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.7 + 3.0).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    beta = (0.3 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    dy = torch.randn(B, C, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    k0 = kernel_counts()
+    y = layer_norm_elu(x, gamma, beta)
+    gx, gg, gb = torch.autograd.grad(y, (x, gamma, beta), grad_outputs=dy)
+    torch.cuda.synchronize()
+    k1 = kernel_counts()
+    for name in ("ln_elu_stats_kernel", "ln_elu_apply_kernel", "ln_elu_bwd_reduce_kernel", "ln_elu_bwd_apply_kernel"):
+        assert k1.get(name, 0) - k0.get(name, 0) == 1, (name, k1)
+    x64, g64, b64 = (t.detach().cpu().double().requires_grad_(True) for t in (x, gamma, beta))
+    y64 = torch.nn.functional.elu(torch.nn.functional.group_norm(x64, 1, g64, b64, 1e-12))
+    r = torch.autograd.grad(y64, (x64, g64, b64), grad_outputs=dy.cpu().double())
+    assert _rel(y, y64) < 2e-6
+    assert _rel(gx, r[0]) < 2e-5 and _rel(gg, r[1]) < 2e-5 and _rel(gb, r[2]) < 2e-5
+    ref = FO.layer_norm_elu(x64.detach().permute(0, 2, 3, 1).numpy(), g64.detach().numpy(), b64.detach().numpy())
+    assert np.abs(y.detach().permute(0, 2, 3, 1).cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_front_end_with_fused_norms_equals_the_library_norms():
+    from sgg_b200.frontend import ConvFrontEnd
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = ConvFrontEnd(seed=4).cuda()
+        images = torch.randn(2, 45, 61, 3, generator=torch.Generator().manual_seed(2)).cuda()
+        outs, grads = [], []
+        for fused in (None, False):
+            net.fused_norm = fused
+            a = net(images)
+            outs.append(a.detach())
+            grads.append(torch.autograd.grad(a.square().sum(), list(net.live_parameters())))
+        assert _rel(outs[0], outs[1]) < 1e-5
+        for a, b in zip(*grads):
+            assert _rel(a, b) < 1e-4
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

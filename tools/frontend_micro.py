@@ -3,8 +3,10 @@
 profiler):
   (a) sgg_disc_step / sgg_gen_step at config 2's shape (B 256) without and with ann_d_grad / ann_g_grad, eager launches,
       rotating annotation tensors (> L2), and the kernels the adjoint adds (by name, from sgg_kernel_counts);
-  (b) SceneGraphGAN.train_from_images (library convolutions around the step-level C ABI) at B = $FE_BATCH (default 64)
-      with fp32 and with bf16-autocast convolutions.
+  (b) the fused H*W*C layer norm + ELU kernels (csrc/frontend.cu) against torch's group_norm + elu at three of the stack's
+      activation shapes, with the fraction of the HBM peak on the algorithmic 3 / 5 passes;
+  (c) SceneGraphGAN.train_from_images (library convolutions around the step-level C ABI) at B = $FE_BATCH (default 64)
+      with this repo's norm kernels, with torch's, and with bf16-autocast convolutions.
 Writes gpurun_out/<TAG>_frontend_micro.json."""
 import json
 import os
@@ -59,14 +61,45 @@ def main():
     out["adjoint_bytes"] = {"output_fp32": B * R * 512 * 4, "W_a_shadow_hi_lo": 2 * R * 512 * 256 * 2}
     del eng, anns
     torch.cuda.empty_cache()
-    # ---- (b) the loop on pixels
+    # ---- (b) the H*W*C layer norm + ELU of gen:30: this repo's kernels against torch's group_norm + elu, forward + reverse
+    from sgg_b200.frontend import layer_norm_elu
+    peak = 6489.0
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f).get("hbm_gbs", peak))
+    except Exception:
+        pass
+    out["layer_norm_elu"] = {"peak_GBps": peak}
+    for shape in ((64, 32, 221, 221), (64, 128, 111, 111), (64, 256, 56, 56)):
+        x = torch.randn(*shape, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        gam = torch.ones(shape[1], device="cuda", requires_grad=True)
+        bet = torch.zeros(shape[1], device="cuda", requires_grad=True)
+        dy = torch.randn_like(x)
+        nbytes = x.numel() * 4
+        row = {"tensor_MB": nbytes / 1e6}
+        for name, fused in (("kernels", True), ("torch", False)):
+            fwd = timed(lambda: layer_norm_elu(x, gam, bet, fused), 10)
+            y = layer_norm_elu(x, gam, bet, fused)
+            bwd = timed(lambda: torch.autograd.grad(y, (x, gam, bet), grad_outputs=dy, retain_graph=True), 10)
+            row[name] = {"forward_ms": fwd, "reverse_ms": bwd}
+            if fused:   # algorithmic traffic: 3 (forward) / 5 (reverse) passes over the tensor
+                row[name]["forward_frac_of_hbm"] = 3 * nbytes / (fwd * 1e-3) / 1e9 / peak
+                row[name]["reverse_frac_of_hbm"] = 5 * nbytes / (bwd * 1e-3) / 1e9 / peak
+            del y
+        out["layer_norm_elu"]["x".join(map(str, shape))] = row
+        del x, dy
+        torch.cuda.empty_cache()
+    # ---- (c) the loop on pixels
     from sgg_b200.train import SceneGraphGAN
     Bf, nc = int(os.environ.get("FE_BATCH", "64")), 5
-    for name, dt in (("fp32_tf32_convs", torch.float32), ("bf16_autocast_convs", torch.bfloat16)):
+    for name, dt, fused in (("fp32_convs_fused_norms", torch.float32, None), ("fp32_convs_torch_norms", torch.float32, False),
+                            ("bf16_autocast_convs", torch.bfloat16, None)):
         with tempfile.TemporaryDirectory() as tmp:
             gan = SceneGraphGAN(tmp, tmp, None, None, None, None, None, critic_iters=nc, batch_size=Bf, lambda_=10, resume=False,
                                 vocab_size=V)
             gan._front().compute_dtype = dt
+            gan._front().fg.fused_norm = gan._front().fd.fused_norm = fused
+            torch.cuda.reset_peak_memory_stats()
             images = torch.randn(Bf, 221, 221, 3, device="cuda")
             lb = torch.randint(0, V, (Bf, 3), device="cuda")
             ms = timed(lambda: gan.train_from_images([(images, lb)]), 3, warm=1)
