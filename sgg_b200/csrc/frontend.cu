@@ -17,9 +17,17 @@ namespace sgg {
 
 constexpr int LE_THREADS = 256;
 constexpr int LE_STEP = LE_THREADS * 4;       // elements per CTA pass; a multiple of every channel count (C | 1024)
-constexpr long long LE_CHUNK = 16 * LE_STEP;  // elements per CTA
 
-static inline long long le_chunks(long long n) { return (n + LE_CHUNK - 1) / LE_CHUNK; }
+// Elements per CTA: a multiple of LE_STEP chosen so that the grid is about 8 CTAs per SM (a CTA's prologue -- the
+// combination of its sample's chunk partials -- is then small against its streaming time), between 4 and 64 passes.
+static inline long long le_chunk_elems(long long B, long long n) {
+  long long c = (B * n + 148 * 8 - 1) / (148 * 8);
+  c = (c + LE_STEP - 1) / LE_STEP * LE_STEP;
+  if (c < 4 * LE_STEP) c = 4 * LE_STEP;
+  if (c > 64 * LE_STEP) c = 64 * LE_STEP;
+  return c;
+}
+static inline long long le_chunks(long long B, long long n) { const long long c = le_chunk_elems(B, n); return (n + c - 1) / c; }
 
 struct LnEluParams {
   const float* x; const float* dy; const float* gamma; const float* beta;
@@ -29,6 +37,7 @@ struct LnEluParams {
   float* cpart;              // reverse: [B * chunks, 2, C] per-CTA dgamma / dbeta
   float* dgamma; float* dbeta;
   long long N;               // H * W * C elements per sample
+  long long chunk;           // elements per CTA (multiple of LE_STEP)
   int C, chunks;
   float eps;
 };
@@ -51,7 +60,7 @@ __global__ void __launch_bounds__(LE_THREADS) ln_elu_stats_kernel(const LnEluPar
   pdl_wait();
   __shared__ float red[LE_THREADS / 32];
   const int b = blockIdx.y, ch = blockIdx.x;
-  const long long e0 = (long long)ch * LE_CHUNK, e1 = min(p.N, e0 + LE_CHUNK);
+  const long long e0 = (long long)ch * p.chunk, e1 = min(p.N, e0 + p.chunk);
   const float* xs = p.x + (long long)b * p.N;
   const float shift = xs[e0];                 // sums about a value of the chunk: no cancellation in M2
   float s = 0.f, q = 0.f;
@@ -71,37 +80,36 @@ __global__ void __launch_bounds__(LE_THREADS) ln_elu_stats_kernel(const LnEluPar
   }
 }
 
-// (mean, rstd) of sample b from its chunk partials (Chan et al.), in double, by one thread; broadcast through shared memory
-__device__ __forceinline__ void ln_elu_combine(const LnEluParams& p, int b, float* sh, float& mean, float& rstd) {
-  if (threadIdx.x == 0) {
-    double n = 0.0, m = 0.0, M2 = 0.0;
-    const float* q = p.part + (long long)b * p.chunks * 3;
-    for (int i = 0; i < p.chunks; ++i) {
-      const double nb = q[3 * i], mb = q[3 * i + 1], Mb = q[3 * i + 2];
-      const double d = mb - m, nn = n + nb;
-      m += d * nb / nn;
-      M2 += Mb + d * d * n * nb / nn;
-      n = nn;
-    }
-    sh[0] = (float)m;
-    sh[1] = (float)(1.0 / sqrt(M2 / n + (double)p.eps));
+// (mean, rstd) of sample b from its chunk partials: n = sum n_i, mean = sum n_i m_i / n, M2 = sum (M2_i + n_i (m_i - mean)^2)
+// (Chan et al., all chunks at once), the chunks spread over the threads
+__device__ __forceinline__ void ln_elu_combine(const LnEluParams& p, int b, float* red, float& mean, float& rstd) {
+  const float* q = p.part + (long long)b * p.chunks * 3;
+  float n = 0.f, nm = 0.f;
+  for (int i = threadIdx.x; i < p.chunks; i += LE_THREADS) { n += q[3 * i]; nm = fmaf(q[3 * i], q[3 * i + 1], nm); }
+  n = block_sum_256(n, red);
+  nm = block_sum_256(nm, red);
+  mean = nm / n;
+  float m2 = 0.f;
+  for (int i = threadIdx.x; i < p.chunks; i += LE_THREADS) {
+    const float d = q[3 * i + 1] - mean;
+    m2 += q[3 * i + 2] + q[3 * i] * d * d;
   }
-  __syncthreads();
-  mean = sh[0]; rstd = sh[1];
+  m2 = block_sum_256(m2, red);
+  rstd = rsqrtf(m2 / n + p.eps);
 }
 
 __global__ void __launch_bounds__(LE_THREADS) ln_elu_apply_kernel(const LnEluParams p) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float sh[2];
+  __shared__ float red[LE_THREADS / 32];
   const int b = blockIdx.y, ch = blockIdx.x;
   float mean, rstd;
-  ln_elu_combine(p, b, sh, mean, rstd);
+  ln_elu_combine(p, b, red, mean, rstd);
   if (ch == 0 && threadIdx.x == 0) { p.stats[2 * b] = mean; p.stats[2 * b + 1] = rstd; }
-  const long long e0 = (long long)ch * LE_CHUNK, e1 = min(p.N, e0 + LE_CHUNK);
+  const long long e0 = (long long)ch * p.chunk, e1 = min(p.N, e0 + p.chunk);
   const float* xs = p.x + (long long)b * p.N;
   float* ys = p.y + (long long)b * p.N;
-  const int c0 = (threadIdx.x * 4) % p.C;     // LE_STEP and LE_CHUNK are multiples of C: the channel group never changes
+  const int c0 = (threadIdx.x * 4) % p.C;     // LE_STEP and the chunk size are multiples of C: the channel group never changes
   const float4 g = *reinterpret_cast<const float4*>(p.gamma + c0), be = *reinterpret_cast<const float4*>(p.beta + c0);
 #pragma unroll 4
   for (long long e = e0 + threadIdx.x * 4; e < e1; e += LE_STEP) {
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(LE_THREADS) ln_elu_bwd_reduce_kernel(const LnE
   const int b = blockIdx.y, ch = blockIdx.x;
   for (int c = threadIdx.x; c < p.C; c += LE_THREADS) { cg[c] = 0.f; cb[c] = 0.f; }
   const float mean = p.stats[2 * b], rstd = p.stats[2 * b + 1];
-  const long long e0 = (long long)ch * LE_CHUNK, e1 = min(p.N, e0 + LE_CHUNK);
+  const long long e0 = (long long)ch * p.chunk, e1 = min(p.N, e0 + p.chunk);
   const float* xs = p.x + (long long)b * p.N;
   const float* ds = p.dy + (long long)b * p.N;
   const int c0 = (threadIdx.x * 4) % p.C;
@@ -174,16 +182,15 @@ __global__ void __launch_bounds__(LE_THREADS) ln_elu_bwd_apply_kernel(const LnEl
     return;
   }
   if (ch >= p.chunks) return;
-  __shared__ float sh[2];
-  if (threadIdx.x == 0) {
-    double t1 = 0.0, t2 = 0.0;
-    for (int i = 0; i < p.chunks; ++i) { t1 += p.part[2 * ((long long)b * p.chunks + i)]; t2 += p.part[2 * ((long long)b * p.chunks + i) + 1]; }
-    sh[0] = (float)(t1 / (double)p.N); sh[1] = (float)(t2 / (double)p.N);
+  __shared__ float red[LE_THREADS / 32];
+  float t1 = 0.f, t2 = 0.f;
+  for (int i = threadIdx.x; i < p.chunks; i += LE_THREADS) {
+    t1 += p.part[2 * ((long long)b * p.chunks + i)];
+    t2 += p.part[2 * ((long long)b * p.chunks + i) + 1];
   }
-  __syncthreads();
-  const float m1 = sh[0], m2 = sh[1];
+  const float m1 = block_sum_256(t1, red) / (float)p.N, m2 = block_sum_256(t2, red) / (float)p.N;
   const float mean = p.stats[2 * b], rstd = p.stats[2 * b + 1];
-  const long long e0 = (long long)ch * LE_CHUNK, e1 = min(p.N, e0 + LE_CHUNK);
+  const long long e0 = (long long)ch * p.chunk, e1 = min(p.N, e0 + p.chunk);
   const float* xs = p.x + (long long)b * p.N;
   const float* ds = p.dy + (long long)b * p.N;
   float* os = p.dx + (long long)b * p.N;
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(LE_THREADS) ln_elu_bwd_apply_kernel(const LnEl
 static int le_check(int64_t B, int64_t HW, int32_t C, const char* who) {
   SGG_CHECK(B >= 1 && HW >= 1 && C >= 4 && C <= 512 && (LE_STEP % C) == 0, "%s: needs 1 <= B, HW and C in {4, 8, ..., 512} dividing 1024 (got B=%lld HW=%lld C=%d)",
             who, (long long)B, (long long)HW, C);
-  SGG_CHECK(le_chunks(HW * C) <= 65535 && B <= 65535, "%s: sample too large for one launch", who);
+  SGG_CHECK(le_chunks(B, HW * C) <= 65535 && B <= 65535, "%s: sample too large for one launch", who);
   return 0;
 }
 
@@ -220,7 +227,7 @@ using namespace sgg;
 
 extern "C" int64_t sgg_ln_elu_scratch_floats(int64_t B, int64_t HW, int32_t C) {
   if (le_check(B, HW, C, "sgg_ln_elu_scratch_floats") != 0) return -1;
-  const long long ctas = B * le_chunks(HW * C);
+  const long long ctas = B * le_chunks(B, HW * C);
   return ctas * 3 + ctas * 2 * C;
 }
 
@@ -230,7 +237,7 @@ extern "C" int sgg_ln_elu_forward(const float* x, const float* gamma, const floa
   SGG_TRY(le_check(B, HW, C, "sgg_ln_elu_forward"));
   LnEluParams p{};
   p.x = x; p.gamma = gamma; p.beta = beta; p.y = y; p.stats = stats; p.part = scratch;
-  p.N = HW * C; p.C = C; p.chunks = (int)le_chunks(p.N); p.eps = eps;
+  p.N = HW * C; p.C = C; p.chunk = le_chunk_elems(B, p.N); p.chunks = (int)le_chunks(B, p.N); p.eps = eps;
   const dim3 grid(p.chunks, (unsigned)B);
   SGG_LAUNCH(ln_elu_stats_kernel, grid, LE_THREADS, 0, (cudaStream_t)stream, p);
   SGG_LAUNCH(ln_elu_apply_kernel, grid, LE_THREADS, 0, (cudaStream_t)stream, p);
@@ -245,7 +252,7 @@ extern "C" int sgg_ln_elu_backward(const float* x, const float* dy, const float*
   LnEluParams p{};
   p.x = x; p.dy = dy; p.gamma = gamma; p.beta = beta; p.dx = dx; p.dgamma = dgamma; p.dbeta = dbeta;
   p.stats = const_cast<float*>(stats);
-  p.N = HW * C; p.C = C; p.chunks = (int)le_chunks(p.N);
+  p.N = HW * C; p.C = C; p.chunk = le_chunk_elems(B, p.N); p.chunks = (int)le_chunks(B, p.N);
   const long long ctas = B * p.chunks;
   p.part = scratch; p.cpart = scratch + ctas * 3;
   SGG_LAUNCH(ln_elu_bwd_reduce_kernel, dim3(p.chunks, (unsigned)B), LE_THREADS, 0, (cudaStream_t)stream, p);
