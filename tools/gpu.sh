@@ -10,7 +10,7 @@
 #   dist:N          tests/dist/check_sharded.py under torchrun with N ranks; extra flags from $DIST_FLAGS
 #   launches        ncu launch list (gpu__time_duration) of tools/profile_iter.py
 #   launches_bench  ncu launch list of the bench command itself
-#   full:<regex>    ncu --set full capture of kernels matching <regex> in tools/profile_iter.py (-c $NCU_COUNT, default 6)
+#   full:<regex>    ncu --set full capture of kernels matching <regex> in $NCU_SCRIPT (default tools/profile_iter.py; -c $NCU_COUNT, default 6)
 #   events          tools/profile_events.py (SGG_TIMING=1 per-launch CUDA-event timing)
 #   py:<file>       python <file> (stdout/stderr to gpurun_out)
 # TAG (env, default r2) prefixes the output files.
@@ -47,7 +47,7 @@ for stage in "$@"; do
       timeout 900 $NCU --metrics gpu__time_duration.sum -c 8000 --csv --log-file $out.csv \
         python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $out.log 2>&1; rc=$? ;;
     full)
-      timeout 900 $NCU --set full --import-source on ${NCU_EXTRA:-} -k "regex:$arg" -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-6} -o $out -f python tools/profile_iter.py > $out.log 2>&1; rc=$?
+      timeout 900 $NCU --set full --import-source on ${NCU_EXTRA:-} -k "regex:$arg" -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-6} -o $out -f python ${NCU_SCRIPT:-tools/profile_iter.py} > $out.log 2>&1; rc=$?
       [ -f $out.ncu-rep ] && ncu -i $out.ncu-rep --page raw --csv > $out.raw.csv 2>/dev/null ;;
     events)
       SGG_TIMING=1 SGG_PDL=0 timeout 600 python tools/profile_events.py > $out.md 2> $out.err; rc=$? ;;
