@@ -54,6 +54,14 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return s;
 }
 
+// expm1(z) for z <= 0 without libdevice's branches (the apply kernel issued 67 % of its cycles with expm1f): the degree-6
+// Taylor polynomial down to -0.25 (truncation 5e-8 relative), exp(z) - 1 from one MUFU.EX2 below (no cancellation there)
+__device__ __forceinline__ float expm1_neg(float z) {
+  const float p = z * (1.f + z * (0.5f + z * (1.f / 6.f + z * (1.f / 24.f + z * (1.f / 120.f + z * (1.f / 720.f))))));
+  const float e = fast_exp(z) - 1.f;
+  return z > -0.25f ? p : e;
+}
+
 // ------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(LE_THREADS) ln_elu_stats_kernel(const LnEluParams p) {
   pdl_trigger();
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(LE_THREADS) ln_elu_apply_kernel(const LnEluPar
     float z[4] = {fmaf((v.x - mean) * rstd, g.x, be.x), fmaf((v.y - mean) * rstd, g.y, be.y),
                   fmaf((v.z - mean) * rstd, g.z, be.z), fmaf((v.w - mean) * rstd, g.w, be.w)};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) z[j] = z[j] > 0.f ? z[j] : expm1f(z[j]);
+    for (int j = 0; j < 4; ++j) z[j] = z[j] > 0.f ? z[j] : expm1_neg(z[j]);
     *reinterpret_cast<float4*>(ys + e) = make_float4(z[0], z[1], z[2], z[3]);
   }
 }
