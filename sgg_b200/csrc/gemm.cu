@@ -446,6 +446,8 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
   return launch_gemm<BN, true, false>(tmA, tmB, kp, splits, stream);
 }
 
+constexpr int GEMM_MAX_CHAIN_KB = 128;   // longest accumulation chain (64-wide k-blocks) of an automatically split GEMM
+
 // One fused launch: parts (nA, nB) as described at GemmKParams.
 static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t stream) {
   // ---- tile width and split-K.  These GEMMs are small (M = a few hundred rows) and long in K, so a plain tile grid
@@ -506,6 +508,12 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
     bn = best_bn;
     splits = best_sp;
   }
+  // The tcgen05 fp32 accumulator truncates: over one accumulator's chain the error is a bias that grows linearly with its
+  // length (measured, tools/accum_micro.py: 1.2e-9 per contraction index on signed data, 6e-9 on same-sign data -- 1.5e-4 /
+  // 8e-4 at K = 128 k), while split-K partial sums are combined by IEEE fp32 reductions in L2.  Unless the caller fixed the
+  // split, no accumulator runs over more than GEMM_MAX_CHAIN_KB k-blocks (8 k contraction indices: <= 1e-5 per product).
+  if (d.splits <= 0 && can_split && (kp.total_kb + splits - 1) / splits > GEMM_MAX_CHAIN_KB)
+    splits = (kp.total_kb + GEMM_MAX_CHAIN_KB - 1) / GEMM_MAX_CHAIN_KB;
   if (splits > kp.total_kb) splits = kp.total_kb;
   SGG_CHECK(splits == 1 || can_split, "sgg_gemm: split-K needs the fp32 output only");
   SGG_CHECK(bn == 64 || bn == 128 || bn == 256, "sgg_gemm: block_n=%d unsupported", bn);
