@@ -23,7 +23,9 @@ torch.nn.functional.interpolate's convention).
 from __future__ import annotations
 
 import json
+import queue
 import random
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
@@ -131,17 +133,20 @@ class ImageBatches:
 
     train / val: repeat + shuffle buffer of 10 batches (train.py:175-177); test: file order, one pass (train.py:299).
     rank / world: rank r takes batches r, r + world, ... of the stream (the reference is single-process).
-    A short final batch of the one-pass mode is dropped (the engine's batch size is fixed)."""
+    A short final batch of the one-pass mode is dropped (the engine's batch size is fixed).
+    prefetch: batches decoded ahead by a background thread (``d.prefetch(...)``, train.py:188), so that JPEG decoding
+    overlaps the consumer's GPU work; 0 decodes in the consumer's thread."""
 
     def __init__(self, files: Sequence[str], labels: np.ndarray, batch_size: int, means: torch.Tensor, stds: torch.Tensor,
                  shuffle: bool = True, repeat: bool = True, seed: int = 0, rank: int = 0, world: int = 1, workers: int = 8,
-                 pin_memory: bool = False):
+                 pin_memory: bool = False, prefetch: int = 2):
         if len(files) != len(labels):
             raise ValueError("files / labels length mismatch")
         self.files, self.labels = list(files), np.asarray(labels, dtype=np.int64).reshape(-1, 3)
         self.B, self.means, self.stds = int(batch_size), means, stds
         self.shuffle, self.repeat, self.seed = shuffle, repeat, seed
         self.rank, self.world, self.workers, self.pin = rank, world, max(1, workers), pin_memory
+        self.prefetch = int(prefetch)
 
     def _index_stream(self) -> Iterator[int]:
         if self.shuffle:
@@ -154,6 +159,43 @@ class ImageBatches:
         return plain()
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        if self.prefetch <= 0:
+            yield from self._batches()
+            return
+        q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+        stop, end = threading.Event(), object()
+
+        def put(item) -> bool:
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def produce():
+            try:
+                for item in self._batches():
+                    if not put(item):
+                        return
+                put(end)
+            except BaseException as exc:          # decoding errors surface in the consumer
+                put(exc)
+
+        threading.Thread(target=produce, daemon=True).start()
+        try:
+            while True:
+                item = q.get()
+                if item is end:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()                            # the consumer stopped early: release the producer
+
+    def _batches(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         if len(self.files) == 0:
             return
         stream = self._index_stream()

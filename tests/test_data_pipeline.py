@@ -152,3 +152,35 @@ def test_load_dataset_wires_the_three_streams(tmp_path):
     assert len(test_batches) == 16 and all(lb.shape == (2, 3) for _, lb in test_batches)
     first_image_rows = [tuple(r) for _, lb in test_batches[:8] for r in lb.tolist()]
     assert set(first_image_rows) == set(map(tuple, ims[list(ims)[18]]))
+
+
+def test_prefetch_thread_keeps_order_stops_early_and_reports_errors(tmp_path):
+    import threading
+    import time
+
+    from PIL import Image
+    files, labels = [], []
+    for i in range(8):
+        p = str(tmp_path / f"{i}.jpg")
+        Image.fromarray(np.full((12, 12, 3), 20 * i, dtype=np.uint8)).save(p)
+        files.append(p); labels.append([i, i, i])
+    means, stds = torch.zeros(3), torch.ones(3)
+    direct = list(D.ImageBatches(files, np.array(labels), 2, means, stds, shuffle=True, repeat=False, seed=3, prefetch=0))
+    ahead = list(D.ImageBatches(files, np.array(labels), 2, means, stds, shuffle=True, repeat=False, seed=3, prefetch=3))
+    assert len(direct) == len(ahead) == 4
+    for (a, la), (b, lb) in zip(direct, ahead):
+        assert torch.equal(a, b) and torch.equal(la, lb)
+    # an endless stream abandoned after two batches: the producer thread goes away
+    before = threading.active_count()
+    it = iter(D.ImageBatches(files, np.array(labels), 2, means, stds, shuffle=True, repeat=True, prefetch=2))
+    next(it); next(it)
+    it.close()
+    deadline = time.time() + 5
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() <= before
+    # a missing file raises in the consumer, not silently in the background
+    bad = D.ImageBatches(files[:2] + [str(tmp_path / "missing.jpg"), files[3]], np.array(labels[:4]), 2, means, stds,
+                         shuffle=False, repeat=False, prefetch=2)
+    with pytest.raises(FileNotFoundError):
+        list(bad)
