@@ -177,8 +177,10 @@ class SceneGraphGAN(object):
                 ds = load_dataset(self.path_to_ims_to_triples, self.path_to_image_means, self.path_to_image_stds, tr.B,
                                   test_batch_multiplier=self.TEST_BATCH_MULTIPLIER, seed=self._seed, eval_batch_size=tr.B)
                 self.dataset = ds
-                return len(self.train_from_images(ds["train"], max_iterations or ds["max_iterations"], ds["val"],
-                                                  ds["validate_iterations"]))
+                logs = self.train_from_images(ds["train"], max_iterations or ds["max_iterations"], ds["val"],
+                                              ds["validate_iterations"])
+                self.last_image_log = logs[-1] if logs else None
+                return len(logs)
             batches = synthetic_batches(tr.B, tr.T, tr.V, tr.R, max_iterations or 100, seed=1234 + tr.rank)
         log_path = os.path.join(self.summaries_dir, "train_log.jsonl") if (self.summaries_dir and tr.rank == 0) else None
         t0, n = time.time(), 0
@@ -336,7 +338,11 @@ def main(argv=None):
         gan.allow_synthetic = True
     n = gan.train(max_iterations=a.iterations)
     gan._saveModel()                                                   # collective; rank 0 writes
-    if gan.trainer.rank == 0:
+    image_log = getattr(gan, "last_image_log", None)      # set when the run went through the conv front-ends
+    if image_log is not None:
+        print(json.dumps({"iterations": n, "disc_cost": image_log["disc_cost"][-1] if image_log["disc_cost"] else None,
+                          "gen_cost": image_log["gen_cost"]}))
+    elif gan.trainer.rank == 0:
         print(json.dumps({"iterations": n, **gan.trainer.losses()}))
     else:
         gan.trainer.losses()
