@@ -152,3 +152,26 @@ def test_conv_variables_travel_through_a_tensorflow_checkpoint(tmp_path):
         dst.load_tf_variables({"Generator/Generator/conv2d/kernel": torch.zeros(3, 3, 3, 31)}, strict=False)
     with pytest.raises(KeyError):
         dst.load_tf_variables({})
+
+
+def test_golden_fixture_of_the_front_end():
+    """tests/golden/frontend_17x13.json (written by tests/golden/make_golden_frontend.py from the numpy restatement): the
+    restatement still produces it, and the torch module agrees with it."""
+    import json
+    import os
+
+    from tests.golden import make_golden_frontend as G
+    from tests.golden.make_golden import sample_index
+    with open(os.path.join(os.path.dirname(G.__file__), "frontend_17x13.json")) as f:
+        gold = json.load(f)
+    again = G.compute()
+    assert again["output_shape"] == gold["output_shape"] == [2, 2, 1, 512]
+    assert again["downsampled"]["norm"] == pytest.approx(gold["downsampled"]["norm"], rel=1e-12)
+    assert again["downsampled"]["samples"] == pytest.approx(gold["downsampled"]["samples"], rel=1e-10, abs=1e-12)
+    cfg = gold["config"]
+    net = _randomised(cfg["scope"], cfg["seed"])
+    images = torch.randn(*cfg["shape"], generator=torch.Generator().manual_seed(cfg["image_seed"]), dtype=torch.float64)
+    flat = net(images).detach().reshape(-1)
+    idx = torch.from_numpy(sample_index("downsampled", flat.numel()))
+    assert float(flat.norm()) == pytest.approx(gold["downsampled"]["norm"], rel=1e-9)
+    assert flat[idx].tolist() == pytest.approx(gold["downsampled"]["samples"], rel=1e-8, abs=1e-10)
