@@ -87,3 +87,33 @@ def test_checkpoint_round_trip_and_bucket_mapping(tmp_path):
     open(prefix + ".data-00000-of-00001", "wb").write(bytes(raw))
     with pytest.raises(ValueError):
         T.read_checkpoint(prefix)
+
+
+def test_round_trip_over_random_variable_sets(tmp_path):
+    """Property test (hypothesis): any set of variables with TF-style names, the four supported dtypes, 0 to 3 dimensions and
+    empty tensors survives write -> sorted string table with prefix-compressed keys across several blocks -> read."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    name = st.text(alphabet="abcdefgXYZ_/0123456789", min_size=1, max_size=40)
+    shape = st.lists(st.integers(0, 5), min_size=0, max_size=3)
+    dtype = st.sampled_from([np.float32, np.float64, np.int32, np.int64])
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.dictionaries(name, st.tuples(shape, dtype, st.integers(0, 2 ** 31 - 1)), min_size=1, max_size=90))
+    def run(spec):
+        counter[0] += 1
+        tensors = {}
+        for k, (shp, dt, seed) in spec.items():
+            a = np.random.default_rng(seed).standard_normal(shp) * 100
+            tensors[k] = np.asarray(a).astype(dt)
+        prefix = str(tmp_path / f"p{counter[0]}" / "model.ckpt")
+        T.write_checkpoint(prefix, tensors)
+        back = T.read_checkpoint(prefix)
+        assert sorted(back) == sorted(tensors)
+        for k, v in tensors.items():
+            assert back[k].dtype == v.dtype and back[k].shape == v.shape and np.array_equal(back[k], v), k
+        meta = T.list_variables(prefix)
+        assert all(meta[k]["shape"] == list(v.shape) for k, v in tensors.items())
+
+    run()
