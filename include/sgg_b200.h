@@ -104,6 +104,10 @@ typedef struct sgg_gemm_desc {
 } sgg_gemm_desc_t;
 
 int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream);
+/* Host-side query, launches nothing: the tile width and split-K sgg_gemm would choose for this descriptor, and the number
+ * of 64-wide k-blocks one accumulator then runs over.  Split-K is also the accuracy device of this library: the tcgen05
+ * fp32 accumulator truncates, so an automatically split contraction never keeps one accumulator for more than 128 k-blocks. */
+int sgg_gemm_plan(const sgg_gemm_desc_t* d, int32_t* block_n, int32_t* splits, int32_t* k_blocks_per_split);
 
 /* ----------------------------------------------------------------------------------------
  * Attention step (gen:16-17 / disc:16-17): for each of `nv` streams that share the annotation tile

@@ -143,5 +143,5 @@ EXPORTS = [
     "sgg_disc_forward", "sgg_disc_step", "sgg_gen_step", "sgg_ws_lookup", "sgg_train_iteration",
     "sgg_comm_unique_id", "sgg_comm_init", "sgg_comm_destroy", "sgg_comm_allreduce_sum",
     "sgg_sample_workspace_bytes", "sgg_gen_sample", "sgg_wa_shard_scratch_bytes", "sgg_wa_shard_slab_elems",
-    "sgg_ln_elu_scratch_floats", "sgg_ln_elu_forward", "sgg_ln_elu_backward",
+    "sgg_ln_elu_scratch_floats", "sgg_ln_elu_forward", "sgg_ln_elu_backward", "sgg_gemm_plan",
 ]

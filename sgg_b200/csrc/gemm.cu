@@ -448,6 +448,10 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
 
 constexpr int GEMM_MAX_CHAIN_KB = 128;   // longest accumulation chain (64-wide k-blocks) of an automatically split GEMM
 
+// sgg_gemm_plan: when set, gemm_fused reports its (tile width, split-K, m-tiles per CTA) choice here and launches nothing
+struct GemmPlan { int block_n, splits, m_tiles; };
+static thread_local GemmPlan* t_plan_out = nullptr;
+
 // One fused launch: parts (nA, nB) as described at GemmKParams.
 static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t stream) {
   // ---- tile width and split-K.  These GEMMs are small (M = a few hundred rows) and long in K, so a plain tile grid
@@ -517,6 +521,10 @@ static int gemm_fused(const sgg_gemm_desc_t& d, GemmKParams kp, cudaStream_t str
   if (splits > kp.total_kb) splits = kp.total_kb;
   SGG_CHECK(splits == 1 || can_split, "sgg_gemm: split-K needs the fp32 output only");
   SGG_CHECK(bn == 64 || bn == 128 || bn == 256, "sgg_gemm: block_n=%d unsupported", bn);
+  if (t_plan_out) {   // host-side query only
+    *t_plan_out = GemmPlan{bn, splits, mt};
+    return 0;
+  }
   if (d.atomic == 2) {             // the caller guarantees a zero-filled output: accumulate or overwrite, whichever fits
     kp.atomic = splits > 1 ? 1 : 0;
   } else if (splits > 1 && !d.atomic) {   // overwrite semantics: clear the output, then accumulate
@@ -593,6 +601,7 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
     return gemm_fused(d, kp, stream);
   }
   // ---- general segment lists: one accumulate-launch per segment
+  SGG_CHECK(t_plan_out == nullptr, "sgg_gemm_plan: this segment list runs as several launches, there is no single plan");
   SGG_CHECK(d.C && !d.Chl && d.out_d0 == 0 && !d.argmax_keys, "sgg_gemm: this segment pattern needs the plain fp32 output");
   if (!d.atomic) SGG_TRY(zero_2d(d.C, d.ldc, d.N, d.M, stream));
   for (int s = 0; s < d.nseg; ++s) {
@@ -611,6 +620,23 @@ int gemm(const sgg_gemm_desc_t& d, cudaStream_t stream) {
 }
 
 }  // namespace sgg
+
+extern "C" int sgg_gemm_plan(const sgg_gemm_desc_t* d, int32_t* block_n, int32_t* splits, int32_t* k_blocks_per_split) {
+  if (!d || !block_n || !splits || !k_blocks_per_split) {
+    sgg::set_error("sgg_gemm_plan: null argument");
+    return -1;
+  }
+  sgg::GemmPlan pl{0, 0, 0};
+  sgg::t_plan_out = &pl;
+  const int rc = sgg::gemm(*d, nullptr);
+  sgg::t_plan_out = nullptr;
+  if (rc != 0) return rc;
+  *block_n = pl.block_n;
+  *splits = pl.splits;
+  const int total_kb = (d->seg_klen[0] + 63) / 64;
+  *k_blocks_per_split = (total_kb + pl.splits - 1) / pl.splits;
+  return 0;
+}
 
 extern "C" int sgg_gemm(const sgg_gemm_desc_t* d, sgg_stream_t stream) {
   if (!d) {
